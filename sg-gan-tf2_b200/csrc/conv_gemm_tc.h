@@ -1,0 +1,36 @@
+// conv_gemm_tc.h -- host interface of the tcgen05 implicit-GEMM kernels (see conv_gemm_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "kparams.h"
+
+namespace sggan {
+
+// A prepared launch: parameters + TMA tensor maps (encoded once, reusable every step and
+// capturable in a CUDA graph).
+struct ConvGemmLaunch {
+  ConvGemmParams p;
+  CUtensorMap tmA, tmB;
+  int grid_x, grid_y, grid_z;
+  int stages;
+  unsigned tmem_cols;
+  size_t smem;
+};
+struct WgradLaunch {
+  WgradParams p;
+  CUtensorMap tmX, tmY;
+  int grid_x, grid_y, grid_z;
+  int stages;
+  unsigned tmem_cols;
+  size_t smem;
+};
+
+// All return 0 on success, a negative SGGAN error code otherwise.  Launches are asynchronous.
+int prepare_conv_gemm(const ConvGemmParams& p, ConvGemmLaunch* L);
+int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st);
+int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L);
+int run_wgrad_gemm(const WgradLaunch& L, cudaStream_t st);
+int read_tc_watchdog();
+
+}  // namespace sggan

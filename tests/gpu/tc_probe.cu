@@ -1,0 +1,430 @@
+// tc_probe.cu -- standalone B200 probe for the tcgen05 kernels (no Python, no torch).
+// Usage: tc_probe <test>   with test in {conv_small, conv_res, conv_out7, wgrad_small, wgrad_res,
+//                                         shift, tmap_overlap}
+// Each test checks the kernel against a CPU loop of its own specification (kparams.h) and,
+// for the *_res shapes, times it with CUDA events.  Exit code 0 = pass.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../sg-gan-tf2_b200/csrc/conv_gemm_tc.h"
+#include "../../sg-gan-tf2_b200/csrc/tc_common.cuh"
+#include "../../sg-gan-tf2_b200/csrc/tmap.h"
+
+using namespace sggan;
+
+#define CK(x)                                                                       \
+  do {                                                                              \
+    cudaError_t e_ = (x);                                                           \
+    if (e_ != cudaSuccess) {                                                        \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                      \
+    }                                                                               \
+  } while (0)
+
+static uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  uint32_t r = u + 0x7FFF + ((u >> 16) & 1);
+  return uint16_t(r >> 16);
+}
+static float bf2f(uint16_t h) {
+  uint32_t u = uint32_t(h) << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static uint32_t rng_state = 12345;
+static float frand() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return ((rng_state >> 8) & 0xFFFF) / 65536.0f - 0.5f;
+}
+
+struct ConvCase {
+  int B, H, W, Cin, Cout, CoutPad, BN, k;  // k x k taps, frame padded by k/2, pitch W + k - 1
+  int act, out_f32, use_stats;
+};
+
+static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
+  const int pad = c.k / 2, P = c.W + 2 * pad, rows = c.H + 2 * pad;
+  const int64_t frame_pix = int64_t(rows) * P + 8;
+  const int ntaps = c.k * c.k;
+  std::vector<uint16_t> hA(size_t(c.B) * frame_pix * c.Cin), hW(size_t(ntaps) * c.CoutPad * c.Cin, 0);
+  for (auto& v : hA) v = f2bf(frand());
+  for (int t = 0; t < ntaps; ++t)
+    for (int n = 0; n < c.Cout; ++n)
+      for (int ci = 0; ci < c.Cin; ++ci) hW[(size_t(t) * c.CoutPad + n) * c.Cin + ci] = f2bf(frand() * 0.1f);
+  std::vector<float> hbias(c.Cout);
+  for (auto& v : hbias) v = frand();
+
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  uint16_t *dA, *dW;
+  void* dOut;
+  float *dBias, *dStats;
+  const size_t out_elems = size_t(c.B) * c.H * c.W * c.Cout;
+  CK(cudaMalloc(&dA, hA.size() * 2));
+  CK(cudaMalloc(&dW, hW.size() * 2));
+  CK(cudaMalloc(&dOut, out_elems * (c.out_f32 ? 4 : 2)));
+  CK(cudaMalloc(&dBias, c.Cout * 4));
+  CK(cudaMalloc(&dStats, size_t(c.B) * c.Cout * 2 * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dBias, hbias.data(), c.Cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dOut, 0, out_elems * (c.out_f32 ? 4 : 2)));
+  CK(cudaMemset(dStats, 0, size_t(c.B) * c.Cout * 2 * 4));
+
+  p.A = dA;
+  p.a_frame_pix = frame_pix;
+  p.Cin = c.Cin;
+  p.B = c.B;
+  p.Wt = dW;
+  p.ntaps = ntaps;
+  p.CoutPad = c.CoutPad;
+  p.Cout = c.Cout;
+  p.BN = c.BN;
+  for (int kh = 0; kh < c.k; ++kh)
+    for (int kw = 0; kw < c.k; ++kw) p.tap_off[kh * c.k + kw] = kh * P + kw;
+  p.M = c.H * P;
+  p.P = P;
+  p.Hv = c.H;
+  p.Wv = c.W;
+  p.out = dOut;
+  p.out_f32 = c.out_f32;
+  p.out_bstride = int64_t(c.H) * c.W * c.Cout;
+  p.out_sy = int64_t(c.W) * c.Cout;
+  p.out_sx = c.Cout;
+  p.out_off = 0;
+  p.bias = dBias;
+  p.stats = c.use_stats ? dStats : nullptr;
+  p.act = c.act;
+  p.act_alpha = 0.3f;
+
+  ConvGemmLaunch L;
+  int r = prepare_conv_gemm(p, &L);
+  if (r) {
+    printf("prepare_conv_gemm failed %d\n", r);
+    return 1;
+  }
+  printf("grid %d x %d x %d, stages %d, smem %zu, tmem cols %u\n", L.grid_x, L.grid_y, L.grid_z, L.stages, L.smem,
+         L.tmem_cols);
+  r = run_conv_gemm(L, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (r || e != cudaSuccess) {
+    printf("launch/sync failed r=%d err=%s watchdog=%d\n", r, cudaGetErrorString(e), 0);
+    return 1;
+  }
+  std::vector<uint8_t> hOut(out_elems * (c.out_f32 ? 4 : 2));
+  std::vector<float> hStats(size_t(c.B) * c.Cout * 2);
+  CK(cudaMemcpy(hOut.data(), dOut, hOut.size(), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hStats.data(), dStats, hStats.size() * 4, cudaMemcpyDeviceToHost));
+
+  // CPU check (all positions if full_check, else a pseudo-random sample of 4096)
+  double max_err = 0, max_ref = 0;
+  int bad = 0;
+  const int64_t npos = int64_t(c.B) * c.H * c.W;
+  const int64_t nsample = full_check ? npos : 4096;
+  std::vector<double> s1(size_t(c.B) * c.Cout, 0.0), s2(size_t(c.B) * c.Cout, 0.0);
+  for (int64_t sidx = 0; sidx < nsample; ++sidx) {
+    int64_t pos = full_check ? sidx : (int64_t)((uint64_t(sidx) * 2654435761ull) % uint64_t(npos));
+    const int b = int(pos / (c.H * c.W)), i = int((pos / c.W) % c.H), j = int(pos % c.W);
+    for (int n = 0; n < c.Cout; ++n) {
+      double acc = hbias[n];
+      for (int t = 0; t < ntaps; ++t) {
+        const int64_t pix = int64_t(i) * P + j + p.tap_off[t];
+        const uint16_t* a = &hA[(size_t(b) * frame_pix + pix) * c.Cin];
+        const uint16_t* w = &hW[(size_t(t) * c.CoutPad + n) * c.Cin];
+        for (int ci = 0; ci < c.Cin; ++ci) acc += double(bf2f(a[ci])) * double(bf2f(w[ci]));
+      }
+      float ref = float(acc);
+      if (c.act == SG_ACT_TANH) ref = tanhf(ref);
+      if (c.act == SG_ACT_LRELU) ref = ref > 0 ? ref : 0.3f * ref;
+      if (c.act == SG_ACT_RELU) ref = ref > 0 ? ref : 0.f;
+      s1[size_t(b) * c.Cout + n] += ref;
+      s2[size_t(b) * c.Cout + n] += double(ref) * ref;
+      const size_t oi = ((size_t(b) * c.H + i) * c.W + j) * c.Cout + n;
+      const float got = c.out_f32 ? reinterpret_cast<float*>(hOut.data())[oi]
+                                  : bf2f(reinterpret_cast<uint16_t*>(hOut.data())[oi]);
+      const double err = fabs(double(got) - ref);
+      const double tol = (c.out_f32 ? 2e-3 : 1e-2) * (fabs(ref) + 1.0);
+      if (err > tol) {
+        if (bad < 8) printf("  mismatch b%d i%d j%d n%d got %f ref %f\n", b, i, j, n, got, ref);
+        ++bad;
+      }
+      if (err > max_err) max_err = err;
+      if (fabs(ref) > max_ref) max_ref = fabs(ref);
+    }
+  }
+  printf("conv check: %lld positions, max_err %.4g (max |ref| %.3g), bad %d\n", (long long)nsample, max_err,
+         max_ref, bad);
+  if (c.use_stats && full_check) {
+    double se = 0;
+    for (size_t q = 0; q < s1.size(); ++q) {
+      se = fmax(se, fabs(hStats[q * 2] - s1[q]) / (fabs(s1[q]) + 1.0));
+      se = fmax(se, fabs(hStats[q * 2 + 1] - s2[q]) / (fabs(s2[q]) + 1.0));
+    }
+    printf("stats check: max rel err %.4g\n", se);
+    if (se > 1e-3) ++bad;
+  }
+  if (iters > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; ++w) run_conv_gemm(L, 0);
+    CK(cudaEventRecord(e0));
+    for (int it = 0; it < iters; ++it) run_conv_gemm(L, 0);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= iters;
+    const double flops = 2.0 * c.B * c.H * c.W * double(c.Cout) * c.Cin * ntaps;
+    printf("TIMING conv %dx%d k%d %d->%d B%d: %.3f ms  %.1f TFLOP/s (algorithmic)\n", c.H, c.W, c.k, c.Cin, c.Cout,
+           c.B, ms, flops / ms * 1e-9);
+  }
+  return bad ? 1 : 0;
+}
+
+static int run_wgrad_case(int B, int H, int W, int Cx, int Cy, int BN, int k, int ksplit, int iters, bool full) {
+  const int pad = k / 2, P = W + 2 * pad, rows = H + 2 * pad;
+  const int64_t xpix = int64_t(rows) * P + 8, ypix = int64_t(H) * P + 8;
+  const int ntaps = k * k;
+  std::vector<uint16_t> hX(size_t(B) * xpix * Cx), hY(size_t(B) * ypix * Cy, 0);
+  for (auto& v : hX) v = f2bf(frand());
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < H; ++i)
+      for (int j = 0; j < W; ++j)  // slack columns stay zero
+        for (int c = 0; c < Cy; ++c) hY[(size_t(b) * ypix + size_t(i) * P + j) * Cy + c] = f2bf(frand());
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  uint16_t *dX, *dY;
+  float* dW;
+  const size_t wel = size_t(ntaps) * Cx * Cy;
+  CK(cudaMalloc(&dX, hX.size() * 2));
+  CK(cudaMalloc(&dY, hY.size() * 2));
+  CK(cudaMalloc(&dW, wel * 4));
+  CK(cudaMemcpy(dX, hX.data(), hX.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dY, hY.data(), hY.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dW, 0, wel * 4));
+  p.X = dX;
+  p.x_frame_pix = xpix;
+  p.Cx = Cx;
+  p.Y = dY;
+  p.y_frame_pix = ypix;
+  p.Cy = Cy;
+  p.BN = BN;
+  p.B = B;
+  p.ntaps = ntaps;
+  for (int kh = 0; kh < k; ++kh)
+    for (int kw = 0; kw < k; ++kw) p.x_off[kh * k + kw] = kh * P + kw;
+  p.y_off = 0;
+  p.Mpix = H * P;
+  p.dW = dW;
+  p.dw_tap_stride = int64_t(Cx) * Cy;
+  p.dw_sx = Cy;
+  p.dw_sy = 1;
+  p.ksplit = ksplit;
+  WgradLaunch L;
+  int r = prepare_wgrad_gemm(p, &L);
+  if (r) {
+    printf("prepare_wgrad_gemm failed %d\n", r);
+    return 1;
+  }
+  printf("grid %d x %d x %d, stages %d, smem %zu\n", L.grid_x, L.grid_y, L.grid_z, L.stages, L.smem);
+  r = run_wgrad_gemm(L, 0);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (r || e != cudaSuccess) {
+    printf("launch/sync failed r=%d err=%s\n", r, cudaGetErrorString(e));
+    return 1;
+  }
+  std::vector<float> hW(wel);
+  CK(cudaMemcpy(hW.data(), dW, wel * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  double max_err = 0, max_ref = 0;
+  const int64_t nsample = full ? int64_t(wel) : 2048;
+  for (int64_t s = 0; s < nsample; ++s) {
+    const size_t idx = full ? size_t(s) : size_t((uint64_t(s) * 2654435761ull) % wel);
+    const int t = int(idx / (size_t(Cx) * Cy)), x = int((idx / Cy) % Cx), y = int(idx % Cy);
+    double acc = 0;
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+          const int64_t m = int64_t(i) * P + j;
+          acc += double(bf2f(hX[(size_t(b) * xpix + m + p.x_off[t]) * Cx + x])) *
+                 double(bf2f(hY[(size_t(b) * ypix + m) * Cy + y]));
+        }
+    const double err = fabs(hW[idx] - acc);
+    if (err > 2e-3 * (fabs(acc) + 1.0)) {
+      if (bad < 8) printf("  mismatch t%d x%d y%d got %f ref %f\n", t, x, y, hW[idx], acc);
+      ++bad;
+    }
+    max_err = fmax(max_err, err);
+    max_ref = fmax(max_ref, fabs(acc));
+  }
+  printf("wgrad check: %lld entries, max_err %.4g (max |ref| %.3g), bad %d\n", (long long)nsample, max_err, max_ref,
+         bad);
+  if (iters > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int w = 0; w < 3; ++w) run_wgrad_gemm(L, 0);
+    CK(cudaEventRecord(e0));
+    for (int it = 0; it < iters; ++it) run_wgrad_gemm(L, 0);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ms /= iters;
+    const double flops = 2.0 * B * H * W * double(Cx) * Cy * ntaps;
+    printf("TIMING wgrad %dx%d k%d %dx%d B%d ksplit %d: %.3f ms  %.1f TFLOP/s (algorithmic)\n", H, W, k, Cx, Cy, B,
+           ksplit, ms, flops / ms * 1e-9);
+  }
+  return bad ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Experiment: can a K-major SWIZZLE_128B descriptor start at a 128-byte ROW offset inside the
+// 1024-byte swizzle atom (shifted view of one smem tile = the kw taps of a convolution)?
+__global__ void shift_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                   float* out, int shift_rows, int base_off) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar, accbar;
+  __shared__ uint32_t tbase;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* sA = smem;          // 256 rows x 128 B = 32 KB
+  uint8_t* sB = smem + 32768;  // 64 rows x 128 B = 8 KB
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&accbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tbase, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bar, 32768 + 8192);
+    tma_load_2d(&tmA, &bar, sA, 0, 0);
+    tma_load_2d(&tmA, &bar, sA + 16384, 0, 128);
+    tma_load_2d(&tmB, &bar, sB, 0, 0);
+    mbar_wait(&bar, 0, 21);
+    tc_fence_after();
+    const uint32_t idesc = idesc_bf16_f32(128, 64, 0, 0);
+    uint64_t adesc = desc_kmajor_sw128(smem_u32(sA) + shift_rows * 128) | (uint64_t(base_off & 7) << 49);
+    uint64_t bdesc = desc_kmajor_sw128(smem_u32(sB));
+    for (int k = 0; k < 4; ++k) umma_bf16(tbase, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, k != 0);
+    umma_commit(&accbar);
+  }
+  mbar_wait(&accbar, 0, 22);
+  tc_fence_after();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < 64; c0 += 32) {
+    float v[32];
+    tmem_ld32(tbase + (uint32_t(warp * 32) << 16) + c0, v);
+    for (int e = 0; e < 32; ++e) out[row * 64 + c0 + e] = v[e];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tbase, 64);
+  }
+}
+
+static int run_shift_probe() {
+  std::vector<uint16_t> hA(256 * 64), hB(64 * 64, 0);
+  for (int n = 0; n < 64; ++n) hB[n * 64 + n] = f2bf(1.0f);
+  uint16_t *dA, *dB;
+  float* dOut;
+  CK(cudaMalloc(&dA, hA.size() * 2));
+  CK(cudaMalloc(&dB, hB.size() * 2));
+  CK(cudaMalloc(&dOut, 128 * 64 * 4));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CUtensorMap tmA, tmB;
+  if (make_tmap_bf16_2d(&tmA, dA, 64, 256, 128, 64, 128) || make_tmap_bf16_2d(&tmB, dB, 64, 64, 128, 64, 64)) {
+    printf("tmap encode failed\n");
+    return 1;
+  }
+  CK(cudaFuncSetAttribute(shift_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+  const int shifts[] = {0, 1, 2, 3, 5, 7, 8, 9, 17};
+  std::vector<float> rowv(128 * 64), colv(128 * 64);
+  for (int si = 0; si < 9; ++si) {
+    for (int mode = 0; mode < 2; ++mode) {
+      const int sh = shifts[si];
+      const int bo = mode ? (sh & 7) : 0;
+      if (mode == 1 && bo == 0) continue;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int r = 0; r < 256; ++r)
+          for (int c = 0; c < 64; ++c) hA[r * 64 + c] = f2bf(pass == 0 ? float(r) : float(c));
+        CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+        shift_probe_kernel<<<1, 128, 41 * 1024>>>(tmA, tmB, dOut, sh, bo);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+          printf("shift %d bo %d: CUDA error %s\n", sh, bo, cudaGetErrorString(e));
+          return 1;
+        }
+        CK(cudaMemcpy(pass == 0 ? rowv.data() : colv.data(), dOut, 128 * 64 * 4, cudaMemcpyDeviceToHost));
+      }
+      int ok = 0;
+      for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < 64; ++n)
+          if (int(rowv[m * 64 + n]) == m + sh && int(colv[m * 64 + n]) == n) ++ok;
+      printf("SHIFT rows=%d base_offset=%d : %d / 8192 correct", sh, bo, ok);
+      if (ok != 8192) {
+        printf("  e.g. D[0][0..63 step 8] src(row,col):");
+        for (int n = 0; n < 64; n += 8) printf(" (%d,%d)", int(rowv[n]), int(colv[n]));
+        printf("  D[1][0],D[7][8],D[8][0]: (%d,%d) (%d,%d) (%d,%d)", int(rowv[64]), int(colv[64]),
+               int(rowv[7 * 64 + 8]), int(colv[7 * 64 + 8]), int(rowv[8 * 64]), int(colv[8 * 64]));
+      }
+      printf("\n");
+    }
+  }
+  return 0;
+}
+
+static int run_tmap_overlap() {
+  // Overlapping-window map: rows of 64 bf16 that start every 8 elements (16 B).  Used for the
+  // Cin=3 (padded to 8) 7x7 convolution if the driver accepts it.
+  uint16_t* d;
+  CK(cudaMalloc(&d, 1 << 20));
+  CUtensorMap tm;
+  int r = make_tmap_bf16_2d(&tm, d, 64, 4096, 16, 64, 128);
+  printf("TMAP_OVERLAP encode (dim0=64 elems, row stride 16 B) -> %d (0 = accepted)\n", r);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  const char* t = argc > 1 ? argv[1] : "conv_small";
+  int rc = 1;
+  if (!strcmp(t, "conv_small")) {
+    ConvCase c = {2, 6, 20, 128, 128, 128, 128, 3, SG_ACT_NONE, 0, 1};
+    rc = run_conv_case(c, 0, true);
+  } else if (!strcmp(t, "conv_small64")) {
+    ConvCase c = {1, 5, 9, 64, 64, 64, 64, 3, SG_ACT_LRELU, 0, 1};
+    rc = run_conv_case(c, 0, true);
+  } else if (!strcmp(t, "conv_res")) {
+    ConvCase c = {8, 64, 128, 256, 256, 256, 256, 3, SG_ACT_NONE, 0, 1};
+    rc = run_conv_case(c, 20, false);
+  } else if (!strcmp(t, "conv_res128")) {
+    ConvCase c = {8, 64, 128, 256, 256, 256, 128, 3, SG_ACT_NONE, 0, 1};
+    rc = run_conv_case(c, 20, false);
+  } else if (!strcmp(t, "conv_out7")) {
+    ConvCase c = {1, 8, 40, 64, 3, 32, 32, 7, SG_ACT_TANH, 1, 0};
+    rc = run_conv_case(c, 0, true);
+  } else if (!strcmp(t, "wgrad_small")) {
+    rc = run_wgrad_case(2, 6, 20, 128, 64, 64, 3, 3, 0, true);
+  } else if (!strcmp(t, "wgrad_res")) {
+    rc = run_wgrad_case(8, 64, 128, 256, 256, 256, 3, 8, 10, false);
+  } else if (!strcmp(t, "shift")) {
+    rc = run_shift_probe();
+  } else if (!strcmp(t, "tmap_overlap")) {
+    rc = run_tmap_overlap();
+  }
+  printf("watchdog flag: %d\n", read_tc_watchdog());
+  printf("RESULT %s %s\n", t, rc == 0 ? "PASS" : "FAIL");
+  return rc;
+}
