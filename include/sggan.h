@@ -1,0 +1,142 @@
+/* sggan.h -- C ABI of libsggan_sm100.so: the B200-native SG-GAN training step.
+ *
+ * The reference (fhfonsecaa/SG-GAN-TF2) has no FFI: its hot path sits behind Python callables
+ * that dispatch TensorFlow eager kernels.  Each entry point below names the reference call it
+ * replaces.  Conventions: plain C types only; every pointer is a raw DEVICE pointer unless the
+ * name ends in _host; tensors are NHWC fp32 at the boundary (what the reference's numpy batches
+ * are, model.py:246-256); every call returns 0 on success or a negative SGGAN_E_* code
+ * (sggan_last_error() gives a string); launches are asynchronous on the given stream; the library
+ * never allocates or frees device memory -- the caller supplies one workspace of
+ * sggan_workspace_bytes() bytes; no CPU fallback exists.  A handle is bound to one device and is
+ * not thread-safe.
+ */
+#ifndef SGGAN_H_
+#define SGGAN_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGGAN_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define SGGAN_E_WORKSPACE (-2) /* workspace missing or too small */
+#define SGGAN_E_CUDA (-3)      /* a CUDA runtime / driver call failed */
+#define SGGAN_E_STATE (-4)     /* call order (e.g. step before weights) */
+
+#define SGGAN_NET_G 0
+#define SGGAN_NET_D 1
+#define SGGAN_LOSS_P2P 0   /* as wired: model.py:190-191 */
+#define SGGAN_LOSS_SGGAN 1 /* the defined-but-unwired SG-GAN losses, model.py:114-133 */
+
+typedef struct sggan_config {
+  int batch;            /* per-GPU batch B (args.batch_size x augmentation, model.py:234-244) */
+  int image_height;     /* main.py:19 --img_height */
+  int image_width;      /* main.py:20 --img_width  */
+  int gf_dim;           /* module.py:221 (hard-coded 64 in the reference; must be 64 here) */
+  int df_dim;           /* module.py:274 (64) */
+  int segment_class;    /* module.py:275 / main.py:43 */
+  int n_blocks;         /* 9 residual blocks, module.py:244-252 */
+  int mask_height;      /* mask grid; must broadcast against the D logit grid */
+  int mask_width;
+  int loss_mode;        /* SGGAN_LOSS_* */
+  int use_lsgan;        /* main.py:40, only read in SGGAN_LOSS_SGGAN mode */
+  float lr;             /* model.py:82,205: 0.001 */
+  float beta1;          /* main.py:28: 0.5 */
+  float beta2;          /* Keras default 0.999 */
+  float adam_eps;       /* Keras default 1e-7 */
+  float in_eps;         /* tfa InstanceNormalization default 1e-3 */
+  float p2p_lambda;     /* LAMBDA = 100, model.py:151 */
+  float L1_lambda;      /* main.py:37 */
+  float Lg_lambda;      /* main.py:38 */
+  int world_size;       /* data-parallel ranks: gradients are scaled by 1/world_size before Adam */
+} sggan_config;
+
+typedef struct sggan_handle sggan_handle;
+
+/* Fill `cfg` with the reference's effective defaults for an image size. */
+void sggan_default_config(sggan_config* cfg, int batch, int height, int width);
+/* D logit grid for an input size (module.py:284-311 shape arithmetic). */
+void sggan_disc_logit_grid(int height, int width, int* hd, int* wd);
+size_t sggan_workspace_bytes(const sggan_config* cfg);
+int sggan_create(const sggan_config* cfg, void* workspace, size_t workspace_bytes, void* stream,
+                 sggan_handle** out);
+void sggan_destroy(sggan_handle* h);
+const char* sggan_last_error(void);
+
+/* Weights in Keras creation order (generator: 94 tensors, discriminator: 28). */
+int sggan_num_tensors(const sggan_handle* h, int net);
+int64_t sggan_tensor_numel(const sggan_handle* h, int net, int idx);
+int sggan_tensor_rank(const sggan_handle* h, int net, int idx);
+void sggan_tensor_shape(const sggan_handle* h, int net, int idx, int64_t shape[4]);
+/* flat fp32 buffers, all tensors back to back in creation order: what=0 params, 1 grads, 2 adam m, 3 adam v */
+float* sggan_flat_buffer(sggan_handle* h, int net, int what, int64_t* numel);
+int64_t sggan_tensor_offset(const sggan_handle* h, int net, int idx);
+/* Must be called after the params buffer was written (re-packs the bf16 GEMM operands). */
+int sggan_weights_changed(sggan_handle* h);
+
+/* generator(x): model.py:176,528-532.  real_A [B,H,W,3] fp32 -> fake_A [B,H,W,3] fp32. */
+int sggan_gen_forward(sggan_handle* h, const float* real_A, float* fake_A);
+/* discriminator([x, mask]): model.py:186-188.  x [B,H,W,3], mask [B,hm,wm,C] -> logits [B,Ho,Wo,1]. */
+int sggan_disc_forward(sggan_handle* h, const float* x, const float* mask, float* logits);
+
+/* sggan.train_step: model.py:169-200.  losses_out[0] = gen_loss, [1] = disc_loss (device floats).
+ * sggan_train_step = forward_backward + adam; the split lets a data-parallel caller all-reduce the
+ * flat gradient buffers in between (discriminator gradients are final after phase 1). */
+int sggan_step_forward_backward_d(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask,
+                                  float* losses_out);
+int sggan_step_backward_g(sggan_handle* h);
+int sggan_step_adam(sggan_handle* h, int net);
+int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask,
+                     float* losses_out);
+int64_t sggan_step_count(const sggan_handle* h);
+int sggan_kernel_launches(const sggan_handle* h); /* kernels launched by the last train step */
+/* fake_A of the last step / forward (device, [B,H,W,3] fp32). */
+const float* sggan_last_fake(const sggan_handle* h);
+
+/* Debug / test access to internal activations.  kind: 0 input frame X, 1 raw conv output Y,
+ * 2 output-gradient frame dY, 3 input-gradient buffer dX, 4 forward stats.  Returns the device
+ * pointer and describes the layout in `desc` (16 ints, see sggan_b200/_lib.py). */
+void* sggan_debug_buffer(sggan_handle* h, int net, int layer, int kind, int64_t desc[16]);
+int sggan_num_layers(const sggan_handle* h, int net);
+
+/* ---- single operators (ops.py surface + criteria), NHWC fp32 in / out ------------------------- */
+/* ops.conv2d (ops.py:24-28) / tf.keras.layers.Conv2D: kernel HWIO, padding 0 VALID, 1 SAME (TF),
+ * 2 REFLECT((k-1)/2) then VALID.  bias may be null.  Cin, Cout multiples of 64, stride 1 or 2 (k=3). */
+size_t sggan_conv2d_workspace(int B, int H, int W, int Cin, int Cout, int k, int stride, int padding);
+int sggan_conv2d_fwd(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
+                     int Cout, int k, int stride, int padding, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* ops.deconv2d (ops.py:30-34) / Conv2DTranspose(3, strides 2, 'same'): kernel (kh,kw,Cout,Cin). */
+int sggan_deconv2d_fwd(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W,
+                       int Cin, int Cout, void* workspace, size_t workspace_bytes, void* stream);
+/* ops.instance_norm (ops.py:13-22) / tfa InstanceNormalization, optionally fused activation
+ * (0 none, 1 relu, 2 leaky(alpha), 3 tanh) and residual add.  C multiple of 64. */
+int sggan_instance_norm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                            int B, int H, int W, int C, float eps, int act, float alpha, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* ops.lrelu (ops.py:36-37) */
+int sggan_lrelu(const float* x, float* y, int64_t n, float leak, void* stream);
+/* multiply([h4, mask]) + reduce_sum(axis=-1) (module.py:312-314) */
+int sggan_mask_reduce(const float* h4, const float* mask, float* out, int B, int Hd, int Wd, int hm, int wm, int C,
+                      void* stream);
+/* abs_criterion / mae_criterion / sce_criterion (module.py:336-345): mode 0 / 1 / 2; out = device float */
+int sggan_criterion(const float* a, const float* b, int64_t n, int mode, float* out, void* stream);
+/* weighted_seg_A (model.py:115-119): seg [B,H,W,3] -> weight [B,H,W,1] */
+int sggan_seg_edge_weight(const float* seg, float* weight, int B, int H, int W, void* stream);
+/* gradloss_criterion (module.py:347-351): out = device float; d_in (may be null) = d out / d in */
+int sggan_gradloss(const float* in, const float* target, const float* weight, float* out, float* d_in, int B, int H,
+                   int W, void* stream);
+/* Keras Adam apply (model.py:199-200): t = 1-based step index */
+int sggan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t t, float lr, float beta1,
+                    float beta2, float eps, void* stream);
+/* one_hot + nearest resample of a class-id map to the D logit grid (utils.py:158-165,190):
+ * ids [B,H,W] uint8 -> mask [B,hd,wd,C] fp32 */
+int sggan_onehot_mask(const uint8_t* ids, float* mask, int B, int H, int W, int hd, int wd, int C, void* stream);
+/* RGB -> class id LUT (segment_class.py:60-70,95-97): rgb [n,3] uint8 -> ids [n] uint8 */
+int sggan_rgb_to_class(const uint8_t* rgb, uint8_t* ids, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGGAN_H_ */

@@ -1,0 +1,357 @@
+// api.cu -- the extern "C" surface declared in include/sggan.h.
+#include <math.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/sggan.h"
+#include "engine.h"
+
+using namespace sggan;
+
+struct sggan_handle {
+  Engine e;
+};
+
+static thread_local std::string g_err;
+
+namespace sggan {
+int layer_geometry(Layer& l);
+int layer_prepare_fwd(Layer& l, const float* bias, void* out, const FrameMap& omap, int out_f32, bool dry);
+}  // namespace sggan
+
+static Net& net_of(sggan_handle* h, int net) { return net == SGGAN_NET_G ? h->e.G : h->e.D; }
+static const Net& net_of(const sggan_handle* h, int net) { return net == SGGAN_NET_G ? h->e.G : h->e.D; }
+
+extern "C" {
+
+const char* sggan_last_error(void) { return g_err.c_str(); }
+
+void sggan_disc_logit_grid(int height, int width, int* hd, int* wd) {
+  auto same = [](int n) { return (n + 1) / 2; };
+  auto valid = [](int n, int s) { return (n - 3) / s + 1; };
+  int h = same(same(same(height))), w = same(same(same(width)));
+  h = valid(h, 2); w = valid(w, 2);
+  h = valid(h, 2); w = valid(w, 2);
+  *hd = valid(h, 1); *wd = valid(w, 1);
+}
+
+void sggan_default_config(sggan_config* c, int batch, int height, int width) {
+  memset(c, 0, sizeof(*c));
+  c->batch = batch; c->image_height = height; c->image_width = width;
+  c->gf_dim = 64; c->df_dim = 64; c->segment_class = 34; c->n_blocks = 9;
+  sggan_disc_logit_grid(height, width, &c->mask_height, &c->mask_width);
+  c->loss_mode = SGGAN_LOSS_P2P; c->use_lsgan = 1;
+  c->lr = 0.001f; c->beta1 = 0.5f; c->beta2 = 0.999f; c->adam_eps = 1e-7f; c->in_eps = 1e-3f;
+  c->p2p_lambda = 100.f; c->L1_lambda = 10.f; c->Lg_lambda = 5.f; c->world_size = 1;
+}
+
+size_t sggan_workspace_bytes(const sggan_config* cfg) {
+  Engine e;
+  size_t need = 0;
+  int r = e.build(*cfg, nullptr, 0, nullptr, true, &need);
+  if (r) { g_err = e.err; return 0; }
+  return need;
+}
+
+int sggan_create(const sggan_config* cfg, void* workspace, size_t workspace_bytes, void* stream, sggan_handle** out) {
+  if (!cfg || !out) { g_err = "null argument"; return SGGAN_E_INVALID; }
+  if (!workspace) { g_err = "workspace is null"; return SGGAN_E_WORKSPACE; }
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0) {
+    g_err = "no CUDA device: libsggan_sm100 has no CPU fallback";
+    return SGGAN_E_CUDA;
+  }
+  sggan_handle* h = new sggan_handle();
+  size_t need = 0;
+  int r = h->e.build(*cfg, workspace, workspace_bytes, (cudaStream_t)stream, false, &need);
+  if (r) { g_err = h->e.err; delete h; return r; }
+  *out = h;
+  return 0;
+}
+
+void sggan_destroy(sggan_handle* h) { delete h; }
+
+
+int sggan_num_tensors(const sggan_handle* h, int net) { return int(net_of(h, net).T.size()); }
+int64_t sggan_tensor_numel(const sggan_handle* h, int net, int idx) { return net_of(h, net).T[idx].numel; }
+int sggan_tensor_rank(const sggan_handle* h, int net, int idx) { return net_of(h, net).T[idx].rank; }
+void sggan_tensor_shape(const sggan_handle* h, int net, int idx, int64_t shape[4]) {
+  for (int i = 0; i < 4; ++i) shape[i] = net_of(h, net).T[idx].shape[i];
+}
+int64_t sggan_tensor_offset(const sggan_handle* h, int net, int idx) { return net_of(h, net).T[idx].offset; }
+float* sggan_flat_buffer(sggan_handle* h, int net, int what, int64_t* numel) {
+  Net& n = net_of(h, net);
+  if (numel) *numel = n.nparams;
+  switch (what) {
+    case 0: return n.p;
+    case 1: return n.g;
+    case 2: return n.m;
+    case 3: return n.v;
+  }
+  return nullptr;
+}
+int sggan_weights_changed(sggan_handle* h) {
+  int r = h->e.pack_weights(SGGAN_NET_G);
+  if (!r) r = h->e.pack_weights(SGGAN_NET_D);
+  if (r) { g_err = "weight packing failed"; return r; }
+  h->e.weights_ready = true;
+  return 0;
+}
+
+#define FWD_ERR(expr)            \
+  do {                           \
+    int r_ = (expr);             \
+    if (r_) { g_err = h->e.err; return r_; } \
+  } while (0)
+
+int sggan_gen_forward(sggan_handle* h, const float* real_A, float* fake_A) {
+  FWD_ERR(h->e.gen_forward(real_A, fake_A));
+  return 0;
+}
+int sggan_disc_forward(sggan_handle* h, const float* x, const float* mask, float* logits) {
+  FWD_ERR(h->e.disc_forward_user(x, mask, logits));
+  return 0;
+}
+int sggan_step_forward_backward_d(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask,
+                                  float* losses_out) {
+  FWD_ERR(h->e.step_fwd_bwd_d(real_A, seg_A, mask, losses_out));
+  return 0;
+}
+int sggan_step_backward_g(sggan_handle* h) {
+  FWD_ERR(h->e.step_bwd_g());
+  return 0;
+}
+int sggan_step_adam(sggan_handle* h, int net) {
+  FWD_ERR(h->e.step_adam(net));
+  if (net == SGGAN_NET_D) h->e.step += 1;  // D is updated last (model.py:199-200)
+  return 0;
+}
+int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask, float* losses_out) {
+  FWD_ERR(h->e.step_fwd_bwd_d(real_A, seg_A, mask, losses_out));
+  FWD_ERR(h->e.step_bwd_g());
+  FWD_ERR(h->e.step_adam(SGGAN_NET_G));
+  FWD_ERR(h->e.step_adam(SGGAN_NET_D));
+  h->e.step += 1;
+  return 0;
+}
+int64_t sggan_step_count(const sggan_handle* h) { return h->e.step; }
+int sggan_kernel_launches(const sggan_handle* h) { return h->e.nlaunch; }
+const float* sggan_last_fake(const sggan_handle* h) { return h->e.fake; }
+int sggan_num_layers(const sggan_handle* h, int net) { return int(net_of(h, net).L.size()); }
+
+static void desc_map(const FrameMap& m, int64_t* d) {
+  d[0] = m.frame_pix; d[1] = m.C; d[2] = m.H; d[3] = m.W; d[4] = m.kind; d[5] = m.P; d[6] = m.pt; d[7] = m.pl;
+  d[8] = m.plane_pix; d[9] = m.reflect;
+}
+void* sggan_debug_buffer(sggan_handle* h, int net, int layer, int kind, int64_t desc[16]) {
+  Net& n = net_of(h, net);
+  if (layer < 0 || layer >= int(n.L.size())) return nullptr;
+  Layer& l = n.L[layer];
+  memset(desc, 0, 16 * sizeof(int64_t));
+  desc[10] = l.nb; desc[11] = l.nbv; desc[12] = 0;  // desc[12]: 1 = fp32 elements
+  switch (kind) {
+    case 0: desc_map(l.xmap, desc); return l.X;
+    case 1: { FrameMap m; memset(&m, 0, sizeof(m)); m.frame_pix = int64_t(l.Hout) * l.Wout; m.C = l.Cout; m.H = l.Hout;
+              m.W = l.Wout; m.P = l.Wout; desc_map(m, desc); return l.Y; }
+    case 2: desc_map(l.dymap, desc); return l.dY;
+    case 3: { FrameMap m; memset(&m, 0, sizeof(m)); m.frame_pix = int64_t(l.dxH) * l.dxW; m.C = l.Cin; m.H = l.dxH;
+              m.W = l.dxW; m.P = l.dxW; m.pt = l.dx_oy; m.pl = l.dx_ox; m.reflect = l.dx_fold; desc_map(m, desc);
+              desc[12] = l.dx_f32; return l.dX; }
+    case 4: desc[1] = l.Cout; desc[12] = 1; return l.stats;
+  }
+  return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single operators
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static int conv_layer_for_op(Layer& l, int B, int H, int W, int Cin, int Cout, int k, int stride, int padding,
+                             bool deconv) {
+  memset(&l.xmap, 0, sizeof(l.xmap));
+  if (Cin % 64 || Cout % 64 || Cin < 64 || Cout < 64) return SGGAN_E_INVALID;
+  l.k = k; l.Cin = Cin; l.Cout = Cout; l.Hin = H; l.Win = W; l.has_norm = false; l.act = SG_ACT_NONE; l.alpha = 0.f;
+  l.nb = l.nbv = B;
+  if (deconv) { l.type = LT_DECONV; l.pad = PAD_ZERO; }
+  else if (stride == 1) {
+    l.type = LT_S1;
+    l.pad = padding == 0 ? PAD_VALID : (padding == 1 ? PAD_ZERO : PAD_REFLECT);
+    if (!(k & 1)) return SGGAN_E_INVALID;
+    if (k * k > SGGAN_MAX_TAPS) return SGGAN_E_INVALID;
+  } else if (stride == 2 && k == 3 && padding != 2) {
+    l.type = LT_S2;
+    l.pad = padding == 0 ? PAD_VALID : PAD_ZERO;
+  } else return SGGAN_E_INVALID;
+  return layer_geometry(l);
+}
+
+static size_t conv_op_bytes(const Layer& l, int64_t* offW, int64_t* offX, int64_t* offY) {
+  size_t off = 0;
+  *offW = off; off = align256(off + size_t(l.packf.T) * l.packf.N * l.packf.K * 2);
+  *offX = off; off = align256(off + size_t(l.nb) * l.xmap.frame_pix * l.xmap.C * 2 + 4096);
+  *offY = off; off = align256(off + size_t(l.nb) * l.Hout * l.Wout * l.Cout * 4);
+  return off;
+}
+
+size_t sggan_conv2d_workspace(int B, int H, int W, int Cin, int Cout, int k, int stride, int padding) {
+  Layer l;
+  if (conv_layer_for_op(l, B, H, W, Cin, Cout, k, stride, padding, stride == -2)) return 0;
+  int64_t a, b, c;
+  return conv_op_bytes(l, &a, &b, &c);
+}
+
+static int conv_op_run(Layer& l, const float* x, const float* kernel, const float* bias, float* y, void* ws,
+                       size_t ws_bytes, cudaStream_t st) {
+  int64_t oW, oX, oY;
+  const size_t need = conv_op_bytes(l, &oW, &oX, &oY);
+  if (!ws || ws_bytes < need) { g_err = "operator workspace too small"; return SGGAN_E_WORKSPACE; }
+  uint8_t* base = (uint8_t*)ws;
+  l.Wf = (sg_bf16*)(base + oW);
+  l.X = (sg_bf16*)(base + oX);
+  if (cudaMemsetAsync(l.X, 0, size_t(l.nb) * l.xmap.frame_pix * l.xmap.C * 2 + 4096, st) != cudaSuccess) return SGGAN_E_CUDA;
+  PackParams pf = l.packf;
+  pf.src = kernel; pf.dst = l.Wf;
+  launch_pack_weights(pf, st);
+  launch_f32_to_frame(x, l.nb, l.Hin, l.Win, l.Cin, l.X, l.xmap, st);
+  FrameMap om;
+  memset(&om, 0, sizeof(om));
+  om.frame_pix = int64_t(l.Hout) * l.Wout; om.C = l.Cout; om.H = l.Hout; om.W = l.Wout; om.P = l.Wout;
+  int r = layer_prepare_fwd(l, bias, y, om, 1, false);
+  if (r) { g_err = "conv prepare failed " + std::to_string(r); return SGGAN_E_CUDA; }
+  for (auto& L : l.fwd)
+    if ((r = run_conv_gemm(L, st))) { g_err = "conv launch failed " + std::to_string(r); return SGGAN_E_CUDA; }
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+
+int sggan_conv2d_fwd(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
+                     int Cout, int k, int stride, int padding, void* workspace, size_t workspace_bytes, void* stream) {
+  Layer l;
+  if (conv_layer_for_op(l, B, H, W, Cin, Cout, k, stride, padding, false)) { g_err = "unsupported conv2d shape"; return SGGAN_E_INVALID; }
+  return conv_op_run(l, x, kernel, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int sggan_deconv2d_fwd(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
+                       int Cout, void* workspace, size_t workspace_bytes, void* stream) {
+  Layer l;
+  if (conv_layer_for_op(l, B, H, W, Cin, Cout, 3, 2, 1, true)) { g_err = "unsupported deconv2d shape"; return SGGAN_E_INVALID; }
+  return conv_op_run(l, x, kernel, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int sggan_instance_norm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y,
+                            int B, int H, int W, int C, float eps, int act, float alpha, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C % 64) { g_err = "C must be a multiple of 64"; return SGGAN_E_INVALID; }
+  const size_t n = size_t(B) * H * W * C;
+  const size_t need = align256(n * 2) * 3 + align256(size_t(B) * C * 8);
+  if (!workspace || workspace_bytes < need) { g_err = "operator workspace too small"; return SGGAN_E_WORKSPACE; }
+  uint8_t* base = (uint8_t*)workspace;
+  sg_bf16* xb = (sg_bf16*)base;
+  sg_bf16* rb = (sg_bf16*)(base + align256(n * 2));
+  sg_bf16* yb = (sg_bf16*)(base + 2 * align256(n * 2));
+  float* stats = (float*)(base + 3 * align256(n * 2));
+  launch_f32_to_bf16(x, xb, n, st);
+  if (residual) launch_f32_to_bf16(residual, rb, n, st);
+  if (cudaMemsetAsync(stats, 0, size_t(B) * C * 8, st) != cudaSuccess) return SGGAN_E_CUDA;
+  launch_in_stats(xb, B, H * W, C, stats, st);
+  InApplyParams p;
+  memset(&p, 0, sizeof(p));
+  FrameMap pm;
+  memset(&pm, 0, sizeof(pm));
+  pm.frame_pix = int64_t(H) * W; pm.C = C; pm.H = H; pm.W = W; pm.P = W;
+  p.Y = xb; p.B = B; p.H = H; p.W = W; p.C = C; p.stats = stats; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.act = act; p.act_alpha = alpha; p.res = residual ? rb : nullptr; p.rmap = pm; p.dst = yb; p.dmap = pm;
+  launch_in_apply(p, st);
+  launch_bf16_to_f32(yb, y, n, st);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+
+int sggan_lrelu(const float* x, float* y, int64_t n, float leak, void* stream) {
+  launch_lrelu(x, y, n, leak, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+int sggan_mask_reduce(const float* h4, const float* mask, float* out, int B, int Hd, int Wd, int hm, int wm, int C,
+                      void* stream) {
+  const int Ho = Hd > hm ? Hd : hm, Wo = Wd > wm ? Wd : wm;
+  if ((Hd != Ho && Hd != 1) || (hm != Ho && hm != 1) || (Wd != Wo && Wd != 1) || (wm != Wo && wm != 1)) {
+    g_err = "shapes do not broadcast";
+    return SGGAN_E_INVALID;
+  }
+  launch_mask_reduce(h4, mask, B, Hd, Wd, hm, wm, C, out, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+int sggan_criterion(const float* a, const float* b, int64_t n, int mode, float* out, void* stream) {
+  if (mode < 0 || mode > 2) return SGGAN_E_INVALID;
+  launch_criterion(a, b, n, mode, out, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+int sggan_seg_edge_weight(const float* seg, float* weight, int B, int H, int W, void* stream) {
+  launch_seg_edge_weight(seg, B, H, W, weight, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+int sggan_gradloss(const float* in, const float* target, const float* weight, float* out, float* d_in, int B, int H,
+                   int W, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(out, 0, 4, st) != cudaSuccess) return SGGAN_E_CUDA;
+  launch_gradloss(in, target, weight, B, H, W, 1.f, out, d_in, st);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+int sggan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t t, float lr, float beta1,
+                    float beta2, float eps, void* stream) {
+  const float alpha_t = float(double(lr) * sqrt(1.0 - pow(double(beta2), double(t))) / (1.0 - pow(double(beta1), double(t))));
+  launch_adam(p, g, m, v, n, alpha_t, beta1, beta2, eps, 1.f, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+
+}  // extern "C"
+
+// integer mask construction kernels live here (tiny, byte work)
+__global__ void onehot_mask_kernel(const uint8_t* __restrict__ ids, float* mask, int B, int H, int W, int hd, int wd,
+                                   int C) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t tot = int64_t(B) * hd * wd * C;
+  if (idx >= tot) return;
+  const int c = int(idx % C);
+  int64_t r = idx / C;
+  const int j = int(r % wd);
+  r /= wd;
+  const int i = int(r % hd), b = int(r / hd);
+  // nearest source pixel: floor((i + 0.5) * H / hd), exact in integers
+  int si = int((int64_t(2 * i + 1) * H) / (2 * hd)), sj = int((int64_t(2 * j + 1) * W) / (2 * wd));
+  si = si < H ? si : H - 1;
+  sj = sj < W ? sj : W - 1;
+  mask[idx] = ids[(int64_t(b) * H + si) * W + sj] == c ? 1.f : 0.f;
+}
+__global__ void rgb_to_class_kernel(const uint8_t* __restrict__ rgb, uint8_t* ids, int64_t n) {
+  // segment_class.py:60-70: 21 colours -> 8 ids, everything else 0
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t key = (uint32_t(rgb[i * 3]) << 16) | (uint32_t(rgb[i * 3 + 1]) << 8) | rgb[i * 3 + 2];
+  uint8_t v = 0;
+  switch (key) {
+    case (128u << 16) | (64u << 8) | 128u: case (244u << 16) | (35u << 8) | 232u:
+    case (250u << 16) | (170u << 8) | 160u: case (230u << 16) | (150u << 8) | 140u: v = 4; break;
+    case (70u << 16) | (70u << 8) | 70u: case (102u << 16) | (102u << 8) | 156u:
+    case (190u << 16) | (153u << 8) | 153u: case (180u << 16) | (165u << 8) | 180u:
+    case (150u << 16) | (100u << 8) | 100u: case (150u << 16) | (120u << 8) | 90u: v = 5; break;
+    case (107u << 16) | (142u << 8) | 35u: v = 7; break;
+    case (70u << 16) | (130u << 8) | 180u: v = 6; break;
+    case (220u << 16) | (20u << 8) | 60u: case (255u << 16) | (0u << 8) | 0u: v = 2; break;
+    case (0u << 16) | (0u << 8) | 142u: case (0u << 16) | (0u << 8) | 70u: case (0u << 16) | (60u << 8) | 100u:
+    case (0u << 16) | (0u << 8) | 90u: case (0u << 16) | (0u << 8) | 110u: v = 1; break;
+    case (0u << 16) | (0u << 8) | 230u: case (119u << 16) | (11u << 8) | 32u: v = 3; break;
+    default: v = 0;
+  }
+  ids[i] = v;
+}
+extern "C" int sggan_onehot_mask(const uint8_t* ids, float* mask, int B, int H, int W, int hd, int wd, int C,
+                                 void* stream) {
+  const int64_t tot = int64_t(B) * hd * wd * C;
+  onehot_mask_kernel<<<unsigned((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, mask, B, H, W, hd, wd, C);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+extern "C" int sggan_rgb_to_class(const uint8_t* rgb, uint8_t* ids, int64_t n, void* stream) {
+  rgb_to_class_kernel<<<unsigned((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rgb, ids, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}

@@ -88,7 +88,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* sa = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
         tma_load_3d(&tmA, &full_bar[s], sa, cc * kChunkK, m0 + p.tap_off[tap], b);
-        tma_load_2d(&tmB, &full_bar[s], sa + kABytes, cc * kChunkK, tap * p.CoutPad + n0);
+        tma_load_2d(&tmB, &full_bar[s], sa + kABytes, cc * kChunkK, int(p.tap_w[tap]) * p.CoutPad + n0);
       }
     }
   } else if (warp == 1) {
@@ -118,10 +118,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int row = q * 32 + lane;
     const int m = m0 + row;
     const int i = m / p.P, j = m - i * p.P;
-    const bool valid = (m < p.M) && (i < p.Hv) && (j < p.Wv);
+    const int oi = i * p.o_scale + p.o_a, oj = j * p.o_scale + p.o_b;
+    const bool valid = (m < p.M) && (i < p.Hv) && (j < p.Wv) && (oi < p.omap.H) && (oj < p.omap.W);
     float* tsm = reinterpret_cast<float*>(smem);  // [BN][129] transposed fp32 tile for the statistics
-    const int64_t obase = int64_t(b) * p.out_bstride + int64_t(i) * p.out_sy + int64_t(j) * p.out_sx + p.out_off;
-    const bool vec_ok = (!p.out_f32) && ((p.Cout & 7) == 0) && ((obase & 7) == 0);
+    const int64_t obase = (int64_t(b) * p.omap.frame_pix + (valid ? frame_pixel(p.omap, oi, oj) : 0)) * p.omap.C;
+    const bool vec_ok = (!p.out_f32) && ((p.omap.C & 7) == 0);
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
@@ -132,7 +133,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float x = v[e];
         if (p.bias != nullptr && n < p.Cout) x += __ldg(p.bias + n);
         x = apply_act(x, p.act, p.act_alpha);
-        v[e] = x;
+        // statistics are taken over the values as stored (bf16), so that the normalisation that
+        // follows is exact for what it reads (H*W == 1 must give exactly beta)
+        v[e] = p.out_f32 ? x : __bfloat162float(__float2bfloat16_rn(x));
       }
       if (p.stats != nullptr) {
 #pragma unroll
@@ -205,7 +208,7 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
   const int stage_bytes = kABytes + BN * 128;
-  const int mtiles = p.Cx / kTileM;
+  const int mtiles = p.x_pair ? 1 : p.Cx / kTileM;
   const int mt = blockIdx.x % mtiles, tap = blockIdx.x / mtiles;
   const int n0 = blockIdx.y * BN;
   const int nchunk = (p.Mpix + 63) / 64;  // 64-pixel K chunks per image
@@ -234,7 +237,9 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      const int xoff = p.x_off[tap];
+      const int xoff = p.x_off[tap], yoff = p.y_off[tap];
+      const int xoff2 = p.x_pair ? p.x_off2[tap] : xoff;
+      const int xc0 = p.x_pair ? 0 : mt * kTileM, xc1 = p.x_pair ? 0 : mt * kTileM + 64;
       for (int ks = 0; ks < ksteps; ++ks) {
         const int s = ks % stages;
         const uint32_t ph = (ks / stages) & 1;
@@ -243,10 +248,10 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int b = c / nchunk, mc = (c - b * nchunk) * 64;
         uint8_t* sa = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_3d(&tmX, &full_bar[s], sa, mt * kTileM, mc + xoff, b);
-        tma_load_3d(&tmX, &full_bar[s], sa + 8192, mt * kTileM + 64, mc + xoff, b);
+        tma_load_3d(&tmX, &full_bar[s], sa, xc0, mc + xoff, b);
+        tma_load_3d(&tmX, &full_bar[s], sa + 8192, xc1, mc + xoff2, b);
         for (int h = 0; h < BN / 64; ++h)
-          tma_load_3d(&tmY, &full_bar[s], sa + kABytes + h * 8192, n0 + h * 64, mc + p.y_off, b);
+          tma_load_3d(&tmY, &full_bar[s], sa + kABytes + h * 8192, n0 + h * 64, mc + yoff, b);
       }
     }
   } else if (warp == 1) {
@@ -277,9 +282,12 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     float* dst = p.dW + int64_t(tap) * p.dw_tap_stride + int64_t(xg) * p.dw_sx;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
-      tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+      tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), v);  // warp-collective: no divergence here
+      if (xg < p.nx_valid) {
 #pragma unroll
-      for (int e = 0; e < 32; ++e) atomicAdd(dst + int64_t(n0 + c0 + e) * p.dw_sy, v[e]);
+        for (int e = 0; e < 32; ++e)
+          if (n0 + c0 + e < p.ny_valid) atomicAdd(dst + int64_t(n0 + c0 + e) * p.dw_sy, v[e]);
+      }
     }
     tc_fence_before();
   }
@@ -308,10 +316,10 @@ int prepare_conv_gemm(const ConvGemmParams& p, ConvGemmLaunch* L) {
   L->grid_x = (p.M + kTileM - 1) / kTileM;
   L->grid_y = p.CoutPad / p.BN;
   L->grid_z = p.B;
-  int r = make_tmap_bf16_3d(&L->tmA, p.A, p.Cin, p.a_frame_pix, p.B, uint64_t(p.Cin) * 2,
-                            uint64_t(p.a_frame_pix) * p.Cin * 2, 64, 128);
+  int r = make_tmap_bf16_3d(&L->tmA, p.A, p.Cin, p.a_frame_pix, p.B, uint64_t(p.a_row_stride) * 2,
+                            uint64_t(p.a_frame_pix) * p.a_row_stride * 2, 64, 128);
   if (r) return -1000 - r;
-  r = make_tmap_bf16_2d(&L->tmB, p.Wt, p.Cin, uint64_t(p.ntaps) * p.CoutPad, uint64_t(p.Cin) * 2, 64, p.BN);
+  r = make_tmap_bf16_2d(&L->tmB, p.Wt, p.Cin, uint64_t(p.wt_taps) * p.CoutPad, uint64_t(p.Cin) * 2, 64, p.BN);
   if (r) return -2000 - r;
   static bool attr_set = false;
   if (!attr_set) {
@@ -331,21 +339,21 @@ int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
 }
 
 int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L) {
-  if (p.Cx % 128 != 0 || p.Cx <= 0) return -20;
+  if (p.Cx <= 0 || (p.x_pair ? p.Cx != 64 : p.Cx % 128 != 0)) return -20;
   if (!(p.BN == 64 || p.BN == 128 || p.BN == 256) || p.Cy % p.BN != 0) return -21;
   if (p.ntaps < 1 || p.ntaps > SGGAN_MAX_TAPS || p.ksplit < 1) return -22;
   L->p = p;
   L->stages = stages_for(p.BN);
   L->tmem_cols = tmem_cols_for(p.BN);
   L->smem = size_t(L->stages) * (kABytes + p.BN * 128) + 1024;
-  L->grid_x = (p.Cx / 128) * p.ntaps;
+  L->grid_x = (p.x_pair ? 1 : p.Cx / 128) * p.ntaps;
   L->grid_y = p.Cy / p.BN;
   L->grid_z = p.ksplit;
-  int r = make_tmap_bf16_3d(&L->tmX, p.X, p.Cx, p.x_frame_pix, p.B, uint64_t(p.Cx) * 2,
-                            uint64_t(p.x_frame_pix) * p.Cx * 2, 64, 64);
+  int r = make_tmap_bf16_3d(&L->tmX, p.X, p.Cx, p.x_frame_pix, p.B, uint64_t(p.x_row_stride) * 2,
+                            uint64_t(p.x_frame_pix) * p.x_row_stride * 2, 64, 64);
   if (r) return -1000 - r;
-  r = make_tmap_bf16_3d(&L->tmY, p.Y, p.Cy, p.y_frame_pix, p.B, uint64_t(p.Cy) * 2,
-                        uint64_t(p.y_frame_pix) * p.Cy * 2, 64, 64);
+  r = make_tmap_bf16_3d(&L->tmY, p.Y, p.Cy, p.y_frame_pix, p.B, uint64_t(p.y_row_stride) * 2,
+                        uint64_t(p.y_frame_pix) * p.y_row_stride * 2, 64, 64);
   if (r) return -2000 - r;
   static bool attr_set = false;
   if (!attr_set) {

@@ -1,0 +1,110 @@
+// engine.h -- host-side plan of the SG-GAN step: layer geometry, frame layouts, workspace carving
+// and the launch sequences for generator / discriminator forward, both backward passes and Adam.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sggan.h"
+#include "conv_gemm_tc.h"
+#include "glue.h"
+
+namespace sggan {
+
+enum LayerType { LT_S1 = 0, LT_S2 = 1, LT_DECONV = 2, LT_WIN_C1 = 3, LT_OUT7 = 4, LT_WIN_H0 = 5 };
+enum PadMode { PAD_VALID = 0, PAD_ZERO = 1, PAD_REFLECT = 2 };
+
+struct TensorInfo {
+  int64_t offset, numel;
+  int rank;
+  int64_t shape[4];
+};
+
+struct Layer {
+  LayerType type;
+  int k;
+  PadMode pad;
+  int Cin, Cout;  // logical channels
+  int Hin, Win, Hout, Wout;
+  bool has_norm;
+  int act;  // activation after the norm (glue) or in the conv epilogue (no norm)
+  float alpha;
+  int nb, nbv;                // forward batch, backward (virtual) batch
+  int ti_w, ti_b, ti_g, ti_be;  // tensor indices inside the net (-1 if absent)
+  int P;                      // shared pitch of the input frame and the output-gradient frame
+  int CoutK;                  // Cout padded to a multiple of 64 (channels of the dY frame)
+  int CoutN;                  // rows per weight slab in the forward GEMM
+  int CinN;                   // rows per weight slab in the dgrad GEMM
+  FrameMap xmap, dymap;
+  sg_bf16 *X, *Y, *dY;
+  void* dX;  // bf16 except h0 (fp32)
+  float* Yf32;
+  int dxH, dxW, dx_oy, dx_ox, dx_fold, dx_f32;
+  float *stats, *bsums;
+  sg_bf16 *Wf, *Wd;
+  PackParams packf, packd;
+  float* wscratch;
+  int wscratch_elems;
+  int unpack_mode;
+  std::vector<ConvGemmLaunch> fwd, dgrad;
+  std::vector<WgradLaunch> wgrad;
+};
+
+struct Net {
+  std::vector<Layer> L;
+  std::vector<TensorInfo> T;
+  int64_t nparams;
+  float *p, *g, *m, *v;
+};
+
+struct Arena {
+  uint8_t* base;
+  size_t off;
+  void* take(size_t bytes) {
+    off = (off + 255) & ~size_t(255);
+    void* r = base ? base + off : nullptr;
+    off += bytes;
+    return r;
+  }
+};
+
+struct Engine {
+  sggan_config cfg;
+  cudaStream_t st;
+  bool dry;
+  Net G, D;
+  int Hd, Wd, Ho, Wo;  // D logit grid and broadcast output grid
+  // misc buffers
+  float *fake, *h4, *logits, *loss, *dD, *edge_w, *dGl;
+  sg_bf16* resG[2];
+  uint8_t *zero_begin, *zero_end;
+  int64_t step;
+  int nlaunch;
+  bool weights_ready;
+  std::string err;
+
+  int build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t stream, bool dry_run, size_t* need);
+  int pack_weights(int net);
+  int gen_forward(const float* real_A, float* fake_out);
+  int disc_forward_2b(const float* real_img, const float* fake_img, int nimg_each);
+  int disc_forward_user(const float* x, const float* mask, float* logits_out);
+  int step_fwd_bwd_d(const float* real_A, const float* seg_A, const float* mask, float* losses_out);
+  int step_bwd_g();
+  int step_adam(int net);
+
+ private:
+  int build_net_g();
+  int build_net_d();
+  void alloc_and_prepare(Net& n, Arena& a, bool zero_part);
+  int prepare_layer(Net& n, int li);
+  int run_conv_list(const std::vector<ConvGemmLaunch>& v);
+  int run_wgrad(Layer& l, Net& n);
+  void in_apply(Net& n, int li, sg_bf16* dst, const FrameMap& dmap, const sg_bf16* res, const FrameMap* rmap);
+  void in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb_act, int act_wrap, int nb_param);
+  GradSrc dx_src(const Layer& l) const;
+  const float *real_A_, *seg_A_, *mask_;
+  float* losses_out_;
+};
+
+}  // namespace sggan

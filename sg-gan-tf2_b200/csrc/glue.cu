@@ -1,0 +1,742 @@
+// glue.cu -- the HBM-bound kernels around the tensor-core convolutions.
+//
+// Everything between two convolutions of the reference graph is one pass here: instance norm
+// (tfa.layers.InstanceNormalization, module.py:212...), its activation (module.py:213,285...),
+// the residual add (module.py:217), and the padding the next convolution wants (tf.pad REFLECT,
+// module.py:210,214,230,262; Keras 'same' zero padding; the 2x2 phase split a stride-2 layer
+// reads) are fused into a single read of the raw conv output and a single write of the next
+// frame.  All accesses are 128-bit (8 bf16 channels per thread), NHWC, coalesced along C.
+#include "glue.h"
+
+#include <cuda_bf16.h>
+#include <math.h>
+
+namespace sggan {
+
+// ------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ void ld_bf16x8(const sg_bf16* p, float* f) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void st_bf16x8(sg_bf16* p, const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float act_fwd(float v, int act, float a) {
+  if (act == SG_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == SG_ACT_LRELU) return v > 0.f ? v : a * v;
+  if (act == SG_ACT_TANH) return tanhf(v);
+  return v;
+}
+__device__ __forceinline__ float act_grad(float zpre, int act, float a) {
+  if (act == SG_ACT_RELU) return zpre > 0.f ? 1.f : 0.f;
+  if (act == SG_ACT_LRELU) return zpre > 0.f ? 1.f : a;
+  return 1.f;
+}
+// Rows (or columns) that logical index i occupies in a reflect-padded plane: itself, plus its
+// mirror images in the border of width p.
+__device__ __forceinline__ int reflect_set(int i, int n, int p, int* out) {
+  int k = 0;
+  out[k++] = i;
+  if (p > 0) {
+    if (i >= 1 && i <= p) out[k++] = -i;
+    if (i >= n - 1 - p && i <= n - 2) out[k++] = 2 * (n - 1) - i;
+  }
+  return k;
+}
+__device__ __forceinline__ void write_frame8(sg_bf16* dst, const FrameMap& m, int b, int i, int j, int c0,
+                                             const float* v) {
+  sg_bf16* base = dst + int64_t(b) * m.frame_pix * m.C + c0;
+  if (m.kind == 0 && m.reflect > 0) {
+    int rr[3], cc[3];
+    const int nr = reflect_set(i, m.H, m.reflect, rr), nc = reflect_set(j, m.W, m.reflect, cc);
+    for (int a = 0; a < nr; ++a)
+      for (int q = 0; q < nc; ++q) st_bf16x8(base + frame_pixel(m, rr[a], cc[q]) * m.C, v);
+  } else {
+    st_bf16x8(base + frame_pixel(m, i, j) * m.C, v);
+  }
+}
+// acc[0..8) += gradient source at logical (i, j), channels c0..c0+7 (folding reflected borders back)
+__device__ __forceinline__ void grad_read8(const GradSrc& g, int b, int i, int j, int H, int W, int C, int c0,
+                                           float* acc) {
+  if (g.ptr == nullptr) return;
+  int rr[3], cc[3];
+  const int nr = reflect_set(i, H, g.fold, rr), nc = reflect_set(j, W, g.fold, cc);
+  for (int a = 0; a < nr; ++a)
+    for (int q = 0; q < nc; ++q) {
+      const int64_t idx = ((int64_t(b) * g.Hs + (rr[a] + g.oy)) * g.Ws + (cc[q] + g.ox)) * C + c0;
+      if (g.f32) {
+        const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.ptr) + idx);
+        const float4 u0 = s[0], u1 = s[1];
+        acc[0] += u0.x; acc[1] += u0.y; acc[2] += u0.z; acc[3] += u0.w;
+        acc[4] += u1.x; acc[5] += u1.y; acc[6] += u1.z; acc[7] += u1.w;
+      } else {
+        float t[8];
+        ld_bf16x8(reinterpret_cast<const sg_bf16*>(g.ptr) + idx, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += t[e];
+      }
+    }
+}
+
+constexpr int kGlueThreads = 256;
+static inline int pix_per_block_for(int HW, int B) {
+  // aim for >= ~4 waves of 148 SMs while keeping blocks reasonably fat
+  int ppb = 1024;
+  while (ppb > 64 && int64_t((HW + ppb - 1) / ppb) * B < 148 * 8) ppb >>= 1;
+  return ppb;
+}
+
+// ------------------------------------------------------------------------------------------ prep
+__global__ void prep_image3_kernel(const float* __restrict__ src, int B, int H, int W, sg_bf16* dst, FrameMap m,
+                                   int dst_b0) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t tot = int64_t(B) * H * W;
+  if (idx >= tot) return;
+  const int b = int(idx / (int64_t(H) * W));
+  const int r = int(idx - int64_t(b) * H * W);
+  const int i = r / W, j = r - i * W;
+  const float* s = src + idx * 3;
+  float v[8] = {s[0], s[1], s[2], 0.f, 0.f, 0.f, 0.f, 0.f};
+  write_frame8(dst, m, dst_b0 + b, i, j, 0, v);
+}
+void launch_prep_image3(const float* src, int B, int H, int W, sg_bf16* dst, const FrameMap& dmap, int dst_b0,
+                        cudaStream_t st) {
+  const int64_t tot = int64_t(B) * H * W;
+  prep_image3_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(src, B, H, W, dst, dmap, dst_b0);
+}
+
+__global__ void f32_to_frame_kernel(const float* __restrict__ src, int B, int H, int W, int C, sg_bf16* dst,
+                                    FrameMap m) {
+  const int C8 = C >> 3;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t tot = int64_t(B) * H * W * C8;
+  if (idx >= tot) return;
+  const int cg = int(idx % C8);
+  const int64_t pix = idx / C8;
+  const int b = int(pix / (int64_t(H) * W));
+  const int r = int(pix - int64_t(b) * H * W);
+  const int i = r / W, j = r - i * W;
+  const float* s = src + pix * C + cg * 8;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = s[e];
+  write_frame8(dst, m, b, i, j, cg * 8, v);
+}
+void launch_f32_to_frame(const float* src, int B, int H, int W, int C, sg_bf16* dst, const FrameMap& dmap,
+                         cudaStream_t st) {
+  const int64_t tot = int64_t(B) * H * W * (C / 8);
+  f32_to_frame_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(src, B, H, W, C, dst, dmap);
+}
+
+__global__ void bf16_to_f32_kernel(const sg_bf16* __restrict__ s, float* d, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(s)[i]);
+}
+void launch_bf16_to_f32(const sg_bf16* src, float* dst, int64_t n, cudaStream_t st) {
+  bf16_to_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ s, sg_bf16* d, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) reinterpret_cast<__nv_bfloat16*>(d)[i] = __float2bfloat16_rn(s[i]);
+}
+void launch_f32_to_bf16(const float* src, sg_bf16* dst, int64_t n, cudaStream_t st) {
+  f32_to_bf16_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+}
+__global__ void lrelu_kernel(const float* __restrict__ x, float* y, int64_t n, float leak) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaxf(x[i], leak * x[i]);
+}
+void launch_lrelu(const float* x, float* y, int64_t n, float leak, cudaStream_t st) {
+  lrelu_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(x, y, n, leak);
+}
+
+// ------------------------------------------------------------------------------------------ IN fwd
+__device__ __forceinline__ void in_coeffs(const float* stats, const float* gamma, const float* beta, int b, int C,
+                                          int c0, float n, float eps, float* mean, float* rstd, float* scale,
+                                          float* shift) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = c0 + e;
+    if (stats != nullptr) {
+      const float s1 = stats[(int64_t(b) * C + c) * 2], s2 = stats[(int64_t(b) * C + c) * 2 + 1];
+      const float mu = s1 / n;
+      const float var = fmaxf(s2 / n - mu * mu, 0.f);
+      mean[e] = mu;
+      rstd[e] = rsqrtf(var + eps);
+    } else {
+      mean[e] = 0.f;
+      rstd[e] = 1.f;
+    }
+    const float g = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    scale[e] = g * rstd[e];
+    shift[e] = be - mean[e] * scale[e];
+  }
+}
+
+__global__ void __launch_bounds__(kGlueThreads) in_apply_kernel(const InApplyParams p, const int ppb) {
+  const int b = blockIdx.y;
+  const int C8 = p.C >> 3;
+  const int cg = threadIdx.x % C8, lp = threadIdx.x / C8, ppi = kGlueThreads / C8;
+  const int c0 = cg * 8, HW = p.H * p.W;
+  float mean[8], rstd[8], scale[8], shift[8];
+  in_coeffs(p.stats, p.gamma, p.beta, b, p.C, c0, float(HW), p.eps, mean, rstd, scale, shift);
+  const int pix0 = blockIdx.x * ppb, pix1 = min(HW, pix0 + ppb);
+  for (int pix = pix0 + lp; pix < pix1; pix += ppi) {
+    const int i = pix / p.W, j = pix - i * p.W;
+    float y[8];
+    ld_bf16x8(p.Y + (int64_t(b) * HW + pix) * p.C + c0, y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) y[e] = act_fwd(fmaf(y[e], scale[e], shift[e]), p.act, p.act_alpha);
+    if (p.res != nullptr) {
+      float r[8];
+      ld_bf16x8(p.res + (int64_t(b) * p.rmap.frame_pix + frame_pixel(p.rmap, i, j)) * p.rmap.C + c0, r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] += r[e];
+    }
+    write_frame8(p.dst, p.dmap, b, i, j, c0, y);
+  }
+}
+void launch_in_apply(const InApplyParams& p, cudaStream_t st) {
+  const int HW = p.H * p.W, ppb = pix_per_block_for(HW, p.B);
+  dim3 grid((HW + ppb - 1) / ppb, p.B);
+  in_apply_kernel<<<grid, kGlueThreads, 0, st>>>(p, ppb);
+}
+
+__global__ void __launch_bounds__(kGlueThreads) in_stats_kernel(const sg_bf16* __restrict__ y, int HW, int C,
+                                                                float* stats, int ppb) {
+  extern __shared__ float sred[];
+  const int b = blockIdx.y;
+  const int C8 = C >> 3;
+  const int cg = threadIdx.x % C8, lp = threadIdx.x / C8, ppi = kGlueThreads / C8;
+  for (int t = threadIdx.x; t < 2 * C; t += kGlueThreads) sred[t] = 0.f;
+  __syncthreads();
+  float a1[8] = {0}, a2[8] = {0};
+  const int pix0 = blockIdx.x * ppb, pix1 = min(HW, pix0 + ppb);
+  for (int pix = pix0 + lp; pix < pix1; pix += ppi) {
+    float v[8];
+    ld_bf16x8(y + (int64_t(b) * HW + pix) * C + cg * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      a1[e] += v[e];
+      a2[e] += v[e] * v[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    atomicAdd(&sred[(cg * 8 + e) * 2], a1[e]);
+    atomicAdd(&sred[(cg * 8 + e) * 2 + 1], a2[e]);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 2 * C; t += kGlueThreads) atomicAdd(stats + int64_t(b) * C * 2 + t, sred[t]);
+}
+void launch_in_stats(const sg_bf16* y, int B, int HW, int C, float* stats, cudaStream_t st) {
+  const int ppb = pix_per_block_for(HW, B);
+  dim3 grid((HW + ppb - 1) / ppb, B);
+  in_stats_kernel<<<grid, kGlueThreads, 2 * C * sizeof(float), st>>>(y, HW, C, stats, ppb);
+}
+
+// ------------------------------------------------------------------------------------------ IN bwd
+template <bool kApply>
+__global__ void __launch_bounds__(kGlueThreads) in_bwd_kernel(const InBwdParams p, const int ppb) {
+  extern __shared__ float sred[];
+  const int b = blockIdx.y;
+  const int ba = b < p.nb_act ? b : b - p.act_wrap;
+  const int C8 = p.C >> 3;
+  const int cg = threadIdx.x % C8, lp = threadIdx.x / C8, ppi = kGlueThreads / C8;
+  const int c0 = cg * 8, HW = p.H * p.W;
+  const float n = float(HW);
+  float mean[8], rstd[8], scale[8], shift[8];
+  in_coeffs(p.stats, p.gamma, p.beta, ba, p.C, c0, n, p.eps, mean, rstd, scale, shift);
+  float m1[8], m2[8], a1[8], a2[8];
+  if (kApply) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      m1[e] = p.sums[(int64_t(b) * p.C + c0 + e) * 2] / n;
+      m2[e] = p.sums[(int64_t(b) * p.C + c0 + e) * 2 + 1] / n;
+    }
+  } else {
+    for (int t = threadIdx.x; t < 2 * p.C; t += kGlueThreads) sred[t] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.f;
+  }
+  const int pix0 = blockIdx.x * ppb, pix1 = min(HW, pix0 + ppb);
+  for (int pix = pix0 + lp; pix < pix1; pix += ppi) {
+    const int i = pix / p.W, j = pix - i * p.W;
+    float y[8], d[8];
+    ld_bf16x8(p.Y + (int64_t(ba) * HW + pix) * p.C + c0, y);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = 0.f;
+    grad_read8(p.g1, b, i, j, p.H, p.W, p.C, c0, d);
+    grad_read8(p.g2, b, i, j, p.H, p.W, p.C, c0, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float xh = (y[e] - mean[e]) * rstd[e];
+      const float dz = d[e] * act_grad(fmaf(y[e], scale[e], shift[e]), p.act, p.act_alpha);
+      if (kApply) {
+        d[e] = scale[e] * (dz - m1[e] - xh * m2[e]);
+      } else {
+        a1[e] += dz;
+        a2[e] += dz * xh;
+      }
+    }
+    if (kApply) write_frame8(p.dst, p.dmap, b, i, j, c0, d);
+  }
+  if (!kApply) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&sred[(c0 + e) * 2], a1[e]);
+      atomicAdd(&sred[(c0 + e) * 2 + 1], a2[e]);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 2 * p.C; t += kGlueThreads) atomicAdd(p.sums + int64_t(b) * p.C * 2 + t, sred[t]);
+  }
+}
+void launch_in_bwd_reduce(const InBwdParams& p, cudaStream_t st) {
+  const int HW = p.H * p.W, ppb = pix_per_block_for(HW, p.B);
+  dim3 grid((HW + ppb - 1) / ppb, p.B);
+  in_bwd_kernel<false><<<grid, kGlueThreads, 2 * p.C * sizeof(float), st>>>(p, ppb);
+}
+void launch_in_bwd_apply(const InBwdParams& p, cudaStream_t st) {
+  const int HW = p.H * p.W, ppb = pix_per_block_for(HW, p.B);
+  dim3 grid((HW + ppb - 1) / ppb, p.B);
+  in_bwd_kernel<true><<<grid, kGlueThreads, 0, st>>>(p, ppb);
+}
+
+__global__ void in_param_grad_kernel(const float* __restrict__ sums, int nb, int C, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float g = 0.f, be = 0.f;
+  for (int b = 0; b < nb; ++b) {
+    be += sums[(int64_t(b) * C + c) * 2];
+    g += sums[(int64_t(b) * C + c) * 2 + 1];
+  }
+  dgamma[c] = g;
+  dbeta[c] = be;
+}
+void launch_in_param_grad(const float* sums, int nb, int C, float* dgamma, float* dbeta, cudaStream_t st) {
+  in_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, nb, C, dgamma, dbeta);
+}
+
+// ------------------------------------------------------------------------------------------ gather
+__global__ void __launch_bounds__(kGlueThreads) grad_gather_kernel(const GradSrc g1, const GradSrc g2, int H, int W,
+                                                                    int C, sg_bf16* out, int ppb) {
+  const int b = blockIdx.y;
+  const int C8 = C >> 3;
+  const int cg = threadIdx.x % C8, lp = threadIdx.x / C8, ppi = kGlueThreads / C8;
+  const int HW = H * W;
+  const int pix0 = blockIdx.x * ppb, pix1 = min(HW, pix0 + ppb);
+  for (int pix = pix0 + lp; pix < pix1; pix += ppi) {
+    const int i = pix / W, j = pix - i * W;
+    float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    grad_read8(g1, b, i, j, H, W, C, cg * 8, d);
+    grad_read8(g2, b, i, j, H, W, C, cg * 8, d);
+    st_bf16x8(out + (int64_t(b) * HW + pix) * C + cg * 8, d);
+  }
+}
+void launch_grad_gather(const GradSrc& g1, const GradSrc& g2, int B, int H, int W, int C, sg_bf16* out,
+                        cudaStream_t st) {
+  const int HW = H * W, ppb = pix_per_block_for(HW, B);
+  dim3 grid((HW + ppb - 1) / ppb, B);
+  grad_gather_kernel<<<grid, kGlueThreads, 0, st>>>(g1, g2, H, W, C, out, ppb);
+}
+
+__global__ void __launch_bounds__(kGlueThreads) act_bwd_kernel(const ActBwdParams p, int ppb) {
+  extern __shared__ float sred[];
+  const int b = blockIdx.y;
+  const int ba = b < p.nb_act ? b : b - p.act_wrap;
+  const int C8 = p.C >> 3;
+  const int cg = threadIdx.x % C8, lp = threadIdx.x / C8, ppi = kGlueThreads / C8;
+  const int c0 = cg * 8, HW = p.H * p.W;
+  for (int t = threadIdx.x; t < p.C; t += kGlueThreads) sred[t] = 0.f;
+  __syncthreads();
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int pix0 = blockIdx.x * ppb, pix1 = min(HW, pix0 + ppb);
+  for (int pix = pix0 + lp; pix < pix1; pix += ppi) {
+    const int i = pix / p.W, j = pix - i * p.W;
+    float z[8], d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    ld_bf16x8(p.Z + (int64_t(ba) * p.zmap.frame_pix + frame_pixel(p.zmap, i, j)) * p.zmap.C + c0, z);
+    grad_read8(p.g, b, i, j, p.H, p.W, p.C, c0, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      d[e] = z[e] > 0.f ? d[e] : p.alpha * d[e];
+      acc[e] += d[e];
+    }
+    write_frame8(p.dst, p.dmap, b, i, j, c0, d);
+  }
+  if (p.dbias != nullptr && b < p.nb_bias) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(&sred[c0 + e], acc[e]);
+  }
+  __syncthreads();
+  if (p.dbias != nullptr && b < p.nb_bias)
+    for (int t = threadIdx.x; t < p.C; t += kGlueThreads) atomicAdd(p.dbias + t, sred[t]);
+}
+void launch_act_bwd(const ActBwdParams& p, cudaStream_t st) {
+  const int HW = p.H * p.W, ppb = pix_per_block_for(HW, p.B);
+  dim3 grid((HW + ppb - 1) / ppb, p.B);
+  act_bwd_kernel<<<grid, kGlueThreads, p.C * sizeof(float), st>>>(p, ppb);
+}
+
+// ------------------------------------------------------------------------------------------ losses
+__device__ __forceinline__ float softplus_negabs(float x) { return log1pf(expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ float block_sum(float v, float* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = l < (blockDim.x >> 5) ? sh[l] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  }
+  return r;  // valid in warp 0
+}
+
+// One block: the logits are KB-sized (B x 5 x 13 at 256x512).
+__global__ void __launch_bounds__(256) disc_loss_kernel(const DiscLossParams p) {
+  __shared__ float sh[32];
+  extern __shared__ float sbias[];
+  const int Ho = max(p.Hd, p.hm), Wo = max(p.Wd, p.wm);
+  const int B2 = 2 * p.B, npos = Ho * Wo;
+  const float N = float(p.B) * npos;
+  for (int t = threadIdx.x; t < p.Cs; t += blockDim.x) sbias[t] = 0.f;
+  // 1. masked logits
+  for (int idx = threadIdx.x; idx < B2 * npos; idx += blockDim.x) {
+    const int b = idx / npos, r = idx - b * npos, I = r / Wo, J = r - I * Wo;
+    const int ih = p.Hd == 1 ? 0 : I, jh = p.Wd == 1 ? 0 : J, im = p.hm == 1 ? 0 : I, jm = p.wm == 1 ? 0 : J;
+    const float* h = p.h4 + ((int64_t(b) * p.Hd + ih) * p.Wd + jh) * p.Cs;
+    const float* mk = p.mask + ((int64_t(b % p.B) * p.hm + im) * p.wm + jm) * p.Cs;
+    float s = 0.f;
+    for (int c = 0; c < p.Cs; ++c) s += h[c] * mk[c];
+    p.logits[idx] = s;
+  }
+  __syncthreads();
+  // 2. losses
+  float lg = 0.f, ld = 0.f;
+  for (int idx = threadIdx.x; idx < B2 * npos; idx += blockDim.x) {
+    const int b = idx / npos;
+    const float x = p.logits[idx];
+    if (p.lsgan) {
+      if (b < p.B) ld += (x - 1.f) * (x - 1.f);
+      else { ld += x * x; lg += (x - 1.f) * (x - 1.f); }
+    } else {
+      const float sp = softplus_negabs(x), mx = fmaxf(x, 0.f);
+      if (b < p.B) ld += mx - x + sp;           // label 1
+      else { ld += mx + sp; lg += mx - x + sp; }  // fake: label 0 for D, label 1 for G
+    }
+  }
+  lg = block_sum(lg, sh);
+  ld = block_sum(ld, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(p.loss + 0, lg / N);
+    atomicAdd(p.loss + 1, ld * p.disc_scale / N);
+  }
+  // 3. d logits -> d h4 (3B virtual images) and bias gradient
+  const int tot = 3 * p.B * p.Hd * p.Wd * p.Cs;
+  for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+    const int c = idx % p.Cs;
+    int r = idx / p.Cs;
+    const int jh = r % p.Wd;
+    r /= p.Wd;
+    const int ih = r % p.Hd, v = r / p.Hd;
+    const int bs = v < B2 ? v : v - p.B;
+    const float label = (v < p.B || v >= B2) ? 1.f : 0.f;
+    const float sc = (v < B2 ? p.disc_scale : 1.f) / N;
+    const int I0 = p.Hd == 1 ? 0 : ih, I1 = p.Hd == 1 ? Ho : ih + 1;
+    const int J0 = p.Wd == 1 ? 0 : jh, J1 = p.Wd == 1 ? Wo : jh + 1;
+    float g = 0.f;
+    for (int I = I0; I < I1; ++I)
+      for (int J = J0; J < J1; ++J) {
+        const int im = p.hm == 1 ? 0 : I, jm = p.wm == 1 ? 0 : J;
+        const float x = p.logits[(bs * Ho + I) * Wo + J];
+        const float dl = (p.lsgan ? 2.f * (x - label) : (sigmoidf(x) - label)) * sc;
+        g += dl * p.mask[((int64_t(bs % p.B) * p.hm + im) * p.wm + jm) * p.Cs + c];
+      }
+    reinterpret_cast<__nv_bfloat16*>(p.dst)[(int64_t(v) * p.dmap.frame_pix + frame_pixel(p.dmap, ih, jh)) * p.dmap.C + c] =
+        __float2bfloat16_rn(g);
+    if (v < B2) atomicAdd(&sbias[c], g);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < p.Cs; t += blockDim.x) atomicAdd(p.dbias + t, sbias[t]);
+}
+void launch_disc_loss(const DiscLossParams& p, cudaStream_t st) {
+  disc_loss_kernel<<<1, 256, p.Cs * sizeof(float), st>>>(p);
+}
+
+__global__ void mask_reduce_kernel(const float* __restrict__ x, const float* __restrict__ mask, int B, int Hd, int Wd,
+                                   int hm, int wm, int Cs, float* out) {
+  const int Ho = max(Hd, hm), Wo = max(Wd, wm);
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= int64_t(B) * Ho * Wo) return;
+  const int b = int(idx / (Ho * Wo)), r = int(idx - int64_t(b) * Ho * Wo), I = r / Wo, J = r - I * Wo;
+  const int ih = Hd == 1 ? 0 : I, jh = Wd == 1 ? 0 : J, im = hm == 1 ? 0 : I, jm = wm == 1 ? 0 : J;
+  const float* h = x + ((int64_t(b) * Hd + ih) * Wd + jh) * Cs;
+  const float* mk = mask + ((int64_t(b) * hm + im) * wm + jm) * Cs;
+  float s = 0.f;
+  for (int c = 0; c < Cs; ++c) s += h[c] * mk[c];
+  out[idx] = s;
+}
+void launch_mask_reduce(const float* x, const float* mask, int B, int Hd, int Wd, int hm, int wm, int Cs, float* out,
+                        cudaStream_t st) {
+  const int Ho = Hd > hm ? Hd : hm, Wo = Wd > wm ? Wd : wm;
+  const int64_t tot = int64_t(B) * Ho * Wo;
+  mask_reduce_kernel<<<unsigned((tot + 127) / 128), 128, 0, st>>>(x, mask, B, Hd, Wd, hm, wm, Cs, out);
+}
+
+__global__ void __launch_bounds__(256) fake_grad_kernel(const FakeGradParams p) {
+  __shared__ float sh[32];
+  const int64_t tot = int64_t(p.B) * p.H * p.W;
+  const float inv_n = 1.f / (float(tot) * 3.f);
+  float l1 = 0.f, db[3] = {0.f, 0.f, 0.f};
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < tot; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int b = int(idx / (int64_t(p.H) * p.W));
+    const int r = int(idx - int64_t(b) * p.H * p.W);
+    const int i = r / p.W, j = r - i * p.W;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float f = p.fake[idx * 3 + c], t = p.target[idx * 3 + c];
+      const float diff = f - t;
+      l1 += fabsf(diff);
+      float g = p.l1_weight * inv_n * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
+      if (p.dD != nullptr) g += p.dD[idx * 3 + c];
+      if (p.dG != nullptr) g += p.dG[idx * 3 + c];
+      g *= (1.f - f * f);
+      v[c] = g;
+      db[c] += g;
+    }
+    write_frame8(p.dst, p.dmap, b, i, j, 0, v);
+  }
+  l1 = block_sum(l1, sh);
+  if (threadIdx.x == 0) atomicAdd(p.loss + 2, l1);
+  for (int c = 0; c < 3; ++c) {
+    const float s = block_sum(db[c], sh);
+    if (threadIdx.x == 0) atomicAdd(p.dbias + c, s);
+  }
+}
+void launch_fake_grad(const FakeGradParams& p, cudaStream_t st) {
+  const int64_t tot = int64_t(p.B) * p.H * p.W;
+  int blocks = int((tot + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  fake_grad_kernel<<<blocks, 256, 0, st>>>(p);
+}
+
+__global__ void finalize_losses_kernel(const float* loss, float l1_weight, float n_l1, float lg_weight, float* out) {
+  out[0] = loss[0] + l1_weight * loss[2] / n_l1 + lg_weight * loss[3];
+  out[1] = loss[1];
+}
+void launch_finalize_losses(const float* loss, float l1_weight, float n_l1, float lg_weight, float* out,
+                            cudaStream_t st) {
+  finalize_losses_kernel<<<1, 1, 0, st>>>(loss, l1_weight, n_l1, lg_weight, out);
+}
+
+// ---- SG-GAN criteria ------------------------------------------------------------------------
+__device__ __forceinline__ int reflect_idx(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i); }
+
+__global__ void seg_edge_weight_kernel(const float* __restrict__ seg, int B, int H, int W, float* w) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= int64_t(B) * H * W) return;
+  const int b = int(idx / (int64_t(H) * W));
+  const int r = int(idx - int64_t(b) * H * W), i = r / W, j = r - i * W;
+  const float* s = seg + int64_t(b) * H * W * 3;
+  float acc = 0.f;
+  const int jl = reflect_idx(j - 1, W), jr = reflect_idx(j + 1, W), iu = reflect_idx(i - 1, H), id = reflect_idx(i + 1, H);
+  for (int c = 0; c < 3; ++c) {
+    acc += fabsf(s[(int64_t(i) * W + jr) * 3 + c] - s[(int64_t(i) * W + jl) * 3 + c]);
+    acc += fabsf(s[(int64_t(id) * W + j) * 3 + c] - s[(int64_t(iu) * W + j) * 3 + c]);
+  }
+  w[idx] = acc > 0.f ? 1.f : 0.f;
+}
+void launch_seg_edge_weight(const float* seg, int B, int H, int W, float* weight, cudaStream_t st) {
+  const int64_t tot = int64_t(B) * H * W;
+  seg_edge_weight_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(seg, B, H, W, weight);
+}
+
+// Sobel responses (x, y) of channel c at (i, j) with SAME zero padding (module.py:325-334).
+__device__ __forceinline__ void sobel_at(const float* img, int H, int W, int i, int j, int c, float* gx, float* gy) {
+  float v[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int ii = i + a - 1, jj = j + q - 1;
+      v[a][q] = (ii >= 0 && ii < H && jj >= 0 && jj < W) ? img[(int64_t(ii) * W + jj) * 3 + c] : 0.f;
+    }
+  *gx = (v[0][2] - v[0][0]) + 2.f * (v[1][2] - v[1][0]) + (v[2][2] - v[2][0]);
+  *gy = (v[2][0] - v[0][0]) + 2.f * (v[2][1] - v[0][1]) + (v[2][2] - v[0][2]);
+}
+__device__ __forceinline__ float sgnf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+__global__ void __launch_bounds__(256) gradloss_kernel(const float* __restrict__ in, const float* __restrict__ tgt,
+                                                       const float* __restrict__ wgt, int B, int H, int W,
+                                                       float scale, float* loss_slot, float* d_in) {
+  __shared__ float sh[32];
+  const int64_t tot = int64_t(B) * H * W;
+  const float inv = 1.f / (float(tot) * 6.f);
+  const float KX[3][3] = {{-1, 0, 1}, {-2, 0, 2}, {-1, 0, 1}};
+  const float KY[3][3] = {{-1, -2, -1}, {0, 0, 0}, {1, 2, 1}};
+  float lsum = 0.f;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < tot; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int b = int(idx / (int64_t(H) * W));
+    const int r = int(idx - int64_t(b) * H * W), u = r / W, v = r - u * W;
+    const float* ib = in + int64_t(b) * H * W * 3;
+    const float* tb = tgt + int64_t(b) * H * W * 3;
+    const float* wb = wgt + int64_t(b) * H * W;
+    float g[3] = {0.f, 0.f, 0.f};
+    for (int a = 0; a < 3; ++a)
+      for (int q = 0; q < 3; ++q) {
+        // output position (i, j) whose 3x3 window touches (u, v) through tap (a, q)
+        const int i = u - (a - 1), j = v - (q - 1);
+        if (i < 0 || i >= H || j < 0 || j >= W) continue;
+        const float w = wb[int64_t(i) * W + j];
+        for (int c = 0; c < 3; ++c) {
+          float gxi, gyi, gxt, gyt;
+          sobel_at(ib, H, W, i, j, c, &gxi, &gyi);
+          sobel_at(tb, H, W, i, j, c, &gxt, &gyt);
+          const float ex = fabsf(gxi) - fabsf(gxt), ey = fabsf(gyi) - fabsf(gyt);
+          if (a == 1 && q == 1) lsum += w * (fabsf(ex) + fabsf(ey));
+          if (w != 0.f) g[c] += w * (sgnf(ex) * sgnf(gxi) * KX[a][q] + sgnf(ey) * sgnf(gyi) * KY[a][q]);
+        }
+      }
+    if (d_in != nullptr)
+      for (int c = 0; c < 3; ++c) d_in[idx * 3 + c] = g[c] * inv * scale;
+  }
+  lsum = block_sum(lsum, sh);
+  if (threadIdx.x == 0 && loss_slot != nullptr) atomicAdd(loss_slot, lsum * inv);
+}
+void launch_gradloss(const float* in, const float* target, const float* weight, int B, int H, int W, float scale,
+                     float* loss_slot, float* d_in, cudaStream_t st) {
+  const int64_t tot = int64_t(B) * H * W;
+  int blocks = int((tot + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gradloss_kernel<<<blocks, 256, 0, st>>>(in, target, weight, B, H, W, scale, loss_slot, d_in);
+}
+
+__global__ void __launch_bounds__(256) criterion_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                        int64_t n, int mode, float* out) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float x = a[i], y = b[i];
+    if (mode == 0) s += fabsf(x - y);
+    else if (mode == 1) s += (x - y) * (x - y);
+    else s += fmaxf(x, 0.f) - x * y + softplus_negabs(x);
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s / float(n));
+}
+void launch_criterion(const float* a, const float* b, int64_t n, int mode, float* out, cudaStream_t st) {
+  int blocks = int((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cudaMemsetAsync(out, 0, sizeof(float), st);
+  criterion_kernel<<<blocks, 256, 0, st>>>(a, b, n, mode, out);
+}
+
+// ------------------------------------------------------------------------------------------ Adam
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                   float alpha_t, float beta1, float beta2, float eps, float gscale) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i],
+           vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float* P = &pp.x; float* M = &mm.x; float* V = &vv.x; const float* G = &gg.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ge = G[e] * gscale;
+      M[e] += (ge - M[e]) * (1.f - beta1);
+      V[e] += (ge * ge - V[e]) * (1.f - beta2);
+      P[e] -= alpha_t * M[e] / (sqrtf(V[e]) + eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  if (blockIdx.x == 0) {
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      const float ge = g[i] * gscale;
+      m[i] += (ge - m[i]) * (1.f - beta1);
+      v[i] += (ge * ge - v[i]) * (1.f - beta2);
+      p[i] -= alpha_t * m[i] / (sqrtf(v[i]) + eps);
+    }
+  }
+}
+void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float alpha_t, float beta1, float beta2,
+                 float eps, float gscale, cudaStream_t st) {
+  adam_kernel<<<148 * 8, 256, 0, st>>>(p, g, m, v, n, alpha_t, beta1, beta2, eps, gscale);
+}
+
+// ------------------------------------------------------------------------------------------ packing
+// Source layouts (Keras): conv kernel [KH][KW][Cin][Cout]; transposed-conv kernel [KH][KW][Cout][Cin]
+// where Cin is the layer INPUT channel count in both cases.  Destination: bf16 slabs [T][N][K].
+//  mode 0 conv fwd      t=(kh,kw)  n=co  k=ci
+//  mode 1 conv dgrad    t=(kh,kw)  n=ci  k=co
+//  mode 2 deconv fwd    t=(kh,kw)  n=co  k=ci
+//  mode 3 deconv dgrad  t=(kh,kw)  n=ci  k=co
+//  mode 4 window fwd, stride 1 (generator c1):   t=kh        n=co  k=q*8+ci, kw=q
+//  mode 5 window dgrad (generator output conv):  t=kh        n=ci  k=q*8+co, kw=KW-1-q
+//  mode 6 window fwd, stride 2 (disc. h0):       t=kh*2+bp   n=co  k=q*8+ci, kw=2q+bp
+__global__ void pack_weights_kernel(const PackParams p) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t tot = int64_t(p.T) * p.N * p.K;
+  if (idx >= tot) return;
+  const int k = int(idx % p.K), n = int((idx / p.K) % p.N), t = int(idx / (int64_t(p.K) * p.N));
+  float v = 0.f;
+  const int Ci = p.Cin, Co = p.Cout;
+  switch (p.mode) {
+    case 0: if (n < Co && k < Ci) v = p.src[(int64_t(t) * Ci + k) * Co + n]; break;
+    case 1: if (n < Ci && k < Co) v = p.src[(int64_t(t) * Ci + n) * Co + k]; break;
+    case 2: if (n < Co && k < Ci) v = p.src[(int64_t(t) * Co + n) * Ci + k]; break;
+    case 3: if (n < Ci && k < Co) v = p.src[(int64_t(t) * Co + k) * Ci + n]; break;
+    case 4: { const int q = k >> 3, ci = k & 7;
+      if (q < p.KW && ci < Ci && n < Co) v = p.src[((int64_t(t) * p.KW + q) * Ci + ci) * Co + n]; break; }
+    case 5: { const int q = k >> 3, co = k & 7;
+      if (q < p.KW && co < Co && n < Ci) v = p.src[((int64_t(t) * p.KW + (p.KW - 1 - q)) * Ci + n) * Co + co]; break; }
+    case 6: { const int kh = t >> 1, bp = t & 1, q = k >> 3, ci = k & 7, kw = 2 * q + bp;
+      if (kw < p.KW && ci < Ci && n < Co) v = p.src[((int64_t(kh) * p.KW + kw) * Ci + ci) * Co + n]; break; }
+  }
+  reinterpret_cast<__nv_bfloat16*>(p.dst)[idx] = __float2bfloat16_rn(v);
+}
+void launch_pack_weights(const PackParams& p, cudaStream_t st) {
+  const int64_t tot = int64_t(p.T) * p.N * p.K;
+  pack_weights_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(p);
+}
+
+// scratch [pair][128 rows][ncol] from the window wgrad launches -> Keras [KH][KW][Cin][Cout] (+=)
+//  mode 0 (c1):  row = h*64 + q*8 + ci, col = co            kh = 2*pair+h, kw = q
+//  mode 1 (out): row = h*64 + ci,       col = q*8 + co      kh = 2*pair+h, kw = KW-1-q
+//  mode 2 (h0):  row = h*64 + q*8 + ci, col = co            group = 2*pair+h = kh*2+bp, kw = 2q+bp
+__global__ void unpack_wgrad_kernel(const float* __restrict__ s, float* dW, int mode, int KH, int KW, int Cin, int Cout,
+                                    int ncol) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tot = KH * KW * Cin * Cout;
+  if (idx >= tot) return;
+  const int co = idx % Cout, ci = (idx / Cout) % Cin, kw = (idx / (Cout * Cin)) % KW, kh = idx / (Cout * Cin * KW);
+  int pair, row, col;
+  if (mode == 0) { pair = kh >> 1; row = (kh & 1) * 64 + kw * 8 + ci; col = co; }
+  else if (mode == 1) { pair = kh >> 1; row = (kh & 1) * 64 + ci; col = (KW - 1 - kw) * 8 + co; }
+  else { const int grp = kh * 2 + (kw & 1); pair = grp >> 1; row = (grp & 1) * 64 + (kw >> 1) * 8 + ci; col = co; }
+  dW[idx] += s[(int64_t(pair) * 128 + row) * ncol + col];
+}
+void launch_unpack_wgrad(const float* scratch, float* dW, int mode, int KH, int KW, int Cin, int Cout, int ncol,
+                         cudaStream_t st) {
+  const int tot = KH * KW * Cin * Cout;
+  unpack_wgrad_kernel<<<(tot + 255) / 256, 256, 0, st>>>(scratch, dW, mode, KH, KW, Cin, Cout, ncol);
+}
+
+}  // namespace sggan

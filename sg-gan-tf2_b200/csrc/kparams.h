@@ -1,7 +1,6 @@
-// kparams.h -- plain-old-data launch parameters shared by the CUDA kernels (csrc/*.cu) and by
-// the CPU emulation of the same kernels that the tests use to check the host-side planning
-// (tests/emu).  No CUDA types here: pointers are raw addresses in whichever memory the build
-// targets.
+// kparams.h -- plain-old-data launch parameters of every kernel in the SG-GAN step.
+// No CUDA types: pointers are raw device addresses, so the host-side planner (engine.cu) and
+// the tests can fill and inspect them without a GPU.
 #pragma once
 #include <stdint.h>
 
@@ -9,68 +8,156 @@
 
 typedef uint16_t sg_bf16;  // raw bfloat16 bits
 
-// Activation codes used by epilogues / glue kernels.
 enum { SG_ACT_NONE = 0, SG_ACT_RELU = 1, SG_ACT_LRELU = 2, SG_ACT_TANH = 3 };
 
 // ---------------------------------------------------------------------------------------------
-// Implicit-GEMM convolution over "pitch-linearised frames".
+// Frames: the HBM layout of every activation / gradient that a convolution consumes.
 //
-// The input of a convolution lives in frames: image b occupies a_frame_pix pixels of Cin bf16
-// channels, rows have pitch P pixels and already contain whatever border (reflect / zero) the
-// convolution needs.  Output position m = i*P + j (i row, j column on the SAME pitch) reads, for
-// tap t, the input pixel m + tap_off[t]; hence every A tile of 128 consecutive m is one dense
-// [128 x 64ch] TMA box.  Columns j >= Wv and rows i >= Hv are pitch slack: computed, never
-// stored, excluded from the statistics.
+// A frame stores one H x W x C image per `frame_pix` pixels.  kind 0 is a single plane with
+// pitch P whose logical pixel (0,0) sits at row pt, column pl; everything outside the logical
+// image is border (zeros, or the reflection written by the producer when reflect > 0) or pitch
+// slack.  kind 1 holds the four 2x2 phases of the image as separate planes (plane_pix apart),
+// plane (a,b) containing pixels (2i+a, 2j+b) at (i+pt, j+pl) -- the layout a stride-2
+// convolution reads with unit stride.  Because producer and consumer share the pitch, tap
+// (kh,kw) of a convolution is a constant pixel offset: that is what lets one dense 2-D TMA box
+// feed the tensor cores with no im2col and no separate padding pass (tf.pad at
+// module.py:210,214,230,262 costs nothing here).
+struct FrameMap {
+  int64_t frame_pix;  // pixels per image
+  int C;              // channels stored per pixel
+  int H, W;           // logical size
+  int kind;           // 0 plane, 1 phase-split
+  int P;              // pitch in pixels
+  int pt, pl;         // origin inside the plane
+  int plane_pix;      // kind 1: pixels per phase plane
+  int reflect;        // kind 0: reflect border width the producer must write (0 = zero border)
+};
+
+#if defined(__CUDACC__)
+#define SG_HD __host__ __device__ __forceinline__
+#else
+#define SG_HD inline
+#endif
+SG_HD int64_t frame_pixel(const FrameMap& f, int i, int j) {
+  if (f.kind == 0) return int64_t(i + f.pt) * f.P + (j + f.pl);
+  return int64_t((i & 1) * 2 + (j & 1)) * f.plane_pix + int64_t((i >> 1) + f.pt) * f.P + ((j >> 1) + f.pl);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Implicit-GEMM convolution over pitch-linearised frames (conv_gemm_tc.cu).
 //
-//   out[b, i, j, n] = act( bias[n] + sum_t sum_c A[b, m + tap_off[t], c] * Wt[t, n, c] )
+//   acc[b, m, n] = sum_t sum_c A[b, m + tap_off[t], c] * Wt[tap_w[t], n, c]        m = i*P + j
+//   out[b, (i*o_scale+o_a, j*o_scale+o_b) via omap, n] = act(acc + bias[n])     (i < Hv, j < Wv)
 //
-// Strided / transposed convolutions reduce to this form by phase-splitting the frames (host
-// plan), so this one kernel serves conv fwd, dgrad and deconv.
+// "Channels" c are whatever 64-element rows the tensor map exposes: real channels (row stride =
+// Cin) or, for the 3-channel layers, a sliding window of 8 pixels x 8 padded channels (row
+// stride 8), which turns the kw taps of a 7x7 / 3x3 filter into K of one tap.
 struct ConvGemmParams {
-  const sg_bf16* A;     // frames [B][a_frame_pix][Cin]
-  int64_t a_frame_pix;  // pixels per frame (TMA zero-fills beyond)
-  int Cin;              // multiple of 64
+  const sg_bf16* A;
+  int64_t a_frame_pix;   // rows (pixels) per image visible to TMA
+  int64_t a_row_stride;  // elements between consecutive rows (= real channel count per pixel)
+  int Cin;               // K per tap, multiple of 64
   int B;
-  const sg_bf16* Wt;  // [ntaps][CoutPad][Cin]  (K-major rows)
-  int ntaps;
-  int CoutPad;  // rows per tap in Wt, multiple of BN
-  int Cout;     // valid output channels (n < Cout stored)
-  int BN;       // N tile: 32, 64, 128 or 256
+  const sg_bf16* Wt;  // [wt_taps][CoutPad][Cin]
+  int wt_taps;        // number of tap slabs in Wt
+  int ntaps;          // taps used by this launch
+  int CoutPad;        // rows per tap slab, multiple of BN
+  int Cout;           // valid output channels
+  int BN;             // N tile: 32, 64, 128, 256
   int tap_off[SGGAN_MAX_TAPS];
-  int M;       // linear output positions per image
-  int P;       // pitch used to decode m -> (i, j)
-  int Hv, Wv;  // valid rows / columns
-  // output addressing (elements): out + b*out_bstride + i*out_sy + j*out_sx + out_off + n
+  uint8_t tap_w[SGGAN_MAX_TAPS];  // slab index in Wt for tap t
+  int M;                          // linear output positions per image
+  int P;                          // pitch used to decode m -> (i, j)
+  int Hv, Wv;                     // valid rows / columns
   void* out;
-  int out_f32;  // 0: bf16 output, 1: fp32 output
-  int64_t out_bstride, out_sy, out_sx, out_off;
+  int out_f32;  // 0 bf16, 1 fp32
+  FrameMap omap;
+  int o_scale, o_a, o_b;
   const float* bias;  // [Cout] or null
-  float* stats;       // [B][Cout][2] running (sum, sum of squares) of the fp32 result, or null
+  float* stats;       // [B][Cout][2] (sum, sum of squares) accumulated atomically, or null
   int act;
-  float act_alpha;  // leaky slope
+  float act_alpha;
 };
 
 // ---------------------------------------------------------------------------------------------
-// Weight gradient as an MN-major GEMM, K = pixels, split-K with fp32 atomics.
+// Weight gradient (wgrad_gemm_tc in conv_gemm_tc.cu): MN-major GEMM, K = pixels, split-K.
 //
-//   dW[t, x, y] += sum_b sum_{m < Mpix} X[b, m + x_off[t], x] * Y[b, m + y_off, y]
+//   dW[t, x, y] += sum_b sum_{m < Mpix} X[b, m + x_off[t], x] * Y[b, m + y_off[t], y]
 //
-// X (activation frames) takes the M role, Y (output-gradient frames) the N role; both share the
-// pitch so tap offsets are constants.  Y must be zero at slack positions.
+// X takes the M role (128-row tiles), Y the N role.  pair mode (x_pair != 0): the 128 M rows are
+// two 64-element windows of X taken at pixel offsets x_off[t] and x_off2[t] (used by the
+// 3-channel layers, whose real channel count is below the 128-row MMA shape).
 struct WgradParams {
   const sg_bf16* X;
-  int64_t x_frame_pix;
-  int Cx;  // multiple of 128
+  int64_t x_frame_pix, x_row_stride;
+  int Cx;  // multiple of 128 (64 in pair mode)
   const sg_bf16* Y;
-  int64_t y_frame_pix;
+  int64_t y_frame_pix, y_row_stride;
   int Cy;  // multiple of BN
-  int BN;  // 64, 128 or 256
+  int BN;  // 64, 128, 256
   int B;
   int ntaps;
   int x_off[SGGAN_MAX_TAPS];
-  int y_off;
-  int Mpix;  // linear positions per image covered (rounded up to 64 inside)
+  int x_off2[SGGAN_MAX_TAPS];
+  int y_off[SGGAN_MAX_TAPS];
+  int x_pair;
+  int nx_valid, ny_valid;  // rows / columns of the tile actually accumulated into dW
+  int Mpix;
   float* dW;
-  int64_t dw_tap_stride, dw_sx, dw_sy;  // element strides of dW for (tap, x channel, y channel)
-  int ksplit;                           // CTAs along the split-K (grid.z)
+  int64_t dw_tap_stride, dw_sx, dw_sy;
+  int ksplit;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Glue kernels (glue.cu)
+
+// Where a gradient w.r.t. a layer's (post-activation) output comes from: a plain [B][Hs][Ws][C]
+// buffer whose logical pixel (0,0) sits at (oy, ox); fold > 0 adds the reflected border back
+// (gradient of tf.pad REFLECT, Appendix A.4).
+struct GradSrc {
+  const void* ptr;  // null = absent
+  int f32;          // element type: 0 bf16, 1 fp32
+  int Hs, Ws;
+  int oy, ox;
+  int fold;
+};
+
+// Instance norm (+ activation, + residual) of a raw convolution output into the next frame.
+//   z = act(gamma * (y - mean) * rstd + beta) (+ res);   mean / var from stats (sum, sum^2).
+// tfa.layers.InstanceNormalization at module.py:212,216,233,...; Activation / LeakyReLU / `y + x`
+// at module.py:213,217,...
+struct InApplyParams {
+  const sg_bf16* Y;  // [B][H][W][C] raw conv output
+  int B, H, W, C;
+  const float* stats;  // [B][C][2]
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int act;
+  float act_alpha;
+  const sg_bf16* res;  // residual frames (interior read) or null
+  FrameMap rmap;
+  sg_bf16* dst;
+  FrameMap dmap;
+};
+
+// Backward of the same: two passes.
+//   dzh = act'(.) * (dz1 + dz2);   sums[b][c] = (sum dzh, sum dzh * xhat)          (reduce)
+//   dy  = gamma * rstd * (dzh - mean(dzh) - xhat * mean(dzh * xhat))  -> dY frame  (apply)
+// Activations of "virtual" image b >= nb_act are those of image b - act_wrap (the generator-loss
+// pass through the discriminator re-uses the fake half of the batch).
+struct InBwdParams {
+  const sg_bf16* Y;
+  int B, H, W, C;
+  int nb_act, act_wrap;
+  const float* stats;  // forward (sum, sum^2) per activation image
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int act;
+  float act_alpha;
+  GradSrc g1, g2;
+  float* sums;  // [B][C][2]
+  sg_bf16* dst;
+  FrameMap dmap;
 };
