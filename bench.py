@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""bench.py -- G+D train img/s of the SG-GAN step (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libsggan_sm100)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU restatement, host cores
+
+N > 1 is launched by the driver under torchrun (one rank per GPU, NCCL); per-GPU batch is fixed
+(weak scaling) and gradients are all-reduced between backward and Adam.  One JSON line on rank 0.
+
+What is timed: K full steps (G fwd, D fwd on real+fake, D backward, G backward, Adam on both nets,
+weight re-pack) with inputs resident in HBM -> `value`; the same K steps through model.sggan.train_step
+with HOST numpy batches (pinned H2D + D2H of the two losses inside the timed region) -> `e2e`.
+Inputs are synthetic; the working set (>5 GB at batch 8) is far larger than the 126 MB L2.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "G+D train img/s at 256x512"
+UNIT = "img/s"
+GFLOP_PER_IMG = {(256, 512, 34): 667.3, (512, 1024, 19): 2677.4}  # 3*G + 7*D algorithmic
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sggan_b200", choices=["sggan_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (config 3: 8)")
+    ap.add_argument("--height", type=int, default=256)
+    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--classes", type=int, default=34)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clock + throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_baseline(H, W, C, steps, warmup, max_seconds=30.0):
+    """The reference's CPU path: the PyTorch-CPU fp32 restatement of train_step (oracle/, 'port';
+    TensorFlow 2.1 is not installable here), batch 1, all host threads."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import sggan_oracle as O
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    gw = O.init_weights(O.generator_spec(), 1)
+    dw = O.init_weights(O.discriminator_spec(segment_class=C), 2)
+    st = O.StepState(gw, dw)
+    a, s, m, _ = O.synthetic_batch(1, H, W, C, seed=19)
+    for _ in range(warmup):
+        O.train_step(st, a, s, m)
+    times = []
+    t_start = time.time()
+    for _ in range(steps):
+        t0 = time.time()
+        O.train_step(st, a, s, m)
+        times.append(time.time() - t0)
+        if time.time() - t_start > max_seconds:
+            break
+    sec = statistics.median(times)
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": ncores, "kind": "port",
+            "sample": "%d timed steps (+%d warm-up) of the fp32 CPU restatement of train_step at %dx%d, batch 1, C=%d; "
+                      "median %.2f s/step" % (len(times), warmup, H, W, C, sec)}, sec, len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = min(args.warmup, 1)
+    k = max(1, min(args.steps, 5))
+    cb, sec, n = cpu_baseline(args.height, args.width, args.classes, k, w, max_seconds=120.0)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+            "warmup": w, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SG-GAN train_step %dx%d C=%d, CPU restatement of the reference (TF2 unavailable), "
+                                   "batch 1 per step" % (args.height, args.width, args.classes)},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                                        "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = importlib.import_module("sg-gan-tf2_b200._lib")
+    M = importlib.import_module("sg-gan-tf2_b200.model")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    B, H, W, C = args.batch, args.height, args.width, args.classes
+
+    # ---- synthetic inputs (seed 19 + rank), generated once, resident on the device
+    rng = np.random.RandomState(19 + rank)
+    real_h = rng.rand(B, H, W, 3).astype(np.float32)
+    seg_h = rng.rand(B, H, W, 3).astype(np.float32)
+    hd, wd = L.disc_logit_grid(H, W)
+    ids = np.zeros((B, hd, wd), dtype=np.int64)
+    for b in range(B):
+        for _ in range(6):
+            y0, x0 = rng.randint(0, hd), rng.randint(0, wd)
+            ids[b, y0:rng.randint(y0, hd) + 1, x0:rng.randint(x0, wd) + 1] = rng.randint(0, C)
+    mask_h = (ids[..., None] == np.arange(C)).astype(np.float32)
+    real_d, seg_d, mask_d = (torch.as_tensor(x).cuda() for x in (real_h, seg_h, mask_h))
+
+    ns = argparse.Namespace(batch_size=B, image_width=W, image_height=H, segment_class=C, use_resnet=True)
+    model = M.sggan(ns)
+    model.real_A, model.seg_A, model.mask_A = real_d, seg_d, mask_d
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        model.train_step(ns)
+    eng = model.runtime.engine
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region 1: inputs resident in HBM
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.profile_begin(18 * args.steps + 8)
+    e0.record()
+    for _ in range(args.steps):
+        model.train_step(ns)
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    launches = eng.kernel_launches
+    conv_ms, conv_n, conv_flops = eng.profile_end()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    losses = [float(model.gen_loss), float(model.disc_loss)]
+    # ---- timed region 2: end to end through the reference-facing API with host batches
+    e2e = None
+    if not args.no_e2e:
+        model.real_A, model.seg_A, model.mask_A = real_h, seg_h, mask_h
+        for _ in range(2):
+            model.train_step(ns)
+            float(model.gen_loss)
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            model.train_step(ns)
+            _ = (float(model.gen_loss), float(model.disc_loss))  # the reference prints both every step (model.py:260)
+        e1.record()
+        sync_all()
+        ms2 = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms2], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms2 = t.item()
+        e2e = {"value": B * world * args.steps / (ms2 * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(real_h.nbytes + seg_h.nbytes + mask_h.nbytes), "d2h_bytes_per_step": 8,
+               "ms_per_step": ms2 / args.steps}
+    sampler.stop_flag = True
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = conv_flops * conv_n / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+    ms_step = ms / args.steps
+    value = B * world * args.steps / (ms * 1e-3)
+    gf = GFLOP_PER_IMG.get((H, W, C))
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "SG-GAN full G+D train step (generator_resnet 9 blocks + semantic-aware D, fwd+bwd+Adam), "
+                               "%dx%d, batch %d per GPU, C=%d, loss p2p" % (H, W, B, C),
+                   "global_batch": B * world, "parallelism": "dp%d" % world,
+                   "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)" % (L.workspace_bytes(eng.cfg) / 2 ** 30)},
+        "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches * args.steps,
+        "losses_last_step": losses,
+        "step_tflops": (gf * B / ms_step) if gf else None,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                     "kernel": "conv_gemm_tc_kernel, residual-block 3x3 256->256 forward (%d launches timed with CUDA events "
+                               "inside the steps; algorithmic %.2f GFLOP per launch)" % (conv_n, conv_flops / 1e9),
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(H, W, C, 3, 1)[0]
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -94,6 +94,12 @@ int sggan_kernel_launches(const sggan_handle* h); /* kernels launched by the las
 /* fake_A of the last step / forward (device, [B,H,W,3] fp32). */
 const float* sggan_last_fake(const sggan_handle* h);
 
+/* Device-side timing of the dominant kernel: CUDA events on the step's stream around every launch of the
+ * residual-block 3x3 convolution (forward) while profiling is on.  flops_per_launch = algorithmic
+ * 2*B*H*W*Cin*Cout*9 of one launch. */
+int sggan_profile_begin(sggan_handle* h, int max_launches);
+int sggan_profile_end(sggan_handle* h, double* total_ms, int* launches, double* flops_per_launch);
+
 /* Debug / test access to internal activations.  kind: 0 input frame X, 1 raw conv output Y,
  * 2 output-gradient frame dY, 3 input-gradient buffer dX, 4 forward stats.  Returns the device
  * pointer and describes the layout in `desc` (16 ints, see sggan_b200/_lib.py). */

@@ -171,10 +171,12 @@ def residule_block(x, w, ks=3, s=1):
     return y + x
 
 
-def generator_resnet(x, w, n_blocks=9, taps=None):
-    """module.py:219-269.  `w` is the flat Keras-order list (94 tensors for 9 blocks).
+def generator_resnet(x, w, n_blocks=None, taps=None):
+    """module.py:219-269.  `w` is the flat Keras-order list (94 tensors for 9 blocks; the block count
+    is inferred from the list length when not given).
     taps, if a dict, receives named intermediates (used by layer-level parity tests)."""
-    it = iter(range(0, len(w), 1))
+    if n_blocks is None:
+        n_blocks = (len(w) - 22) // 8
     idx = [0]
 
     def take(n):
@@ -205,7 +207,6 @@ def generator_resnet(x, w, n_blocks=9, taps=None):
     k, b = take(2)
     pred = torch.tanh(conv2d(d2, k, b, 1, "VALID"))
     assert idx[0] == len(w)
-    del it
     return pred
 
 

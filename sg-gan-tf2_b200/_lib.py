@@ -60,6 +60,8 @@ SYMBOLS = {
     "sggan_step_count": (_I64, [_P]),
     "sggan_kernel_launches": (_I, [_P]),
     "sggan_last_fake": (_P, [_P]),
+    "sggan_profile_begin": (_I, [_P, _I]),
+    "sggan_profile_end": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I), C.POINTER(C.c_double)]),
     "sggan_debug_buffer": (_P, [_P, _I, _I, _I, C.POINTER(_I64)]),
     "sggan_num_layers": (_I, [_P, _I]),
     "sggan_conv2d_workspace": (_SZ, [_I] * 8),
@@ -250,6 +252,15 @@ class Engine:
         c = self.cfg
         n = c.batch * c.image_height * c.image_width * 3
         return self.workspace[off:off + 4 * n].view(torch.float32).view(c.batch, c.image_height, c.image_width, 3)
+
+    def profile_begin(self, max_launches=8192):
+        check(lib().sggan_profile_begin(self.h, max_launches))
+
+    def profile_end(self):
+        """-> (total ms, launches, algorithmic flops per launch) of the residual-block conv kernel."""
+        ms, n, fl = C.c_double(), C.c_int(), C.c_double()
+        check(lib().sggan_profile_end(self.h, C.byref(ms), C.byref(n), C.byref(fl)))
+        return ms.value, n.value, fl.value
 
     @property
     def kernel_launches(self):

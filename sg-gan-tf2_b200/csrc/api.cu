@@ -140,6 +140,34 @@ int sggan_kernel_launches(const sggan_handle* h) { return h->e.nlaunch; }
 const float* sggan_last_fake(const sggan_handle* h) { return h->e.fake; }
 int sggan_num_layers(const sggan_handle* h, int net) { return int(net_of(h, net).L.size()); }
 
+int sggan_profile_begin(sggan_handle* h, int max_launches) {
+  Engine& e = h->e;
+  while (int(e.prof_ev.size()) < 2 * max_launches) {
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) { g_err = "cudaEventCreate failed"; return SGGAN_E_CUDA; }
+    e.prof_ev.push_back(ev);
+  }
+  e.prof_used = 0;
+  e.prof_on = true;
+  return 0;
+}
+int sggan_profile_end(sggan_handle* h, double* total_ms, int* launches, double* flops_per_launch) {
+  Engine& e = h->e;
+  e.prof_on = false;
+  if (cudaStreamSynchronize(e.st) != cudaSuccess) { g_err = "stream sync failed"; return SGGAN_E_CUDA; }
+  double tot = 0;
+  for (size_t i = 0; i + 1 < e.prof_used; i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e.prof_ev[i], e.prof_ev[i + 1]) != cudaSuccess) { g_err = "event read failed"; return SGGAN_E_CUDA; }
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = int(e.prof_used / 2);
+  const Layer& l = e.G.L[3];
+  if (flops_per_launch) *flops_per_launch = 2.0 * l.nb * l.Hout * l.Wout * double(l.Cout) * l.Cin * l.k * l.k;
+  return 0;
+}
+
 static void desc_map(const FrameMap& m, int64_t* d) {
   d[0] = m.frame_pix; d[1] = m.C; d[2] = m.H; d[3] = m.W; d[4] = m.kind; d[5] = m.P; d[6] = m.pt; d[7] = m.pl;
   d[8] = m.plane_pix; d[9] = m.reflect;

@@ -319,7 +319,8 @@ int layer_prepare_wgrad(Layer& l, float* dW, int nimg, bool dry) {
     q.Mpix = Mpix;
     const int tiles = (q.x_pair ? 1 : q.Cx / 128) * q.ntaps * (q.Cy / q.BN);
     const int chunks = nimg * ((Mpix + 63) / 64);
-    int ks = (296 + tiles - 1) / tiles;
+    // one CTA per SM holds a whole accumulator: fill exactly one wave of 148 SMs (no tail round)
+    int ks = tiles >= 148 ? 1 : 148 / tiles;
     if (ks > chunks / 8) ks = chunks / 8;
     if (ks < 1) ks = 1;
     q.ksplit = ks;
@@ -658,10 +659,14 @@ int Engine::gen_forward(const float* real_A, float* fake_out) {
     if (l.has_norm) {
       if (cudaMemsetAsync(l.stats, 0, size_t(l.nb) * l.Cout * 8, st) != cudaSuccess) return SGGAN_E_CUDA;
     }
+    const bool in_block = (li >= 3 && li < 3 + 2 * cfg.n_blocks);
+    const bool timed = prof_on && in_block && prof_used + 2 <= prof_ev.size();
+    if (timed) cudaEventRecord(prof_ev[prof_used++], st);
     if ((r = run_conv_list(l.fwd))) return r;
+    if (timed) cudaEventRecord(prof_ev[prof_used++], st);
     if (!l.has_norm) continue;
     Layer& nx = G.L[li + 1];
-    const bool block_b = (li >= 3 && li < 3 + 2 * cfg.n_blocks && ((li - 3) & 1) == 1);
+    const bool block_b = in_block && ((li - 3) & 1) == 1;
     if (block_b) in_apply(G, li, nx.X, nx.xmap, G.L[li - 1].X, &G.L[li - 1].xmap);  // y + x (module.py:217)
     else in_apply(G, li, nx.X, nx.xmap, nullptr, nullptr);
   }

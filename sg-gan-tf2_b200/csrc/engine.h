@@ -83,6 +83,10 @@ struct Engine {
   int nlaunch;
   bool weights_ready;
   std::string err;
+  // optional device-side timing of the dominant kernel (the 3x3 residual-block convolutions)
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  bool prof_on = false;
 
   int build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t stream, bool dry_run, size_t* need);
   int pack_weights(int net);

@@ -76,24 +76,29 @@ __device__ __forceinline__ void grad_read8(const GradSrc& g, int b, int i, int j
       const int64_t idx = ((int64_t(b) * g.Hs + (rr[a] + g.oy)) * g.Ws + (cc[q] + g.ox)) * C + c0;
       if (g.f32) {
         const float4* s = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.ptr) + idx);
-        const float4 u0 = s[0], u1 = s[1];
+        const float4 u0 = __ldg(s), u1 = __ldg(s + 1);
         acc[0] += u0.x; acc[1] += u0.y; acc[2] += u0.z; acc[3] += u0.w;
         acc[4] += u1.x; acc[5] += u1.y; acc[6] += u1.z; acc[7] += u1.w;
       } else {
-        float t[8];
-        ld_bf16x8(reinterpret_cast<const sg_bf16*>(g.ptr) + idx, t);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const sg_bf16*>(g.ptr) + idx));
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += t[e];
+        for (int k = 0; k < 4; ++k) {
+          const float2 t = __bfloat1622float2(h[k]);
+          acc[2 * k] += t.x;
+          acc[2 * k + 1] += t.y;
+        }
       }
     }
 }
 
 constexpr int kGlueThreads = 256;
 static inline int pix_per_block_for(int HW, int B) {
-  // aim for >= ~4 waves of 148 SMs while keeping blocks reasonably fat
-  int ppb = 1024;
-  while (ppb > 64 && int64_t((HW + ppb - 1) / ppb) * B < 148 * 8) ppb >>= 1;
-  return ppb;
+  // about 6 blocks per SM over the whole grid, at least 64 pixels per block
+  const int want_blocks_per_image = (148 * 6 + B - 1) / B;
+  int ppb = (HW + want_blocks_per_image - 1) / want_blocks_per_image;
+  ppb = (ppb + 63) / 64 * 64;
+  return ppb < 64 ? 64 : ppb;
 }
 
 // ------------------------------------------------------------------------------------------ prep
@@ -191,19 +196,44 @@ __global__ void __launch_bounds__(kGlueThreads) in_apply_kernel(const InApplyPar
   float mean[8], rstd[8], scale[8], shift[8];
   in_coeffs(p.stats, p.gamma, p.beta, b, p.C, c0, float(HW), p.eps, mean, rstd, scale, shift);
   const int pix0 = blockIdx.x * ppb, pix1 = min(HW, pix0 + ppb);
-  for (int pix = pix0 + lp; pix < pix1; pix += ppi) {
-    const int i = pix / p.W, j = pix - i * p.W;
-    float y[8];
-    ld_bf16x8(p.Y + (int64_t(b) * HW + pix) * p.C + c0, y);
+  constexpr int U = 4;  // pixels in flight per thread: all 128-bit loads are issued before any use
+  const sg_bf16* ybase = p.Y + int64_t(b) * HW * p.C + c0;
+  const sg_bf16* rbase = p.res ? p.res + int64_t(b) * p.rmap.frame_pix * p.rmap.C + c0 : nullptr;
+  for (int pix = pix0 + lp; pix < pix1; pix += U * ppi) {
+    uint4 raw[U], rr[U];
+    int pi[U], pj[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = act_fwd(fmaf(y[e], scale[e], shift[e]), p.act, p.act_alpha);
-    if (p.res != nullptr) {
-      float r[8];
-      ld_bf16x8(p.res + (int64_t(b) * p.rmap.frame_pix + frame_pixel(p.rmap, i, j)) * p.rmap.C + c0, r);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) y[e] += r[e];
+    for (int u = 0; u < U; ++u) {
+      const int q = pix + u * ppi;
+      pi[u] = q / p.W;
+      pj[u] = q - pi[u] * p.W;
+      if (q < pix1) {
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(ybase + int64_t(q) * p.C));
+        if (rbase) rr[u] = __ldg(reinterpret_cast<const uint4*>(rbase + frame_pixel(p.rmap, pi[u], pj[u]) * p.rmap.C));
+      }
     }
-    write_frame8(p.dst, p.dmap, b, i, j, c0, y);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (pix + u * ppi >= pix1) break;
+      float y[8];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 t = __bfloat1622float2(h[k]);
+        y[2 * k] = act_fwd(fmaf(t.x, scale[2 * k], shift[2 * k]), p.act, p.act_alpha);
+        y[2 * k + 1] = act_fwd(fmaf(t.y, scale[2 * k + 1], shift[2 * k + 1]), p.act, p.act_alpha);
+      }
+      if (rbase) {
+        const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&rr[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 t = __bfloat1622float2(hr[k]);
+          y[2 * k] += t.x;
+          y[2 * k + 1] += t.y;
+        }
+      }
+      write_frame8(p.dst, p.dmap, b, pi[u], pj[u], c0, y);
+    }
   }
 }
 void launch_in_apply(const InApplyParams& p, cudaStream_t st) {
@@ -255,42 +285,73 @@ __global__ void __launch_bounds__(kGlueThreads) in_bwd_kernel(const InBwdParams 
   const int cg = threadIdx.x % C8, lp = threadIdx.x / C8, ppi = kGlueThreads / C8;
   const int c0 = cg * 8, HW = p.H * p.W;
   const float n = float(HW);
-  float mean[8], rstd[8], scale[8], shift[8];
-  in_coeffs(p.stats, p.gamma, p.beta, ba, p.C, c0, n, p.eps, mean, rstd, scale, shift);
-  float m1[8], m2[8], a1[8], a2[8];
-  if (kApply) {
+  // per-channel constants:  zpre = y*scale + shift;  xhat = y*rstd - mr;
+  // apply:  dy = scale*dz + ca*y + cb   with ca = -scale*m2*rstd, cb = scale*(m2*mr - m1)
+  float scale[8], shift[8], k0[8], k1[8], a1[8], a2[8];
+  {
+    float mean[8], rstd[8];
+    in_coeffs(p.stats, p.gamma, p.beta, ba, p.C, c0, n, p.eps, mean, rstd, scale, shift);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      m1[e] = p.sums[(int64_t(b) * p.C + c0 + e) * 2] / n;
-      m2[e] = p.sums[(int64_t(b) * p.C + c0 + e) * 2 + 1] / n;
+      if (kApply) {
+        const float m1 = p.sums[(int64_t(b) * p.C + c0 + e) * 2] / n;
+        const float m2 = p.sums[(int64_t(b) * p.C + c0 + e) * 2 + 1] / n;
+        k0[e] = -scale[e] * m2 * rstd[e];
+        k1[e] = scale[e] * (m2 * mean[e] * rstd[e] - m1);
+      } else {
+        k0[e] = rstd[e];
+        k1[e] = mean[e] * rstd[e];
+      }
+      a1[e] = a2[e] = 0.f;
     }
-  } else {
+  }
+  if (!kApply) {
     for (int t = threadIdx.x; t < 2 * p.C; t += kGlueThreads) sred[t] = 0.f;
     __syncthreads();
-#pragma unroll
-    for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.f;
   }
   const int pix0 = blockIdx.x * ppb, pix1 = min(HW, pix0 + ppb);
-  for (int pix = pix0 + lp; pix < pix1; pix += ppi) {
-    const int i = pix / p.W, j = pix - i * p.W;
-    float y[8], d[8];
-    ld_bf16x8(p.Y + (int64_t(ba) * HW + pix) * p.C + c0, y);
+  constexpr int U = 2;
+  const sg_bf16* ybase = p.Y + int64_t(ba) * HW * p.C + c0;
+  for (int pix = pix0 + lp; pix < pix1; pix += U * ppi) {
+    uint4 raw[U];
+    float d[U][8];
+    int pi[U], pj[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) d[e] = 0.f;
-    grad_read8(p.g1, b, i, j, p.H, p.W, p.C, c0, d);
-    grad_read8(p.g2, b, i, j, p.H, p.W, p.C, c0, d);
+    for (int u = 0; u < U; ++u) {
+      const int q = pix + u * ppi;
+      pi[u] = q / p.W;
+      pj[u] = q - pi[u] * p.W;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float xh = (y[e] - mean[e]) * rstd[e];
-      const float dz = d[e] * act_grad(fmaf(y[e], scale[e], shift[e]), p.act, p.act_alpha);
-      if (kApply) {
-        d[e] = scale[e] * (dz - m1[e] - xh * m2[e]);
-      } else {
-        a1[e] += dz;
-        a2[e] += dz * xh;
+      for (int e = 0; e < 8; ++e) d[u][e] = 0.f;
+      if (q < pix1) {
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(ybase + int64_t(q) * p.C));
+        grad_read8(p.g1, b, pi[u], pj[u], p.H, p.W, p.C, c0, d[u]);
+        grad_read8(p.g2, b, pi[u], pj[u], p.H, p.W, p.C, c0, d[u]);
       }
     }
-    if (kApply) write_frame8(p.dst, p.dmap, b, i, j, c0, d);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (pix + u * ppi >= pix1) break;
+      float y[8];
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 t = __bfloat1622float2(h[k]);
+        y[2 * k] = t.x;
+        y[2 * k + 1] = t.y;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float dz = d[u][e] * act_grad(fmaf(y[e], scale[e], shift[e]), p.act, p.act_alpha);
+        if (kApply) {
+          d[u][e] = fmaf(scale[e], dz, fmaf(k0[e], y[e], k1[e]));
+        } else {
+          a1[e] += dz;
+          a2[e] += dz * fmaf(y[e], k0[e], -k1[e]);
+        }
+      }
+      if (kApply) write_frame8(p.dst, p.dmap, b, pi[u], pj[u], c0, d[u]);
+    }
   }
   if (!kApply) {
 #pragma unroll

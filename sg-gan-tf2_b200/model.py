@@ -1,0 +1,207 @@
+"""model.py -- drop-in for the reference trainer's hot path (model.py:39-200,450-567).
+
+`sggan(args)` keeps the reference's attribute and method names: `.generator`, `.discriminator`,
+`.train_step(args)` (reads `.real_A/.seg_A/.mask_A`, sets `.fake_A/.gen_loss/.disc_loss`),
+`.gen_loss_p2p`, `.disc_loss_p2p`, `.generator_loss`, `.discriminator_loss`,
+`.generate_test_images`, `.save`, `.load`, `.train`, `.test`.  One call of `train_step` is ONE call
+into libsggan_sm100.so (forward, both backward passes, Adam) -- no TensorFlow, no autograd tape.
+
+Deliberate deviations: D5 -- `fake_A = G(real_A)` every step (the reference's
+concat-with-previous-fake branch only survives step 2 at batch 10); D6 -- `lr` is live but
+defaults to the reference-effective 0.001; D9 -- only the `use_resnet` generator exists.
+Data loading / eval / TensorBoard (model.py:202-448) are host orchestration outside the path:
+`train()` consumes an iterable of numpy batches instead of globbing PNGs.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib as L
+from . import module
+from .module import (abs_criterion, discriminator, generator_resnet, gradloss_criterion, mae_criterion,  # noqa: F401
+                     sce_criterion, tf_kernel_prep_3d)
+
+
+class sggan(object):
+    def __init__(self, args):
+        self.batch_size = args.batch_size
+        self.image_width = args.image_width
+        self.image_height = args.image_height
+        self.input_c_dim = getattr(args, "input_nc", 3)
+        self.output_c_dim = getattr(args, "output_nc", 3)
+        self.L1_lambda = getattr(args, "L1_lambda", 10.0)
+        self.Lg_lambda = getattr(args, "Lg_lambda", 5.0)
+        self.dataset_dir = getattr(args, "dataset_dir", "city")
+        self.segment_class = getattr(args, "segment_class", 34)
+        r = getattr(args, "ratio_gan2seg", 10)
+        self.alpha_recip = 1. / r if r > 0 else 0
+        self.use_pix2pix = getattr(args, "use_pix2pix", False)
+        if self.use_pix2pix or not getattr(args, "use_resnet", True):
+            raise L.SgganError("only the use_resnet generator + semantic-aware discriminator path is implemented "
+                               "(SURVEY D9 / 8(f) row f4)")
+        self.use_lsgan = bool(getattr(args, "use_lsgan", True))
+        self.criterionGAN = mae_criterion if self.use_lsgan else sce_criterion
+        # loss_mode "p2p" = what train_step actually calls (model.py:190-191); "sggan" = the defined-but-unwired
+        # SG-GAN losses (model.py:114-133) + gradient-sensitive term
+        self.loss_mode = getattr(args, "loss_mode", "p2p")
+        self.lr = getattr(args, "lr_effective", 0.001)  # model.py:82,205: hard-coded 0.001 (args.lr unused)
+        self.beta1 = getattr(args, "beta1", 0.5)
+        self.discriminator = discriminator(self.image_height, self.image_width, getattr(args, "ndf", 64), self.segment_class)
+        self.generator = generator_resnet(self.image_height, self.image_width, getattr(args, "ngf", 64), self.output_c_dim)
+        self.kernels = [tf_kernel_prep_3d(np.array([[0, 0, 0], [-1, 0, 1], [0, 0, 0]]), self.input_c_dim),
+                        tf_kernel_prep_3d(np.array([[0, -1, 0], [0, 0, 0], [0, 1, 0]]), self.input_c_dim)]
+        self.kernel = np.stack(self.kernels, axis=-1).astype(np.float32)  # "DerivKernel_seg" (model.py:109-112)
+        self.weighted_seg_A = []
+        self.real_A = self.seg_A = self.mask_A = self.fake_A = None
+        self.gen_loss = self.disc_loss = None
+        self.runtime = None
+        self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._pinned = {}
+
+    # ---- plan -----------------------------------------------------------------------------------------
+    def _ensure_runtime(self, B, H, W, mask_hw):
+        rt = self.runtime
+        if rt is not None and (rt.cfg.batch, rt.cfg.image_height, rt.cfg.image_width, rt.cfg.mask_height,
+                               rt.cfg.mask_width) == (B, H, W, mask_hw[0], mask_hw[1]):
+            return rt
+        rt = module.Runtime(B, H, W, segment_class=self.segment_class, n_blocks=self.generator.n_blocks,
+                            mask_hw=mask_hw, loss_mode=L.LOSS_P2P if self.loss_mode == "p2p" else L.LOSS_SGGAN,
+                            use_lsgan=int(self.use_lsgan), lr=self.lr, beta1=self.beta1, L1_lambda=self.L1_lambda,
+                            Lg_lambda=self.Lg_lambda, world_size=self.world_size)
+        self.generator.runtime = None
+        self.discriminator.runtime = None
+        self.generator.bind(rt)
+        self.discriminator.bind(rt)
+        if self.world_size > 1:  # identical replicas: broadcast rank 0's weights
+            for net in (L.NET_G, L.NET_D):
+                dist.broadcast(rt.engine.flat(net, 0), src=0)
+            rt.engine.weights_changed()
+        self.runtime = rt
+        return rt
+
+    def _upload(self, name, x):
+        """numpy batch -> device through a persistent pinned staging buffer (H2D inside the step)."""
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            return x.float().contiguous()
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        buf = self._pinned.get(name)
+        if buf is None or buf.shape != x.shape:
+            buf = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+            self._pinned[name] = buf
+        buf.numpy()[...] = x
+        return buf.to("cuda", non_blocking=True)
+
+    # ---- the hot path ---------------------------------------------------------------------------------
+    def train_step(self, args=None):
+        """model.py:169-200.  Inputs come from self.real_A / self.seg_A / self.mask_A exactly as in the
+        reference's train loop (model.py:249-256)."""
+        real_A = self._upload("real_A", self.real_A)
+        seg_A = self._upload("seg_A", self.seg_A)
+        mask_A = self._upload("mask_A", self.mask_A)
+        B, H, W, _ = real_A.shape
+        rt = self._ensure_runtime(B, H, W, (int(mask_A.shape[1]), int(mask_A.shape[2])))
+        eng = rt.engine
+        if self.world_size == 1:
+            eng.train_step(real_A, seg_A, mask_A)
+        else:
+            # data parallel: D gradients are final after phase 1 and are all-reduced on NCCL's stream while
+            # the generator backward runs; G gradients follow; Adam applies 1/world_size.
+            eng.step_forward_backward_d(real_A, seg_A, mask_A)
+            hd = dist.all_reduce(eng.flat(L.NET_D, 1), async_op=True)
+            eng.step_backward_g()
+            hg = dist.all_reduce(eng.flat(L.NET_G, 1), async_op=True)
+            hg.wait()
+            eng.step_adam(L.NET_G)
+            hd.wait()
+            eng.step_adam(L.NET_D)
+        self.fake_A = eng.last_fake()
+        self.gen_loss, self.disc_loss = eng.losses[0], eng.losses[1]  # device scalars; float() syncs
+        return self.gen_loss, self.disc_loss
+
+    def generate_test_images(self, sample_imgA):
+        """model.py:528-532."""
+        return self.generator(sample_imgA)
+
+    # ---- losses as callables (model.py:114-166); train_step fuses them, these serve API parity ---------------
+    def gen_loss_p2p(self, DA_fake, fake_A, seg_A):
+        LAMBDA = 100
+        DA_fake = L.as_cuda_f32(DA_fake)
+        gan_loss = sce_criterion(DA_fake, torch.ones_like(DA_fake))
+        return gan_loss + LAMBDA * abs_criterion(seg_A, fake_A)
+
+    def disc_loss_p2p(self, DA_real, DA_fake):
+        DA_real, DA_fake = L.as_cuda_f32(DA_real), L.as_cuda_f32(DA_fake)
+        return sce_criterion(DA_real, torch.ones_like(DA_real)) + sce_criterion(DA_fake, torch.zeros_like(DA_fake))
+
+    def generator_loss(self, DA_fake, args):
+        import ctypes as C
+        seg = L.as_cuda_f32(self.seg_A)
+        B, H, W, _ = seg.shape
+        w = torch.empty((B, H, W, 1), dtype=torch.float32, device=seg.device)
+        L.check(L.lib().sggan_seg_edge_weight(C.c_void_p(seg.data_ptr()), C.c_void_p(w.data_ptr()), B, H, W, L.stream_ptr()))
+        self.weighted_seg_A = w
+        DA_fake = L.as_cuda_f32(DA_fake)
+        return self.criterionGAN(DA_fake, torch.ones_like(DA_fake)) + args.L1_lambda * abs_criterion(self.real_A, self.fake_A)
+
+    def discriminator_loss(self, DA_real, DA_fake_sample):
+        DA_real, DA_fake_sample = L.as_cuda_f32(DA_real), L.as_cuda_f32(DA_fake_sample)
+        return (self.criterionGAN(DA_real, torch.ones_like(DA_real)) +
+                self.criterionGAN(DA_fake_sample, torch.zeros_like(DA_fake_sample))) / 2
+
+    # ---- orchestration around the path ---------------------------------------------------------------------
+    def train(self, args, batches=None):
+        """model.py:202-275 with the PNG loader replaced by `batches`: an iterable (or a callable taking the
+        epoch) of (real_A, seg_A, mask_A) numpy/torch batches."""
+        if batches is None:
+            raise L.SgganError("train(): pass `batches` -- the PNG/skimage loader (utils.py:167-233) is outside the "
+                               "accelerated path (SURVEY 8(f) row f1)")
+        start_time = time.time()
+        if getattr(args, "continue_train", False):
+            print(" [*] Load SUCCESS" if self.load(args.checkpoint_dir) else " [!] Load failed...")
+        epoch = 0
+        try:
+            for epoch in range(args.epoch):
+                it = batches(epoch) if callable(batches) else batches
+                for idx, (a, s, m) in enumerate(it):
+                    self.real_A, self.seg_A, self.mask_A = a, s, m
+                    self.train_step(args)
+                    print("Epoch: [%2d] [%4d] time: %4.4f Gen_Loss: %f Disc_Loss: %f " % (
+                        epoch, idx, time.time() - start_time, float(self.gen_loss), float(self.disc_loss)))
+        finally:
+            if getattr(args, "checkpoint_dir", None):
+                self.save(args.checkpoint_dir, epoch)
+
+    def save(self, checkpoint_dir, ep):
+        """model.py:450-468 (same directory layout; .npz instead of TF checkpoints)."""
+        path = "%s/%s" % (checkpoint_dir, self.dataset_dir)
+        for sub in ("gen", "disc"):
+            os.makedirs(os.path.join(path, sub), exist_ok=True)
+        self.generator.save_weights(os.path.join(path, "gen/cp-%04d.ckpt" % ep))
+        self.discriminator.save_weights(os.path.join(path, "disc/cp-%04d.ckpt" % ep))
+
+    def load(self, checkpoint_dir):
+        """model.py:471-503: latest checkpoint of both nets, False if either is missing."""
+        path = "%s/%s" % (checkpoint_dir, self.dataset_dir)
+
+        def latest(sub):
+            d = os.path.join(path, sub)
+            fs = sorted(f for f in os.listdir(d) if f.endswith(".ckpt.npz")) if os.path.isdir(d) else []
+            return os.path.join(d, fs[-1]) if fs else None
+
+        g, d = latest("gen"), latest("disc")
+        if g and d:
+            self.generator.load_weights(g)
+            self.discriminator.load_weights(d)
+            return True
+        return False
+
+    def test(self, args, images=None):
+        """model.py:535-567 without file IO: returns G(x) for each image (x in [0,255] like model.py:555-561)."""
+        if not self.load(args.checkpoint_dir):
+            print(" [!] Load failed...")
+        return [self.generator(np.asarray(im, dtype=np.float32)[None]) for im in (images or [])]

@@ -1,0 +1,270 @@
+"""module.py -- drop-in for the reference's module.py on the hot path (module.py:208-351).
+
+Same names, argument meaning and defaults as the reference; the arithmetic runs in
+libsggan_sm100.so (hand-written sm_100a kernels) through the ctypes binding in _lib.py.
+`generator_resnet()` / `discriminator()` return callables with a Keras-like surface
+(`model(x)`, `model([x, mask])`, `.trainable_variables` in Keras creation order,
+`.save_weights / .load_weights`).  The builders take the sizes the reference hard-codes
+(module.py:221,225,274-277) as keyword arguments defaulting to the reference's constants
+(SURVEY D3); activations are fully convolutional, so a model is re-planned for whatever NHWC
+shape it is called with.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+__all__ = ["generator_resnet", "discriminator", "residule_block", "tf_kernel_prep_3d", "tf_deriv", "abs_criterion",
+           "mae_criterion", "sce_criterion", "gradloss_criterion"]
+
+_SEED = 19  # main.py:4 tf.random.set_seed(19)
+
+
+def _glorot(gen, shape):
+    rf = shape[0] * shape[1]
+    lim = math.sqrt(6.0 / (shape[2] * rf + shape[3] * rf))
+    return (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * lim
+
+
+class Runtime:
+    """One libsggan engine (generator + discriminator planned together for a fixed NHWC shape)."""
+    _cache = {}
+
+    def __init__(self, batch, height, width, segment_class=34, n_blocks=9, mask_hw=None, **cfg_kw):
+        kw = dict(segment_class=segment_class, n_blocks=n_blocks)
+        if mask_hw is not None:
+            kw.update(mask_height=int(mask_hw[0]), mask_width=int(mask_hw[1]))
+        kw.update(cfg_kw)
+        self.cfg = L.default_config(batch, height, width, **kw)
+        self.engine = L.Engine(self.cfg)
+        self.bound = {L.NET_G: None, L.NET_D: None}
+
+    @classmethod
+    def get(cls, batch, height, width, **kw):
+        key = (batch, height, width, tuple(sorted(kw.items())))
+        if key not in cls._cache:
+            cls._cache.clear()  # one live plan at a time: workspaces are GBs
+            cls._cache[key] = cls(batch, height, width, **kw)
+        return cls._cache[key]
+
+
+class _Net:
+    """Keras-Model-like holder of one network's variables."""
+    net_id = None
+
+    def __init__(self, shapes, seed):
+        gen = torch.Generator().manual_seed(seed)
+        self._vars = []
+        for s in shapes:
+            if len(s) == 4:
+                self._vars.append(_glorot(gen, s))
+            else:
+                self._vars.append(None)  # filled below: bias / beta zeros, gamma ones
+        self._shapes = shapes
+        self.runtime = None
+
+    @property
+    def trainable_variables(self):
+        return self._vars
+
+    def bind(self, runtime):
+        """Move the variables into `runtime`'s flat parameter buffer (they become views of it)."""
+        if self.runtime is runtime:
+            return
+        eng = runtime.engine
+        eng.set_weights(self.net_id, self._vars)
+        self._vars = eng.tensors(self.net_id, 0)
+        self.runtime = runtime
+        runtime.bound[self.net_id] = self
+        eng.weights_changed()
+
+    def get_weights(self):
+        return [v.detach().cpu().numpy().copy() for v in self._vars]
+
+    def set_weights(self, weights):
+        if len(weights) != len(self._vars):
+            raise ValueError("expected %d arrays, got %d" % (len(self._vars), len(weights)))
+        for v, w in zip(self._vars, weights):
+            w = torch.as_tensor(np.asarray(w), dtype=torch.float32)
+            if tuple(w.shape) != tuple(v.shape):
+                raise ValueError("shape mismatch %s vs %s" % (tuple(w.shape), tuple(v.shape)))
+            v.copy_(w.to(v.device))
+        if self.runtime is not None:
+            self.runtime.engine.weights_changed()
+
+    # Keras' Model.save_weights / load_weights write TF checkpoints (model.py:463-466,499-500); here the
+    # same variable list goes to an .npz.
+    def save_weights(self, path):
+        np.savez(path if path.endswith(".npz") else path + ".npz", *self.get_weights())
+
+    def load_weights(self, path):
+        z = np.load(path if path.endswith(".npz") else path + ".npz")
+        self.set_weights([z["arr_%d" % i] for i in range(len(z.files))])
+
+
+class GeneratorResnet(_Net):
+    """generator_resnet (module.py:219-269): c7s1-64, d128, d256, 9 x R256, u128, u64, c7s1-3 + tanh."""
+    net_id = L.NET_G
+
+    def __init__(self, image_height=64, image_width=64, gf_dim=64, output_c_dim=3, n_blocks=9, seed=_SEED):
+        if gf_dim != 64 or output_c_dim != 3:
+            raise L.SgganError("generator_resnet: gf_dim=64, output_c_dim=3 only (module.py:221-222)")
+        g = gf_dim
+        shapes = [(7, 7, 3, g), (g,), (g,), (g,), (3, 3, g, 2 * g), (2 * g,), (2 * g,), (2 * g,),
+                  (3, 3, 2 * g, 4 * g), (4 * g,), (4 * g,), (4 * g,)]
+        for _ in range(2 * n_blocks):
+            shapes += [(3, 3, 4 * g, 4 * g), (4 * g,), (4 * g,), (4 * g,)]
+        shapes += [(3, 3, 2 * g, 4 * g), (2 * g,), (2 * g,), (2 * g,), (3, 3, g, 2 * g), (g,), (g,), (g,),
+                   (7, 7, g, 3), (3,)]
+        super().__init__(shapes, seed)
+        # [kernel, bias, gamma, beta] per conv+norm; Keras defaults zeros / ones / zeros
+        i = 0
+        while i < len(shapes):
+            self._vars[i + 1] = torch.zeros(shapes[i + 1])
+            if i + 2 < len(shapes) and len(shapes[i + 2]) == 1:
+                self._vars[i + 2] = torch.ones(shapes[i + 2])
+                self._vars[i + 3] = torch.zeros(shapes[i + 3])
+                i += 4
+            else:
+                i += 2
+        self.n_blocks = n_blocks
+        self.input_hw = (image_height, image_width)
+
+    def __call__(self, x):
+        x = L.as_cuda_f32(x)
+        B, H, W, _ = x.shape
+        rt = self.runtime
+        if rt is None or (rt.cfg.batch, rt.cfg.image_height, rt.cfg.image_width) != (B, H, W):
+            kw = dict(n_blocks=self.n_blocks)
+            if H < 128 or W < 128:
+                # the discriminator stack needs >= 128 px (Appendix B); plan it on a dummy grid instead
+                raise L.SgganError("generator_resnet: images smaller than 128x128 are not supported by the joint plan")
+            rt = Runtime.get(B, H, W, **kw)
+            self.runtime = None
+            self.bind(rt)
+        return rt.engine.gen_forward(x)
+
+
+class Discriminator(_Net):
+    """discriminator (module.py:272-318): 8 convs, 6 instance norms, LeakyReLU(0.3), logits x mask, sum over C."""
+    net_id = L.NET_D
+
+    def __init__(self, image_height=128, image_width=128, df_dim=64, segment_class=34, seed=_SEED + 1):
+        if df_dim != 64:
+            raise L.SgganError("discriminator: df_dim=64 only (module.py:274)")
+        d = df_dim
+        shapes = [(3, 3, 3, d), (d,)]
+        for cin, cout in ((d, 2 * d), (2 * d, 4 * d), (4 * d, 8 * d), (8 * d, 8 * d), (8 * d, 8 * d), (8 * d, 8 * d)):
+            shapes += [(3, 3, cin, cout), (cout,), (cout,), (cout,)]
+        shapes += [(3, 3, 8 * d, segment_class), (segment_class,)]
+        super().__init__(shapes, seed)
+        self._vars[1] = torch.zeros(shapes[1])
+        for i in range(2, len(shapes) - 2, 4):
+            self._vars[i + 1] = torch.zeros(shapes[i + 1])
+            self._vars[i + 2] = torch.ones(shapes[i + 2])
+            self._vars[i + 3] = torch.zeros(shapes[i + 3])
+        self._vars[-1] = torch.zeros(shapes[-1])
+        self.segment_class = segment_class
+
+    def __call__(self, inputs):
+        x, mask = inputs
+        x, mask = L.as_cuda_f32(x), L.as_cuda_f32(mask)
+        B, H, W, _ = x.shape
+        rt = self.runtime
+        want = (B, H, W, int(mask.shape[1]), int(mask.shape[2]))
+        if rt is None or (rt.cfg.batch, rt.cfg.image_height, rt.cfg.image_width, rt.cfg.mask_height,
+                          rt.cfg.mask_width) != want:
+            rt = Runtime.get(B, H, W, segment_class=self.segment_class, mask_hw=(mask.shape[1], mask.shape[2]))
+            self.runtime = None
+            self.bind(rt)
+        return rt.engine.disc_forward(x, mask)
+
+
+def generator_resnet(image_height=64, image_width=64, gf_dim=64, output_c_dim=3, n_blocks=9):
+    print("generator_resnet")
+    return GeneratorResnet(image_height, image_width, gf_dim, output_c_dim, n_blocks)
+
+
+def discriminator(image_height=128, image_width=128, df_dim=64, segment_class=34):
+    print("discriminator")
+    return Discriminator(image_height, image_width, df_dim, segment_class)
+
+
+def residule_block(x, dim, ks=3, s=1, weights=None):
+    """module.py:208-217 as a standalone op: reflect-pad -> conv -> IN -> relu -> reflect-pad -> conv -> IN, + x.
+    `weights` = [k1, b1, g1, be1, k2, b2, g2, be2] (Keras order); created glorot/zeros/ones if omitted."""
+    from . import ops
+    x = L.as_cuda_f32(x)
+    if s != 1 or ks % 2 == 0:
+        raise L.SgganError("residule_block: stride 1 and odd kernel only")
+    cin = x.shape[-1]
+    if weights is None:
+        gen = torch.Generator().manual_seed(_SEED)
+        weights = [_glorot(gen, (ks, ks, cin, dim)), torch.zeros(dim), torch.ones(dim), torch.zeros(dim),
+                   _glorot(gen, (ks, ks, dim, dim)), torch.zeros(dim), torch.ones(dim), torch.zeros(dim)]
+    y = ops.conv2d_raw(x, weights[0], weights[1], stride=1, padding="REFLECT")
+    y = ops.instance_norm_raw(y, weights[2], weights[3], eps=1e-3, act="relu")
+    y = ops.conv2d_raw(y, weights[4], weights[5], stride=1, padding="REFLECT")
+    return ops.instance_norm_raw(y, weights[6], weights[7], eps=1e-3, act=None, residual=x)
+
+
+# ---- criteria (module.py:322-351) ---------------------------------------------------------------------
+
+def tf_kernel_prep_3d(kernel, n_channels):
+    return np.tile(kernel, (n_channels, 1, 1)).swapaxes(0, 1).swapaxes(1, 2)
+
+
+def tf_deriv(batch, ksize=3, padding="SAME"):
+    """Sobel x / y per channel (module.py:325-334); returned as (B,H,W,2*C), channel = c*2 + {x,y}.
+    Only the fused gradloss kernel uses it on the hot path; this standalone form is plain torch glue on
+    the device and exists for API completeness."""
+    x = L.as_cuda_f32(batch)
+    n_ch = x.shape[3]
+    gx = torch.tensor([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], dtype=torch.float32, device=x.device)
+    gy = torch.tensor([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], dtype=torch.float32, device=x.device)
+    w = torch.stack([gx, gy]).repeat(n_ch, 1, 1).unsqueeze(1)
+    xi = x.permute(0, 3, 1, 2)
+    if padding == "SAME":
+        xi = torch.nn.functional.pad(xi, (1, 1, 1, 1))
+    return torch.nn.functional.conv2d(xi, w, groups=n_ch).permute(0, 2, 3, 1).contiguous()
+
+
+def _criterion(a, b, mode):
+    import ctypes as C
+    a, b = L.as_cuda_f32(a), L.as_cuda_f32(b)
+    if a.shape != b.shape:
+        b = b.expand_as(a).contiguous()
+    out = torch.zeros(1, dtype=torch.float32, device=a.device)
+    L.check(L.lib().sggan_criterion(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), a.numel(), mode,
+                                    C.c_void_p(out.data_ptr()), L.stream_ptr()))
+    return out[0]
+
+
+def abs_criterion(in_, target):
+    return _criterion(in_, target, 0)
+
+
+def mae_criterion(in_, target):
+    return _criterion(in_, target, 1)
+
+
+def sce_criterion(logits, labels):
+    return _criterion(logits, labels, 2)
+
+
+def gradloss_criterion(in_, target, weight, return_grad=False):
+    import ctypes as C
+    a, b, w = L.as_cuda_f32(in_), L.as_cuda_f32(target), L.as_cuda_f32(weight)
+    B, H, W, ch = a.shape
+    if ch != 3:
+        raise L.SgganError("gradloss_criterion: 3-channel images only")
+    out = torch.zeros(1, dtype=torch.float32, device=a.device)
+    d_in = torch.empty_like(a) if return_grad else None
+    L.check(L.lib().sggan_gradloss(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(w.data_ptr()),
+                                   C.c_void_p(out.data_ptr()), C.c_void_p(d_in.data_ptr() if return_grad else None),
+                                   B, H, W, L.stream_ptr()))
+    return (out[0], d_in) if return_grad else out[0]

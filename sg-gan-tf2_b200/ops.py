@@ -1,0 +1,148 @@
+"""ops.py -- the reference's op wrappers (ops.py:10-49) over the sm_100a kernels.
+
+The reference file is dead TF1 code (tf.variable_scope / slim); its *names and
+signatures* are part of the surface, so they are re-created here: `conv2d`, `deconv2d`
+(bias-free, truncated-normal(stddev) kernels, per the commented slim calls at ops.py:24-34),
+`instance_norm` (eps 1e-5, scale ~ N(1, 0.02), offset 0, ops.py:13-22) and `lrelu` (leak 0.2).
+Variables are created once per `name` (the tf.variable_scope behaviour) and kept in VARIABLES.
+`batch_norm` and `linear` are never used anywhere in the reference and are out of scope.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+VARIABLES = {}  # name -> list of torch tensors, like a TF1 variable scope
+_PAD = {"VALID": 0, "SAME": 1, "REFLECT": 2}
+_ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2, "tanh": 3}
+_ws = {}
+
+
+def _workspace(nbytes, device):
+    t = _ws.get(device)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _ws[device] = t
+    return t
+
+
+def _trunc_normal(shape, stddev, seed):
+    g = torch.Generator().manual_seed(seed)
+    w = torch.empty(shape)
+    torch.nn.init.trunc_normal_(w, 0.0, stddev, -2 * stddev, 2 * stddev, generator=g)
+    return w
+
+
+def conv2d_raw(x, kernel, bias=None, stride=1, padding="SAME"):
+    """Conv2D forward: x NHWC, kernel HWIO.  Cin and Cout multiples of 64; stride 1 (odd k) or 2 (k=3)."""
+    x = L.as_cuda_f32(x)
+    kernel = L.as_cuda_f32(kernel, x.device)
+    bias = None if bias is None else L.as_cuda_f32(bias, x.device)
+    B, H, W, Cin = x.shape
+    k, Cout = kernel.shape[0], kernel.shape[3]
+    pad = _PAD[padding.upper()]
+    nbytes = L.lib().sggan_conv2d_workspace(B, H, W, Cin, Cout, k, stride, pad)
+    if nbytes == 0:
+        raise L.SgganError("conv2d: unsupported shape (Cin %d, Cout %d, k %d, stride %d, %s)" % (Cin, Cout, k, stride, padding))
+    if pad == 0:
+        Ho, Wo = (H - k) // stride + 1, (W - k) // stride + 1
+    elif pad == 1:
+        Ho, Wo = -(-H // stride), -(-W // stride)
+    else:
+        Ho, Wo = H, W
+    y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    ws = _workspace(nbytes, x.device)
+    L.check(L.lib().sggan_conv2d_fwd(C.c_void_p(x.data_ptr()), C.c_void_p(kernel.data_ptr()),
+                                     C.c_void_p(bias.data_ptr() if bias is not None else None),
+                                     C.c_void_p(y.data_ptr()), B, H, W, Cin, Cout, k, stride, pad,
+                                     C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
+    return y
+
+
+def deconv2d_raw(x, kernel, bias=None):
+    """Conv2DTranspose(3, strides 2, 'same') forward: kernel (kh, kw, Cout, Cin)."""
+    x = L.as_cuda_f32(x)
+    kernel = L.as_cuda_f32(kernel, x.device)
+    bias = None if bias is None else L.as_cuda_f32(bias, x.device)
+    B, H, W, Cin = x.shape
+    if kernel.shape[0] != 3 or kernel.shape[3] != Cin:
+        raise L.SgganError("deconv2d: kernel must be (3, 3, Cout, Cin)")
+    Cout = kernel.shape[2]
+    nbytes = L.lib().sggan_conv2d_workspace(B, H, W, Cin, Cout, 3, -2, 1)
+    if nbytes == 0:
+        raise L.SgganError("deconv2d: unsupported shape")
+    y = torch.empty((B, 2 * H, 2 * W, Cout), dtype=torch.float32, device=x.device)
+    ws = _workspace(nbytes, x.device)
+    L.check(L.lib().sggan_deconv2d_fwd(C.c_void_p(x.data_ptr()), C.c_void_p(kernel.data_ptr()),
+                                       C.c_void_p(bias.data_ptr() if bias is not None else None),
+                                       C.c_void_p(y.data_ptr()), B, H, W, Cin, Cout, C.c_void_p(ws.data_ptr()),
+                                       ws.numel(), L.stream_ptr()))
+    return y
+
+
+def instance_norm_raw(x, gamma, beta, eps=1e-3, act=None, alpha=0.3, residual=None):
+    x = L.as_cuda_f32(x)
+    B, H, W, Cc = x.shape
+    gamma, beta = L.as_cuda_f32(gamma, x.device), L.as_cuda_f32(beta, x.device)
+    residual = None if residual is None else L.as_cuda_f32(residual, x.device)
+    y = torch.empty_like(x)
+    ws = _workspace(x.numel() * 6 + B * Cc * 8 + 4096, x.device)
+    L.check(L.lib().sggan_instance_norm_fwd(C.c_void_p(x.data_ptr()), C.c_void_p(gamma.data_ptr()),
+                                            C.c_void_p(beta.data_ptr()),
+                                            C.c_void_p(residual.data_ptr() if residual is not None else None),
+                                            C.c_void_p(y.data_ptr()), B, H, W, Cc, eps, _ACT[act], alpha,
+                                            C.c_void_p(ws.data_ptr()), ws.numel(), L.stream_ptr()))
+    return y
+
+
+# ---- the reference's signatures --------------------------------------------------------------------------
+
+def conv2d(input_, output_dim, ks=4, s=2, stddev=0.02, padding="SAME", name="conv2d"):
+    """ops.py:24-28 (slim.conv2d, activation_fn=None, biases_initializer=None)."""
+    x = L.as_cuda_f32(input_)
+    if name not in VARIABLES:
+        VARIABLES[name] = [_trunc_normal((ks, ks, x.shape[-1], output_dim), stddev, hash(name) & 0xFFFF)]
+    return conv2d_raw(x, VARIABLES[name][0], None, stride=s, padding=padding)
+
+
+def deconv2d(input_, output_dim, ks=4, s=2, stddev=0.02, name="deconv2d"):
+    """ops.py:30-34 (slim.conv2d_transpose, 'SAME').  Kernel layout (kh, kw, Cout, Cin); k=3, s=2 only."""
+    x = L.as_cuda_f32(input_)
+    if ks != 3 or s != 2:
+        raise L.SgganError("deconv2d: only ks=3, s=2 (the generator's transposed convolutions) is implemented")
+    if name not in VARIABLES:
+        VARIABLES[name] = [_trunc_normal((ks, ks, output_dim, x.shape[-1]), stddev, hash(name) & 0xFFFF)]
+    return deconv2d_raw(x, VARIABLES[name][0], None)
+
+
+def instance_norm(input, name="instance_norm"):
+    """ops.py:13-22: moments over axes [1,2], epsilon 1e-5, scale ~ N(1, 0.02), offset 0."""
+    x = L.as_cuda_f32(input)
+    depth = x.shape[3]
+    if name not in VARIABLES:
+        g = torch.Generator().manual_seed(hash(name) & 0xFFFF)
+        VARIABLES[name] = [1.0 + 0.02 * torch.randn(depth, generator=g), torch.zeros(depth)]
+    scale, offset = VARIABLES[name]
+    return instance_norm_raw(x, scale, offset, eps=1e-5)
+
+
+def lrelu(x, leak=0.2, name="lrelu"):
+    """ops.py:36-37: tf.maximum(x, leak*x)."""
+    x = L.as_cuda_f32(x)
+    y = torch.empty_like(x)
+    L.check(L.lib().sggan_lrelu(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), x.numel(), leak, L.stream_ptr()))
+    return y
+
+
+def mask_reduce(h4, mask):
+    """multiply([h4, mask]) + reduce_sum(axis=-1, keepdims=True) (module.py:312-314)."""
+    h4, mask = L.as_cuda_f32(h4), L.as_cuda_f32(mask)
+    B, Hd, Wd, Cs = h4.shape
+    hm, wm = mask.shape[1], mask.shape[2]
+    out = torch.empty((B, max(Hd, hm), max(Wd, wm), 1), dtype=torch.float32, device=h4.device)
+    L.check(L.lib().sggan_mask_reduce(C.c_void_p(h4.data_ptr()), C.c_void_p(mask.data_ptr()), C.c_void_p(out.data_ptr()),
+                                      B, Hd, Wd, hm, wm, Cs, L.stream_ptr()))
+    return out

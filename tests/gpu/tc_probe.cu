@@ -79,25 +79,32 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
 
   p.A = dA;
   p.a_frame_pix = frame_pix;
+  p.a_row_stride = c.Cin;
   p.Cin = c.Cin;
   p.B = c.B;
   p.Wt = dW;
+  p.wt_taps = ntaps;
   p.ntaps = ntaps;
   p.CoutPad = c.CoutPad;
   p.Cout = c.Cout;
   p.BN = c.BN;
   for (int kh = 0; kh < c.k; ++kh)
-    for (int kw = 0; kw < c.k; ++kw) p.tap_off[kh * c.k + kw] = kh * P + kw;
+    for (int kw = 0; kw < c.k; ++kw) {
+      p.tap_off[kh * c.k + kw] = kh * P + kw;
+      p.tap_w[kh * c.k + kw] = uint8_t(kh * c.k + kw);
+    }
   p.M = c.H * P;
   p.P = P;
   p.Hv = c.H;
   p.Wv = c.W;
   p.out = dOut;
   p.out_f32 = c.out_f32;
-  p.out_bstride = int64_t(c.H) * c.W * c.Cout;
-  p.out_sy = int64_t(c.W) * c.Cout;
-  p.out_sx = c.Cout;
-  p.out_off = 0;
+  p.omap.frame_pix = int64_t(c.H) * c.W;
+  p.omap.C = c.Cout;
+  p.omap.H = c.H;
+  p.omap.W = c.W;
+  p.omap.P = c.W;
+  p.o_scale = 1;
   p.bias = dBias;
   p.stats = c.use_stats ? dStats : nullptr;
   p.act = c.act;
@@ -211,16 +218,22 @@ static int run_wgrad_case(int B, int H, int W, int Cx, int Cy, int BN, int k, in
   CK(cudaMemset(dW, 0, wel * 4));
   p.X = dX;
   p.x_frame_pix = xpix;
+  p.x_row_stride = Cx;
   p.Cx = Cx;
   p.Y = dY;
   p.y_frame_pix = ypix;
+  p.y_row_stride = Cy;
   p.Cy = Cy;
+  p.nx_valid = Cx;
+  p.ny_valid = Cy;
   p.BN = BN;
   p.B = B;
   p.ntaps = ntaps;
   for (int kh = 0; kh < k; ++kh)
-    for (int kw = 0; kw < k; ++kw) p.x_off[kh * k + kw] = kh * P + kw;
-  p.y_off = 0;
+    for (int kw = 0; kw < k; ++kw) {
+      p.x_off[kh * k + kw] = kh * P + kw;
+      p.y_off[kh * k + kw] = 0;
+    }
   p.Mpix = H * P;
   p.dW = dW;
   p.dw_tap_stride = int64_t(Cx) * Cy;
