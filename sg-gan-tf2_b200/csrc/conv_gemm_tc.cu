@@ -10,20 +10,37 @@
 // Replaces the cuDNN/Eigen calls behind tf.keras.layers.Conv2D / Conv2DTranspose and their
 // gradients on the reference path (module.py:211-216,232-265,284-311; model.py:196-197).
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA
-// issuer (one lane), warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31).
+// The convolution is L2-bandwidth bound unless operand re-use is organised on chip (measured:
+// 392 TFLOP/s with one TMA box per tap).  Two forms of re-use are built in:
+//   * the CTA tile is MT = 256 output positions x BN channels held as two 128-row accumulators in
+//     TMEM, so each weight tile (B) loaded into smem feeds two MMAs;
+//   * taps whose pixel offsets are consecutive (the kw taps of one filter row) form a "run": the
+//     A tile of a run is loaded ONCE as MT + 8 rows, and tap q reads it through a shared-memory
+//     descriptor whose start address is shifted by q rows (q * 128 B).  SWIZZLE_128B is a function
+//     of the absolute smem address, so a row-shifted descriptor (base_offset 0) addresses the same
+//     swizzled data -- verified on hardware by tests/gpu/tc_probe.cu `shift`.
+// A and B therefore travel in separate mbarrier rings fed by two producer warps.
+//
+// Warp roles (352 threads): warp 0 = A producer, warp 1 = TMEM allocator + MMA issuer, warp 2 = B
+// producer, warps 3..10 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31; two warps per quarter).
 #include "conv_gemm_tc.h"
 #include "tc_common.cuh"
 #include "tmap.h"
 
+#include <algorithm>
+#include <utility>
+#include <vector>
+
 namespace sggan {
 
 constexpr int kTileM = 128;
-constexpr int kChunkK = 64;                          // bf16 elements per 128-byte swizzled row
-constexpr int kABytes = kTileM * kChunkK * 2;        // 16 KB
+constexpr int kChunkK = 64;                    // bf16 elements per 128-byte swizzled row
+constexpr int kABytes = kTileM * kChunkK * 2;  // 16 KB: one 128-row A box
+constexpr int kHaloRows = 8;                   // one extra swizzle atom of rows covers runs of up to 8 taps
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 200 * 1024;              // pipeline bytes (leaves room for alignment slack)
-constexpr int kThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;  // pipeline bytes (leaves room for alignment slack)
+constexpr int kConvThreads = 352;  // 3 control warps + 8 epilogue warps
+constexpr int kWgradThreads = 192;
 
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
   if (act == SG_ACT_RELU) return v > 0.f ? v : 0.f;
@@ -37,153 +54,211 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-static inline uint32_t tmem_cols_for(int bn) {
+static inline uint32_t tmem_cols_for(int n) {
   uint32_t c = 32;
-  while ((int)c < bn) c <<= 1;
+  while ((int)c < n) c <<= 1;
   return c;
 }
 
 // =============================================================================================
-__global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const ConvGemmParams p, const int stages, const uint32_t tmem_cols) {
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA8,
+                    const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p, const int sa_stages,
+                    const int sb_stages, const uint32_t tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t full_bar[kMaxStages];
-  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ uint64_t a_full[kMaxStages], a_empty[kMaxStages], b_full[kMaxStages], b_empty[kMaxStages];
   __shared__ uint64_t acc_bar;
   __shared__ uint32_t tmem_base_sh;
+  __shared__ __align__(16) float sbias[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int BN = p.BN;
-  const int stage_bytes = kABytes + BN * 128;
-  const int m0 = blockIdx.x * kTileM, n0 = blockIdx.y * BN, b = blockIdx.z;
+  long long* dbg = p.dbg ? p.dbg + (int64_t(blockIdx.z) * gridDim.y * gridDim.x + blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  const int BN = p.BN, MT = p.MT, NA = MT / kTileM;
+  const int a_stage_bytes = (MT + kHaloRows) * 128, b_stage_bytes = BN * 128;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + sa_stages * a_stage_bytes;
+  const int m0 = blockIdx.x * MT, n0 = blockIdx.y * BN, b = blockIdx.z;
   const int cchunks = p.Cin / kChunkK;
-  const int ksteps = p.ntaps * cchunks;
+  const int agroups = p.nruns * cchunks;  // A tiles this CTA consumes
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
+    for (int s = 0; s < sa_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < sb_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     mbar_init(&acc_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA8);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(&tmem_base_sh, tmem_cols);
+  for (int t = threadIdx.x; t < 256; t += kConvThreads)
+    sbias[t] = (p.bias != nullptr && t < BN && n0 + t < p.Cout) ? __ldg(p.bias + n0 + t) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_sh;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ A producer: one tile per (run, chunk)
     if (lane == 0) {
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int s = ks % stages;
-        const uint32_t ph = (ks / stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1, 1);
-        const int tap = ks / cchunks, cc = ks - tap * cchunks;
-        uint8_t* sa = smem + s * stage_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_3d(&tmA, &full_bar[s], sa, cc * kChunkK, m0 + p.tap_off[tap], b);
-        tma_load_2d(&tmB, &full_bar[s], sa + kABytes, cc * kChunkK, int(p.tap_w[tap]) * p.CoutPad + n0);
+      for (int g = 0; g < agroups; ++g) {
+        const int s = g % sa_stages;
+        const uint32_t ph = (g / sa_stages) & 1;
+        mbar_wait(&a_empty[s], ph ^ 1, 1);
+        const int r = g / cchunks, cc = g - r * cchunks;
+        uint8_t* sa = smA + s * a_stage_bytes;
+        const int row0 = m0 + p.run_off[r];
+        mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
+        for (int a = 0; a < NA; ++a) tma_load_3d(&tmA, &a_full[s], sa + a * kABytes, cc * kChunkK, row0 + a * kTileM, b);
+        tma_load_3d(&tmA8, &a_full[s], sa + NA * kABytes, cc * kChunkK, row0 + MT, b);
       }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ B producer: one weight tile per (tap, chunk)
+    if (lane == 0) {
+      int it = 0;
+      for (int r = 0, t0 = 0; r < p.nruns; t0 += p.run_len[r], ++r)
+        for (int cc = 0; cc < cchunks; ++cc)
+          for (int q = 0; q < p.run_len[r]; ++q, ++it) {
+            const int s = it % sb_stages;
+            const uint32_t ph = (it / sb_stages) & 1;
+            mbar_wait(&b_empty[s], ph ^ 1, 4);
+            mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
+            tma_load_2d(&tmB, &b_full[s], smB + s * b_stage_bytes, cc * kChunkK, int(p.run_w[t0 + q]) * p.CoutPad + n0);
+          }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_f32(kTileM, BN, 0, 0);
-      for (int ks = 0; ks < ksteps; ++ks) {
-        const int s = ks % stages;
-        const uint32_t ph = (ks / stages) & 1;
-        mbar_wait(&full_bar[s], ph, 2);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * stage_bytes);
-        const uint64_t adesc = desc_kmajor_sw128(sa);
-        const uint64_t bdesc = desc_kmajor_sw128(sa + kABytes);
+      int it = 0, g = 0;
+      for (int r = 0; r < p.nruns; ++r)
+        for (int cc = 0; cc < cchunks; ++cc, ++g) {
+          const int sa_i = g % sa_stages;
+          mbar_wait(&a_full[sa_i], (g / sa_stages) & 1, 2);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smA + sa_i * a_stage_bytes);
+          for (int q = 0; q < p.run_len[r]; ++q, ++it) {
+            const int sb_i = it % sb_stages;
+            mbar_wait(&b_full[sb_i], (it / sb_stages) & 1, 5);
+            tc_fence_after();
+            const uint64_t bdesc = desc_kmajor_sw128(smem_u32(smB + sb_i * b_stage_bytes));
+            for (int a = 0; a < NA; ++a) {
+              // tap q of the run: the A view starts q rows (q * 128 B) into the tile
+              const uint64_t adesc = desc_kmajor_sw128(a_base + uint32_t(a * kTileM + q) * 128u);
 #pragma unroll
-        for (int k = 0; k < kChunkK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
-          umma_bf16(tmem_acc, adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (ks | k) != 0);
-        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
-      }
-      umma_commit(&acc_bar);  // accumulator complete
+              for (int k = 0; k < kChunkK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
+                umma_bf16(tmem_acc + uint32_t(a * BN), adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc,
+                          (it | k) != 0);
+            }
+            umma_commit(&b_empty[sb_i]);  // frees the weight slot once these MMAs retire
+          }
+          umma_commit(&a_empty[sa_i]);
+        }
+      umma_commit(&acc_bar);  // accumulators complete
+      if (dbg) dbg[2] = clock64();
     }
   } else {
-    // ------------------------------------------------------------ epilogue (128 threads)
+    // ------------------------------------------------------------ epilogue (8 warps = 256 threads)
+    // Two warps share each TMEM lane quarter and split the 32-column chunks between them, so every
+    // scheduler has two epilogue warps to interleave.  The per-element work is kept branch-free: bias
+    // comes from smem (zero padded), padded weight rows make columns >= Cout exactly zero, the
+    // activation is chosen once per chunk.
     mbar_wait(&acc_bar, 0, 3);
     tc_fence_after();
     const int q = warp & 3;
+    const int half = (warp - 3) >> 2;
     const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const int i = m / p.P, j = m - i * p.P;
-    const int oi = i * p.o_scale + p.o_a, oj = j * p.o_scale + p.o_b;
-    const bool valid = (m < p.M) && (i < p.Hv) && (j < p.Wv) && (oi < p.omap.H) && (oj < p.omap.W);
+    const int et = threadIdx.x - 96;  // 0..255
+    if (dbg && et == 0) dbg[3] = clock64();
     float* tsm = reinterpret_cast<float*>(smem);  // [BN][129] transposed fp32 tile for the statistics
-    const int64_t obase = (int64_t(b) * p.omap.frame_pix + (valid ? frame_pixel(p.omap, oi, oj) : 0)) * p.omap.C;
-    const bool vec_ok = (!p.out_f32) && ((p.omap.C & 7) == 0);
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
-      const int nb = n0 + c0;
+    const bool has_stats = p.stats != nullptr;
+    const int act = p.act;
+    const float alpha = p.act_alpha;
+    for (int a = 0; a < NA; ++a) {
+      const int m = m0 + a * kTileM + row;
+      const int i = m / p.P, j = m - i * p.P;
+      const int oi = i * p.o_scale + p.o_a, oj = j * p.o_scale + p.o_b;
+      const bool valid = (m < p.M) && (i < p.Hv) && (j < p.Wv) && (oi < p.omap.H) && (oj < p.omap.W);
+      const int64_t obase = (int64_t(b) * p.omap.frame_pix + (valid ? frame_pixel(p.omap, oi, oj) : 0)) * p.omap.C;
+      const bool vec_ok = (!p.out_f32) && ((p.omap.C & 7) == 0);
+      const float msk = valid ? 1.f : 0.f;
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        float v[32];
+        tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(a * BN + c0), v);
+        const int nb = n0 + c0;
+        const float4* sb4 = reinterpret_cast<const float4*>(sbias + c0);
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int n = nb + e;
-        float x = v[e];
-        if (p.bias != nullptr && n < p.Cout) x += __ldg(p.bias + n);
-        x = apply_act(x, p.act, p.act_alpha);
-        // statistics are taken over the values as stored (bf16), so that the normalisation that
-        // follows is exact for what it reads (H*W == 1 must give exactly beta)
-        v[e] = p.out_f32 ? x : __bfloat162float(__float2bfloat16_rn(x));
-      }
-      if (p.stats != nullptr) {
+        for (int g = 0; g < 8; ++g) {
+          const float4 bb = sb4[g];
+          v[4 * g] += bb.x; v[4 * g + 1] += bb.y; v[4 * g + 2] += bb.z; v[4 * g + 3] += bb.w;
+        }
+        if (act == SG_ACT_RELU) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) tsm[(c0 + e) * 129 + row] = (valid && nb + e < p.Cout) ? v[e] : 0.f;
-      }
-      if (valid) {
-        if (vec_ok && nb + 32 <= p.Cout) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + nb);
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+        } else if (act == SG_ACT_LRELU) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 w;
-            w.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-            w.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-            w.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-            w.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-            dst[g] = w;
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], alpha * v[e]);  // 0 < alpha < 1
+        } else if (act == SG_ACT_TANH) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = tanhf(v[e]);
+        }
+        uint32_t pk[16];
+        if (!p.out_f32) {
+          // statistics are taken over the values as stored (bf16), so that the normalisation that
+          // follows is exact for what it reads (H*W == 1 must give exactly beta)
+#pragma unroll
+          for (int e2 = 0; e2 < 16; ++e2) {
+            pk[e2] = pack_bf16x2(v[2 * e2], v[2 * e2 + 1]);
+            v[2 * e2] = __uint_as_float(pk[e2] << 16);
+            v[2 * e2 + 1] = __uint_as_float(pk[e2] & 0xffff0000u);
           }
-        } else if (p.out_f32) {
-          float* dst = reinterpret_cast<float*>(p.out) + obase;
+        }
+        if (has_stats) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (nb + e < p.Cout) dst[nb + e] = v[e];
-        } else {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + obase;
+          for (int e = 0; e < 32; ++e) tsm[(c0 + e) * 129 + row] = v[e] * msk;
+        }
+        if (valid) {
+          if (vec_ok && nb + 32 <= p.Cout) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + nb);
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (nb + e < p.Cout) dst[nb + e] = __float2bfloat16_rn(v[e]);
+            for (int g = 0; g < 4; ++g) dst[g] = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+          } else if (p.out_f32) {
+            float* dst = reinterpret_cast<float*>(p.out) + obase;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (nb + e < p.Cout) dst[nb + e] = v[e];
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + obase;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (nb + e < p.Cout) dst[nb + e] = __float2bfloat16_rn(v[e]);
+          }
         }
       }
-    }
-    if (p.stats != nullptr) {
-      named_bar_sync(1, 128);
-      const int t = threadIdx.x - 64;  // 0..127
-      for (int c = t; c < BN; c += 128) {
-        const int n = n0 + c;
-        if (n >= p.Cout) continue;
-        const float* col = tsm + c * 129;
-        float s1 = 0.f, s2 = 0.f;
+      if (has_stats) {
+        named_bar_sync(1, 256);
+        for (int c = et; c < BN; c += 256) {
+          const int n = n0 + c;
+          if (n >= p.Cout) continue;
+          const float* col = tsm + c * 129;
+          float s1 = 0.f, s2 = 0.f, s1b = 0.f, s2b = 0.f;
 #pragma unroll 8
-        for (int r = 0; r < 128; ++r) {
-          const float x = col[r];
-          s1 += x;
-          s2 += x * x;
+          for (int r = 0; r < 128; r += 2) {
+            const float x = col[r], y = col[r + 1];
+            s1 += x; s2 += x * x;
+            s1b += y; s2b += y * y;
+          }
+          float* dst = p.stats + (int64_t(b) * p.Cout + n) * 2;
+          atomicAdd(dst, s1 + s1b);
+          atomicAdd(dst + 1, s2 + s2b);
         }
-        float* dst = p.stats + (int64_t(b) * p.Cout + n) * 2;
-        atomicAdd(dst, s1);
-        atomicAdd(dst + 1, s2);
+        if (a + 1 < NA) named_bar_sync(1, 256);  // tsm is rewritten by the next accumulator
       }
+      if (dbg && et == 0) dbg[4 + a] = clock64();
     }
     tc_fence_before();
   }
@@ -192,10 +267,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_acc, tmem_cols);
   }
+  if (dbg && threadIdx.x == 0) dbg[6] = clock64();
 }
 
 // =============================================================================================
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                      const WgradParams p, const int stages, const uint32_t tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
@@ -300,25 +376,59 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
 // =============================================================================================
 // Host side
-static int stages_for(int bn) {
+static int wgrad_stages_for(int bn) {
   int st = kSmemBudget / (kABytes + bn * 128);
   return st > kMaxStages ? kMaxStages : st;
 }
 
-int prepare_conv_gemm(const ConvGemmParams& p, ConvGemmLaunch* L) {
+// Sort the taps by pixel offset and group consecutive offsets into runs (at most kHaloRows taps each).
+static void build_runs(ConvGemmParams& p) {
+  std::vector<std::pair<int, int>> t;
+  for (int i = 0; i < p.ntaps; ++i) t.push_back({p.tap_off[i], int(p.tap_w[i])});
+  std::sort(t.begin(), t.end());
+  p.nruns = 0;
+  int i = 0;
+  while (i < p.ntaps) {
+    int len = 1;
+    while (i + len < p.ntaps && len < kHaloRows && t[i + len].first == t[i].first + len) ++len;
+    p.run_off[p.nruns] = t[i].first;
+    p.run_len[p.nruns] = uint8_t(len);
+    ++p.nruns;
+    i += len;
+  }
+  for (int k = 0; k < p.ntaps; ++k) p.run_w[k] = uint8_t(t[k].second);
+}
+
+int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
+  ConvGemmParams p = pin;
   if (p.Cin % 64 != 0 || p.Cin <= 0) return -10;
   if (!(p.BN == 32 || p.BN == 64 || p.BN == 128 || p.BN == 256)) return -11;
   if (p.CoutPad % p.BN != 0 || p.ntaps < 1 || p.ntaps > SGGAN_MAX_TAPS) return -12;
+  build_runs(p);
+  // two accumulators per CTA when that still leaves enough CTAs to fill the 148 SMs
+  const int64_t ctas256 = int64_t((p.M + 255) / 256) * (p.CoutPad / p.BN) * p.B;
+  if (p.MT != 128 && p.MT != 256) p.MT = ctas256 >= 120 ? 256 : 128;
+  const int a_stage = (p.MT + kHaloRows) * 128, b_stage = p.BN * 128;
+  // split the smem budget: at least 2 A stages, the rest to B (up to 8), then leftover back to A
+  int sa = 2, sb = (kSmemBudget - sa * a_stage) / b_stage;
+  if (sb > kMaxStages) sb = kMaxStages;
+  if (sb < 2) return -13;
+  sa = (kSmemBudget - sb * b_stage) / a_stage;
+  if (sa > 4) sa = 4;
   L->p = p;
-  L->stages = stages_for(p.BN);
-  L->tmem_cols = tmem_cols_for(p.BN);
-  L->smem = size_t(L->stages) * (kABytes + p.BN * 128) + 1024;
-  L->grid_x = (p.M + kTileM - 1) / kTileM;
+  L->sa_stages = sa;
+  L->sb_stages = sb;
+  L->tmem_cols = tmem_cols_for((p.MT / 128) * p.BN);
+  L->smem = size_t(sa) * a_stage + size_t(sb) * b_stage + 1024;
+  if (L->smem < size_t(p.BN) * 129 * 4 + 1024) L->smem = size_t(p.BN) * 129 * 4 + 1024;  // epilogue statistics tile
+  L->grid_x = (p.M + p.MT - 1) / p.MT;
   L->grid_y = p.CoutPad / p.BN;
   L->grid_z = p.B;
-  int r = make_tmap_bf16_3d(&L->tmA, p.A, p.Cin, p.a_frame_pix, p.B, uint64_t(p.a_row_stride) * 2,
-                            uint64_t(p.a_frame_pix) * p.a_row_stride * 2, 64, 128);
+  const uint64_t rs = uint64_t(p.a_row_stride) * 2, fs = uint64_t(p.a_frame_pix) * p.a_row_stride * 2;
+  int r = make_tmap_bf16_3d(&L->tmA, p.A, p.Cin, p.a_frame_pix, p.B, rs, fs, 64, 128);
   if (r) return -1000 - r;
+  r = make_tmap_bf16_3d(&L->tmA8, p.A, p.Cin, p.a_frame_pix, p.B, rs, fs, 64, kHaloRows);
+  if (r) return -1500 - r;
   r = make_tmap_bf16_2d(&L->tmB, p.Wt, p.Cin, uint64_t(p.wt_taps) * p.CoutPad, uint64_t(p.Cin) * 2, 64, p.BN);
   if (r) return -2000 - r;
   static bool attr_set = false;
@@ -333,7 +443,8 @@ int prepare_conv_gemm(const ConvGemmParams& p, ConvGemmLaunch* L) {
 
 int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
   dim3 grid(L.grid_x, L.grid_y, L.grid_z);
-  conv_gemm_tc_kernel<<<grid, kThreads, L.smem, st>>>(L.tmA, L.tmB, L.p, L.stages, L.tmem_cols);
+  conv_gemm_tc_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tmA, L.tmA8, L.tmB, L.p, L.sa_stages, L.sb_stages,
+                                                          L.tmem_cols);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -4000 - int(e);
 }
@@ -343,7 +454,7 @@ int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L) {
   if (!(p.BN == 64 || p.BN == 128 || p.BN == 256) || p.Cy % p.BN != 0) return -21;
   if (p.ntaps < 1 || p.ntaps > SGGAN_MAX_TAPS || p.ksplit < 1) return -22;
   L->p = p;
-  L->stages = stages_for(p.BN);
+  L->stages = wgrad_stages_for(p.BN);
   L->tmem_cols = tmem_cols_for(p.BN);
   L->smem = size_t(L->stages) * (kABytes + p.BN * 128) + 1024;
   L->grid_x = (p.x_pair ? 1 : p.Cx / 128) * p.ntaps;
@@ -367,7 +478,7 @@ int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L) {
 
 int run_wgrad_gemm(const WgradLaunch& L, cudaStream_t st) {
   dim3 grid(L.grid_x, L.grid_y, L.grid_z);
-  wgrad_gemm_tc_kernel<<<grid, kThreads, L.smem, st>>>(L.tmX, L.tmY, L.p, L.stages, L.tmem_cols);
+  wgrad_gemm_tc_kernel<<<grid, kWgradThreads, L.smem, st>>>(L.tmX, L.tmY, L.p, L.stages, L.tmem_cols);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -4000 - int(e);
 }

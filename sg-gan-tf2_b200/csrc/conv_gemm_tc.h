@@ -11,9 +11,9 @@ namespace sggan {
 // capturable in a CUDA graph).
 struct ConvGemmLaunch {
   ConvGemmParams p;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmA8, tmB;  // A boxes of 128 rows / 8 halo rows, weight boxes of BN rows
   int grid_x, grid_y, grid_z;
-  int stages;
+  int sa_stages, sb_stages;  // depth of the A ring and of the B ring
   unsigned tmem_cols;
   size_t smem;
 };

@@ -66,6 +66,14 @@ struct ConvGemmParams {
   int BN;             // N tile: 32, 64, 128, 256
   int tap_off[SGGAN_MAX_TAPS];
   uint8_t tap_w[SGGAN_MAX_TAPS];  // slab index in Wt for tap t
+  // Derived by prepare_conv_gemm: taps sorted by offset and grouped into runs of consecutive pixel
+  // offsets.  One A tile (MT + 8 rows) is loaded per (run, channel chunk) and every tap of the run
+  // reads it through a row-shifted shared-memory descriptor (the kw taps of a filter row share one load).
+  int nruns;
+  int run_off[SGGAN_MAX_TAPS];
+  uint8_t run_len[SGGAN_MAX_TAPS];
+  uint8_t run_w[SGGAN_MAX_TAPS];  // slab index of the sorted taps, runs back to back
+  int MT;                         // rows of the CTA tile: 128 (one accumulator) or 256 (two)
   int M;                          // linear output positions per image
   int P;                          // pitch used to decode m -> (i, j)
   int Hv, Wv;                     // valid rows / columns
@@ -77,6 +85,7 @@ struct ConvGemmParams {
   float* stats;       // [B][Cout][2] (sum, sum of squares) accumulated atomically, or null
   int act;
   float act_alpha;
+  long long* dbg;  // optional per-CTA clock64 stamps [grid][8] (tests/gpu/tc_probe.cu); null in production
 };
 
 // ---------------------------------------------------------------------------------------------
