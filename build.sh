@@ -3,4 +3,4 @@
 set -e
 cd "$(dirname "$0")/sg-gan-tf2_b200"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC \
-  -o libsggan_sm100.so csrc/api.cu csrc/engine.cu csrc/glue.cu csrc/conv_gemm_tc.cu csrc/tmap.cu "$@"
+  -o libsggan_sm100.so csrc/*.cu "$@"

@@ -252,9 +252,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             s1 += x; s2 += x * x;
             s1b += y; s2b += y * y;
           }
-          float* dst = p.stats + (int64_t(b) * p.Cout + n) * 2;
-          atomicAdd(dst, s1 + s1b);
-          atomicAdd(dst + 1, s2 + s2b);
+          const int tile = p.stats_t0 + blockIdx.x * NA + a;
+          float2* dst = reinterpret_cast<float2*>(p.stats) + (int64_t(b) * p.stats_T + tile) * p.Cout + n;
+          *dst = make_float2(s1 + s1b, s2 + s2b);
         }
         if (a + 1 < NA) named_bar_sync(1, 256);  // tsm is rewritten by the next accumulator
       }
@@ -356,13 +356,27 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int row = q * 32 + lane;
     const int xg = mt * kTileM + row;
     float* dst = p.dW + int64_t(tap) * p.dw_tap_stride + int64_t(xg) * p.dw_sx;
+    // y channels contiguous in dW and 16-byte aligned rows: 128-bit vector reductions
+    const bool vec = (p.dw_sy == 1) && ((p.dw_sx & 3) == 0) && ((p.dw_tap_stride & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(p.dW) & 15) == 0);
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), v);  // warp-collective: no divergence here
       if (xg < p.nx_valid) {
+        if (vec && n0 + c0 + 32 <= p.ny_valid) {
+          float* d4 = dst + n0 + c0;
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (n0 + c0 + e < p.ny_valid) atomicAdd(dst + int64_t(n0 + c0 + e) * p.dw_sy, v[e]);
+          for (int g = 0; g < 8; ++g)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d4 + 4 * g), "f"(v[4 * g]),
+                         "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
+                         : "memory");
+        } else {
+          const int64_t sy = p.dw_sy;
+          float* d1 = dst + int64_t(n0 + c0) * sy;
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (n0 + c0 + e < p.ny_valid) atomicAdd(d1 + e * sy, v[e]);
+        }
       }
     }
     tc_fence_before();

@@ -94,6 +94,11 @@ int layer_geometry(Layer& l) {
   l.packf.Cin = l.packd.Cin = l.Cin; l.packf.Cout = l.packd.Cout = l.Cout;
   l.unpack_mode = -1;
   l.wscratch_elems = 0;
+  {  // upper bound on the number of 128-row tiles the forward launches produce per image
+    const int m = (l.type == LT_DECONV ? l.Hin : l.Hout) * l.P;
+    l.stats_T_max = (l.type == LT_DECONV ? 4 : 1) * ((m + 127) / 128 + 1);
+    l.stats_T = 0;
+  }
   switch (l.type) {
     case LT_S1:
     case LT_S2:
@@ -138,7 +143,18 @@ static int bn_for(int n) { return n >= 256 ? 256 : n; }
 
 // forward launches.  `out`/`omap`: destination of the conv result (raw Y, the next frame, or an fp32
 // plain tensor).
+static int layer_prepare_fwd_impl(Layer& l, const float* bias, void* out, const FrameMap& omap, int out_f32, bool dry);
 int layer_prepare_fwd(Layer& l, const float* bias, void* out, const FrameMap& omap, int out_f32, bool dry) {
+  int r = layer_prepare_fwd_impl(l, bias, out, omap, out_f32, dry);
+  if (r || dry) return r;
+  int T = 0;
+  for (auto& L : l.fwd) { L.p.stats_t0 = T; T += L.grid_x * (L.p.MT / 128); }
+  for (auto& L : l.fwd) L.p.stats_T = T;
+  l.stats_T = T;
+  if (l.has_norm && T > l.stats_T_max) return SGGAN_E_WORKSPACE;
+  return 0;
+}
+static int layer_prepare_fwd_impl(Layer& l, const float* bias, void* out, const FrameMap& omap, int out_f32, bool dry) {
   l.fwd.clear();
   const int k = l.k, P = l.P;
   ConvGemmParams p;
@@ -146,7 +162,7 @@ int layer_prepare_fwd(Layer& l, const float* bias, void* out, const FrameMap& om
   p.A = l.X; p.a_frame_pix = l.xmap.frame_pix; p.a_row_stride = l.xmap.C; p.B = l.nb;
   p.Wt = l.Wf; p.wt_taps = l.packf.T; p.CoutPad = l.CoutN; p.Cout = l.Cout; p.BN = bn_for(l.CoutN);
   p.P = P; p.out = out; p.out_f32 = out_f32; p.omap = omap; p.bias = bias;
-  p.stats = l.has_norm ? l.stats : nullptr;
+  p.stats = l.has_norm ? l.stats_part : nullptr;
   if (!l.has_norm) p.act = l.act;
   auto push = [&](const ConvGemmParams& q) -> int {
     ConvGemmLaunch L;
@@ -405,7 +421,7 @@ static Layer make_layer(Net& n, LayerType type, int k, PadMode pad, int Cin, int
   Layer l;
   l.type = type; l.k = k; l.pad = pad; l.Cin = Cin; l.Cout = Cout; l.Hin = Hin; l.Win = Win;
   l.has_norm = norm; l.act = act; l.alpha = alpha; l.nb = nb; l.nbv = nbv;
-  l.X = l.Y = l.dY = nullptr; l.dX = nullptr; l.Yf32 = nullptr; l.stats = l.bsums = nullptr; l.Wf = l.Wd = nullptr;
+  l.X = l.Y = l.dY = nullptr; l.dX = nullptr; l.Yf32 = nullptr; l.stats = l.bsums = l.stats_part = nullptr; l.Wf = l.Wd = nullptr;
   l.wscratch = nullptr;
   l.ti_w = int(n.T.size());
   if (type == LT_DECONV) add_tensor(n, 4, k, k, Cout, Cin); else add_tensor(n, 4, k, k, Cin, Cout);
@@ -469,6 +485,7 @@ void Engine::alloc_and_prepare(Net& n, Arena& a, bool zero_part) {
     n.g = (float*)a.take(size_t(n.nparams) * 4);
     for (auto& l : n.L) {
       l.stats = l.has_norm ? (float*)a.take(size_t(l.nb) * l.Cout * 2 * 4) : nullptr;
+      l.stats_part = l.has_norm ? (float*)a.take(size_t(l.nb) * l.stats_T_max * l.Cout * 2 * 4) : nullptr;
       l.bsums = l.has_norm ? (float*)a.take(size_t(l.nbv) * l.Cout * 2 * 4) : nullptr;
       l.wscratch = l.wscratch_elems ? (float*)a.take(size_t(l.wscratch_elems) * 4) : nullptr;
     }
@@ -656,15 +673,13 @@ int Engine::gen_forward(const float* real_A, float* fake_out) {
   const int nl = int(G.L.size());
   for (int li = 0; li < nl; ++li) {
     Layer& l = G.L[li];
-    if (l.has_norm) {
-      if (cudaMemsetAsync(l.stats, 0, size_t(l.nb) * l.Cout * 8, st) != cudaSuccess) return SGGAN_E_CUDA;
-    }
     const bool in_block = (li >= 3 && li < 3 + 2 * cfg.n_blocks);
     const bool timed = prof_on && in_block && prof_used + 2 <= prof_ev.size();
     if (timed) cudaEventRecord(prof_ev[prof_used++], st);
     if ((r = run_conv_list(l.fwd))) return r;
     if (timed) cudaEventRecord(prof_ev[prof_used++], st);
     if (!l.has_norm) continue;
+    launch_stats_finalize(l.stats_part, l.nb, l.stats_T, l.Cout, l.stats, st); ++nlaunch;
     Layer& nx = G.L[li + 1];
     const bool block_b = in_block && ((li - 3) & 1) == 1;
     if (block_b) in_apply(G, li, nx.X, nx.xmap, G.L[li - 1].X, &G.L[li - 1].xmap);  // y + x (module.py:217)
@@ -685,10 +700,11 @@ int Engine::disc_forward_2b(const float* first, const float* second, int nimg_ea
   const int nl = int(D.L.size());
   for (int li = 0; li < nl; ++li) {
     Layer& l = D.L[li];
-    if (l.has_norm)
-      if (cudaMemsetAsync(l.stats, 0, size_t(l.nb) * l.Cout * 8, st) != cudaSuccess) return SGGAN_E_CUDA;
     if ((r = run_conv_list(l.fwd))) return r;
-    if (l.has_norm) in_apply(D, li, D.L[li + 1].X, D.L[li + 1].xmap, nullptr, nullptr);
+    if (l.has_norm) {
+      launch_stats_finalize(l.stats_part, l.nb, l.stats_T, l.Cout, l.stats, st); ++nlaunch;
+      in_apply(D, li, D.L[li + 1].X, D.L[li + 1].xmap, nullptr, nullptr);
+    }
   }
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }

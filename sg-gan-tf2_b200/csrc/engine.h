@@ -42,6 +42,8 @@ struct Layer {
   float* Yf32;
   int dxH, dxW, dx_oy, dx_ox, dx_fold, dx_f32;
   float *stats, *bsums;
+  float* stats_part;  // per-tile partial statistics written by the conv epilogue
+  int stats_T, stats_T_max;
   sg_bf16 *Wf, *Wd;
   PackParams packf, packd;
   float* wscratch;

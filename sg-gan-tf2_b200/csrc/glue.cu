@@ -70,7 +70,14 @@ __device__ __forceinline__ void grad_read8(const GradSrc& g, int b, int i, int j
                                            float* acc) {
   if (g.ptr == nullptr) return;
   int rr[3], cc[3];
-  const int nr = reflect_set(i, H, g.fold, rr), nc = reflect_set(j, W, g.fold, cc);
+  int nr = 1, nc = 1;
+  rr[0] = i;
+  cc[0] = j;
+  // only pixels within `fold` of the image edge receive folded-back border gradient
+  if (g.fold > 0 && (i <= g.fold || i >= H - 1 - g.fold || j <= g.fold || j >= W - 1 - g.fold)) {
+    nr = reflect_set(i, H, g.fold, rr);
+    nc = reflect_set(j, W, g.fold, cc);
+  }
   for (int a = 0; a < nr; ++a)
     for (int q = 0; q < nc; ++q) {
       const int64_t idx = ((int64_t(b) * g.Hs + (rr[a] + g.oy)) * g.Ws + (cc[q] + g.ox)) * C + c0;
@@ -94,8 +101,9 @@ __device__ __forceinline__ void grad_read8(const GradSrc& g, int b, int i, int j
 
 constexpr int kGlueThreads = 256;
 static inline int pix_per_block_for(int HW, int B) {
-  // about 6 blocks per SM over the whole grid, at least 64 pixels per block
-  const int want_blocks_per_image = (148 * 6 + B - 1) / B;
+  // about 3 blocks per SM over the whole grid (fat blocks amortise the per-block coefficient set-up),
+  // at least 64 pixels per block
+  const int want_blocks_per_image = (148 * 3 + B - 1) / B;
   int ppb = (HW + want_blocks_per_image - 1) / want_blocks_per_image;
   ppb = (ppb + 63) / 64 * 64;
   return ppb < 64 ? 64 : ppb;
@@ -166,80 +174,37 @@ void launch_lrelu(const float* x, float* y, int64_t n, float leak, cudaStream_t 
 }
 
 // ------------------------------------------------------------------------------------------ IN fwd
-__device__ __forceinline__ void in_coeffs(const float* stats, const float* gamma, const float* beta, int b, int C,
-                                          int c0, float n, float eps, float* mean, float* rstd, float* scale,
-                                          float* shift) {
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = c0 + e;
-    if (stats != nullptr) {
-      const float s1 = stats[(int64_t(b) * C + c) * 2], s2 = stats[(int64_t(b) * C + c) * 2 + 1];
-      const float mu = s1 / n;
-      const float var = fmaxf(s2 / n - mu * mu, 0.f);
-      mean[e] = mu;
-      rstd[e] = rsqrtf(var + eps);
-    } else {
-      mean[e] = 0.f;
-      rstd[e] = 1.f;
-    }
-    const float g = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-    scale[e] = g * rstd[e];
-    shift[e] = be - mean[e] * scale[e];
-  }
-}
-
-__global__ void __launch_bounds__(kGlueThreads) in_apply_kernel(const InApplyParams p, const int ppb) {
-  const int b = blockIdx.y;
-  const int C8 = p.C >> 3;
-  const int cg = threadIdx.x % C8, lp = threadIdx.x / C8, ppi = kGlueThreads / C8;
-  const int c0 = cg * 8, HW = p.H * p.W;
-  float mean[8], rstd[8], scale[8], shift[8];
-  in_coeffs(p.stats, p.gamma, p.beta, b, p.C, c0, float(HW), p.eps, mean, rstd, scale, shift);
-  const int pix0 = blockIdx.x * ppb, pix1 = min(HW, pix0 + ppb);
-  constexpr int U = 4;  // pixels in flight per thread: all 128-bit loads are issued before any use
-  const sg_bf16* ybase = p.Y + int64_t(b) * HW * p.C + c0;
-  const sg_bf16* rbase = p.res ? p.res + int64_t(b) * p.rmap.frame_pix * p.rmap.C + c0 : nullptr;
-  for (int pix = pix0 + lp; pix < pix1; pix += U * ppi) {
-    uint4 raw[U], rr[U];
-    int pi[U], pj[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int q = pix + u * ppi;
-      pi[u] = q / p.W;
-      pj[u] = q - pi[u] * p.W;
-      if (q < pix1) {
-        raw[u] = __ldg(reinterpret_cast<const uint4*>(ybase + int64_t(q) * p.C));
-        if (rbase) rr[u] = __ldg(reinterpret_cast<const uint4*>(rbase + frame_pixel(p.rmap, pi[u], pj[u]) * p.rmap.C));
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (pix + u * ppi >= pix1) break;
-      float y[8];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 t = __bfloat1622float2(h[k]);
-        y[2 * k] = act_fwd(fmaf(t.x, scale[2 * k], shift[2 * k]), p.act, p.act_alpha);
-        y[2 * k + 1] = act_fwd(fmaf(t.y, scale[2 * k + 1], shift[2 * k + 1]), p.act, p.act_alpha);
-      }
-      if (rbase) {
-        const __nv_bfloat162* hr = reinterpret_cast<const __nv_bfloat162*>(&rr[u]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 t = __bfloat1622float2(hr[k]);
-          y[2 * k] += t.x;
-          y[2 * k + 1] += t.y;
-        }
-      }
-      write_frame8(p.dst, p.dmap, b, pi[u], pj[u], c0, y);
+// Fixed-order reduction of the per-tile partials: 16 slices of the tile range are summed sequentially by
+// 16 threads per channel, then combined in a fixed tree -> bitwise reproducible statistics.
+__global__ void __launch_bounds__(1024) stats_finalize_kernel(const float2* __restrict__ part, int T, int C,
+                                                              float2* stats) {
+  __shared__ float2 sh[16][64];
+  const int b = blockIdx.y, cl = threadIdx.x & 63, sl = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  const int per = (T + 15) / 16, t0 = sl * per, t1 = min(T, t0 + per);
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C) {
+    const float2* p = part + int64_t(b) * T * C + c;
+    for (int t = t0; t < t1; ++t) {
+      const float2 v = __ldg(p + int64_t(t) * C);
+      s1 += v.x;
+      s2 += v.y;
     }
   }
+  sh[sl][cl] = make_float2(s1, s2);
+  __syncthreads();
+  for (int w = 8; w > 0; w >>= 1) {
+    if (sl < w) {
+      sh[sl][cl].x += sh[sl + w][cl].x;
+      sh[sl][cl].y += sh[sl + w][cl].y;
+    }
+    __syncthreads();
+  }
+  if (sl == 0 && c < C) stats[int64_t(b) * C + c] = sh[0][cl];
 }
-void launch_in_apply(const InApplyParams& p, cudaStream_t st) {
-  const int HW = p.H * p.W, ppb = pix_per_block_for(HW, p.B);
-  dim3 grid((HW + ppb - 1) / ppb, p.B);
-  in_apply_kernel<<<grid, kGlueThreads, 0, st>>>(p, ppb);
+void launch_stats_finalize(const float* part, int B, int T, int C, float* stats, cudaStream_t st) {
+  dim3 grid((C + 63) / 64, B);
+  stats_finalize_kernel<<<grid, 1024, 0, st>>>(reinterpret_cast<const float2*>(part), T, C, reinterpret_cast<float2*>(stats));
 }
 
 __global__ void __launch_bounds__(kGlueThreads) in_stats_kernel(const sg_bf16* __restrict__ y, int HW, int C,
@@ -275,105 +240,7 @@ void launch_in_stats(const sg_bf16* y, int B, int HW, int C, float* stats, cudaS
   in_stats_kernel<<<grid, kGlueThreads, 2 * C * sizeof(float), st>>>(y, HW, C, stats, ppb);
 }
 
-// ------------------------------------------------------------------------------------------ IN bwd
-template <bool kApply>
-__global__ void __launch_bounds__(kGlueThreads) in_bwd_kernel(const InBwdParams p, const int ppb) {
-  extern __shared__ float sred[];
-  const int b = blockIdx.y;
-  const int ba = b < p.nb_act ? b : b - p.act_wrap;
-  const int C8 = p.C >> 3;
-  const int cg = threadIdx.x % C8, lp = threadIdx.x / C8, ppi = kGlueThreads / C8;
-  const int c0 = cg * 8, HW = p.H * p.W;
-  const float n = float(HW);
-  // per-channel constants:  zpre = y*scale + shift;  xhat = y*rstd - mr;
-  // apply:  dy = scale*dz + ca*y + cb   with ca = -scale*m2*rstd, cb = scale*(m2*mr - m1)
-  float scale[8], shift[8], k0[8], k1[8], a1[8], a2[8];
-  {
-    float mean[8], rstd[8];
-    in_coeffs(p.stats, p.gamma, p.beta, ba, p.C, c0, n, p.eps, mean, rstd, scale, shift);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (kApply) {
-        const float m1 = p.sums[(int64_t(b) * p.C + c0 + e) * 2] / n;
-        const float m2 = p.sums[(int64_t(b) * p.C + c0 + e) * 2 + 1] / n;
-        k0[e] = -scale[e] * m2 * rstd[e];
-        k1[e] = scale[e] * (m2 * mean[e] * rstd[e] - m1);
-      } else {
-        k0[e] = rstd[e];
-        k1[e] = mean[e] * rstd[e];
-      }
-      a1[e] = a2[e] = 0.f;
-    }
-  }
-  if (!kApply) {
-    for (int t = threadIdx.x; t < 2 * p.C; t += kGlueThreads) sred[t] = 0.f;
-    __syncthreads();
-  }
-  const int pix0 = blockIdx.x * ppb, pix1 = min(HW, pix0 + ppb);
-  constexpr int U = 2;
-  const sg_bf16* ybase = p.Y + int64_t(ba) * HW * p.C + c0;
-  for (int pix = pix0 + lp; pix < pix1; pix += U * ppi) {
-    uint4 raw[U];
-    float d[U][8];
-    int pi[U], pj[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int q = pix + u * ppi;
-      pi[u] = q / p.W;
-      pj[u] = q - pi[u] * p.W;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) d[u][e] = 0.f;
-      if (q < pix1) {
-        raw[u] = __ldg(reinterpret_cast<const uint4*>(ybase + int64_t(q) * p.C));
-        grad_read8(p.g1, b, pi[u], pj[u], p.H, p.W, p.C, c0, d[u]);
-        grad_read8(p.g2, b, pi[u], pj[u], p.H, p.W, p.C, c0, d[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (pix + u * ppi >= pix1) break;
-      float y[8];
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 t = __bfloat1622float2(h[k]);
-        y[2 * k] = t.x;
-        y[2 * k + 1] = t.y;
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float dz = d[u][e] * act_grad(fmaf(y[e], scale[e], shift[e]), p.act, p.act_alpha);
-        if (kApply) {
-          d[u][e] = fmaf(scale[e], dz, fmaf(k0[e], y[e], k1[e]));
-        } else {
-          a1[e] += dz;
-          a2[e] += dz * fmaf(y[e], k0[e], -k1[e]);
-        }
-      }
-      if (kApply) write_frame8(p.dst, p.dmap, b, pi[u], pj[u], c0, d[u]);
-    }
-  }
-  if (!kApply) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sred[(c0 + e) * 2], a1[e]);
-      atomicAdd(&sred[(c0 + e) * 2 + 1], a2[e]);
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < 2 * p.C; t += kGlueThreads) atomicAdd(p.sums + int64_t(b) * p.C * 2 + t, sred[t]);
-  }
-}
-void launch_in_bwd_reduce(const InBwdParams& p, cudaStream_t st) {
-  const int HW = p.H * p.W, ppb = pix_per_block_for(HW, p.B);
-  dim3 grid((HW + ppb - 1) / ppb, p.B);
-  in_bwd_kernel<false><<<grid, kGlueThreads, 2 * p.C * sizeof(float), st>>>(p, ppb);
-}
-void launch_in_bwd_apply(const InBwdParams& p, cudaStream_t st) {
-  const int HW = p.H * p.W, ppb = pix_per_block_for(HW, p.B);
-  dim3 grid((HW + ppb - 1) / ppb, p.B);
-  in_bwd_kernel<true><<<grid, kGlueThreads, 0, st>>>(p, ppb);
-}
-
+// (instance-norm forward / backward and the residual-gradient gather live in glue_rows.cu)
 __global__ void in_param_grad_kernel(const float* __restrict__ sums, int nb, int C, float* dgamma, float* dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -390,28 +257,6 @@ void launch_in_param_grad(const float* sums, int nb, int C, float* dgamma, float
 }
 
 // ------------------------------------------------------------------------------------------ gather
-__global__ void __launch_bounds__(kGlueThreads) grad_gather_kernel(const GradSrc g1, const GradSrc g2, int H, int W,
-                                                                    int C, sg_bf16* out, int ppb) {
-  const int b = blockIdx.y;
-  const int C8 = C >> 3;
-  const int cg = threadIdx.x % C8, lp = threadIdx.x / C8, ppi = kGlueThreads / C8;
-  const int HW = H * W;
-  const int pix0 = blockIdx.x * ppb, pix1 = min(HW, pix0 + ppb);
-  for (int pix = pix0 + lp; pix < pix1; pix += ppi) {
-    const int i = pix / W, j = pix - i * W;
-    float d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    grad_read8(g1, b, i, j, H, W, C, cg * 8, d);
-    grad_read8(g2, b, i, j, H, W, C, cg * 8, d);
-    st_bf16x8(out + (int64_t(b) * HW + pix) * C + cg * 8, d);
-  }
-}
-void launch_grad_gather(const GradSrc& g1, const GradSrc& g2, int B, int H, int W, int C, sg_bf16* out,
-                        cudaStream_t st) {
-  const int HW = H * W, ppb = pix_per_block_for(HW, B);
-  dim3 grid((HW + ppb - 1) / ppb, B);
-  grad_gather_kernel<<<grid, kGlueThreads, 0, st>>>(g1, g2, H, W, C, out, ppb);
-}
-
 __global__ void __launch_bounds__(kGlueThreads) act_bwd_kernel(const ActBwdParams p, int ppb) {
   extern __shared__ float sred[];
   const int b = blockIdx.y;

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../sg-gan-tf2_b200/csrc/conv_gemm_tc.h"
@@ -72,6 +73,9 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
   CK(cudaMalloc(&dOut, out_elems * (c.out_f32 ? 4 : 2)));
   CK(cudaMalloc(&dBias, c.Cout * 4));
   CK(cudaMalloc(&dStats, size_t(c.B) * c.Cout * 2 * 4));
+  const int Tmax = (c.H * (c.W + c.k - 1) + 127) / 128 + 1;
+  float* dPart;
+  CK(cudaMalloc(&dPart, size_t(c.B) * Tmax * c.Cout * 2 * 4));
   CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dW, hW.data(), hW.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dBias, hbias.data(), c.Cout * 4, cudaMemcpyHostToDevice));
@@ -107,7 +111,7 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
   p.omap.P = c.W;
   p.o_scale = 1;
   p.bias = dBias;
-  p.stats = c.use_stats ? dStats : nullptr;
+  p.stats = c.use_stats ? dPart : nullptr;
   p.act = c.act;
   p.act_alpha = 0.3f;
   p.MT = c.MT;
@@ -118,6 +122,8 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
     printf("prepare_conv_gemm failed %d\n", r);
     return 1;
   }
+  L.p.stats_T = L.grid_x * (L.p.MT / 128);
+  L.p.stats_t0 = 0;
   printf("grid %d x %d x %d, MT %d, runs %d, stages A %d B %d, smem %zu, tmem cols %u\n", L.grid_x, L.grid_y, L.grid_z,
          L.p.MT, L.p.nruns, L.sa_stages, L.sb_stages, L.smem, L.tmem_cols);
   r = run_conv_gemm(L, 0);
@@ -127,9 +133,17 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
     return 1;
   }
   std::vector<uint8_t> hOut(out_elems * (c.out_f32 ? 4 : 2));
-  std::vector<float> hStats(size_t(c.B) * c.Cout * 2);
+  std::vector<float> hStats(size_t(c.B) * c.Cout * 2, 0.f);
   CK(cudaMemcpy(hOut.data(), dOut, hOut.size(), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(hStats.data(), dStats, hStats.size() * 4, cudaMemcpyDeviceToHost));
+  auto read_stats = [&](std::vector<float>& dst) {
+    std::vector<float> part(size_t(c.B) * L.p.stats_T * c.Cout * 2);
+    CK(cudaMemcpy(part.data(), dPart, part.size() * 4, cudaMemcpyDeviceToHost));
+    std::fill(dst.begin(), dst.end(), 0.f);
+    for (int b = 0; b < c.B; ++b)
+      for (int t = 0; t < L.p.stats_T; ++t)
+        for (int q = 0; q < c.Cout * 2; ++q) dst[size_t(b) * c.Cout * 2 + q] += part[(size_t(b) * L.p.stats_T + t) * c.Cout * 2 + q];
+  };
+  if (c.use_stats) read_stats(hStats);
 
   // CPU check (all positions if full_check, else a pseudo-random sample of 4096)
   double max_err = 0, max_ref = 0;
@@ -178,6 +192,21 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
     }
     printf("stats check: max rel err %.4g\n", se);
     if (se > 5e-3) ++bad;
+  }
+  {  // determinism: a second launch must reproduce the output bit for bit (statistics up to atomic order)
+    CK(cudaMemset(dStats, 0, size_t(c.B) * c.Cout * 2 * 4));
+    run_conv_gemm(L, 0);
+    CK(cudaDeviceSynchronize());
+    std::vector<uint8_t> hOut2(hOut.size());
+    std::vector<float> hStats2(hStats.size());
+    CK(cudaMemcpy(hOut2.data(), dOut, hOut2.size(), cudaMemcpyDeviceToHost));
+    if (c.use_stats) read_stats(hStats2);
+    size_t ndiff = 0;
+    for (size_t q = 0; q < hOut.size(); ++q) ndiff += hOut[q] != hOut2[q];
+    double sd = 0;
+    for (size_t q = 0; q < hStats.size(); ++q) sd = fmax(sd, fabs(hStats[q] - hStats2[q]) / (fabs(hStats[q]) + 1.0));
+    printf("DETERMINISM: %zu output bytes differ between two launches; stats max rel diff %.3g\n", ndiff, sd);
+    if (ndiff || sd != 0.0) ++bad;
   }
   if (iters > 0) {
     {  // per-phase clock64 stamps of one launch
