@@ -155,7 +155,9 @@ def main():
     real_d, seg_d, mask_d = (torch.as_tensor(x).cuda() for x in (real_h, seg_h, mask_h))
 
     ns = argparse.Namespace(batch_size=B, image_width=W, image_height=H, segment_class=C, use_resnet=True)
-    model = M.sggan(ns)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):  # the builders print their names like the reference (module.py:220,273)
+        model = M.sggan(ns)
     model.real_A, model.seg_A, model.mask_A = real_d, seg_d, mask_d
 
     def sync_all():
