@@ -1,22 +1,56 @@
-// glue_rows.cu -- the per-layer elementwise passes of the step, organised by image ROWS:
+// glue_rows.cu -- the per-layer elementwise passes of the step as TMA-staged row streams:
 //
 //   in_apply      instance norm + activation (+ residual) of a raw conv output -> next frame
 //   in_bwd        its backward (reduce pass and apply pass)
 //   grad_gather   residual-stream gradient accumulation
 //
-// A block owns a few whole image rows; a thread owns 8 channels (one 128-bit access) and walks the
-// row's columns with a fixed stride.  Row / column bookkeeping (reflected border rows, phase planes,
-// folded gradient rows) is resolved once per row into base pointers, so the per-pixel work is a handful
-// of address adds around the 128-bit loads and stores -- these passes were instruction-bound, not
-// HBM-bound, when every pixel recomputed its (i, j) with integer divisions and 64-bit frame arithmetic.
-// All primary loads of a batch of U pixels are issued before any of them is used.
+// These passes move 70-110 MB each and were latency-bound (1.2-2.2 TB/s) as plain load/compute/store loops:
+// with ~100 live registers per thread only 16 warps fit an SM and every warp idles for the HBM round trip
+// between its batches.  Here one persistent block per SM streams its share of an image as 16 KB row chunks:
+// a producer warp runs four chunks ahead with 1-D bulk copies (cp.async.bulk -> shared, mbarrier
+// complete_tx), so ~190 KB per SM are in flight independent of register pressure, and 16 consumer warps
+// compute out of shared memory (conflict-free 128-bit accesses, 8 channels per thread) and store 128-bit
+// results straight into the destination frame.  Row bookkeeping (reflected border rows/columns, 2x2 phase
+// planes, folded gradient borders) is resolved once per chunk into base pointers.
 #include <cuda_bf16.h>
 
 #include "glue.h"
+#include "tc_common.cuh"
 
 namespace sggan {
 
-constexpr int kRowThreads = 256;
+constexpr int kConsumers = 512;                 // 16 consumer warps
+constexpr int kStreamThreads = kConsumers + 32;  // + 1 producer warp
+constexpr int kStages = 4;
+constexpr int kChunkBytes = 16384;  // per stream and stage
+constexpr int kMaxStreams = 3;
+
+enum { RS_APPLY = 0, RS_BWD_REDUCE = 1, RS_BWD_APPLY = 2, RS_GATHER = 3 };
+
+struct StreamDesc {
+  const sg_bf16* base;  // null = absent (reads as zeros)
+  int64_t img_stride;   // elements between images
+  int64_t row_stride;   // elements between rows
+  int oy, ox;           // logical (0,0) sits at row oy, column ox
+  int act_index;        // 1: indexed by the activation image (virtual-batch wrap), 0: by the gradient image
+};
+
+struct RowStreamParams {
+  int B, H, W, C, CW;  // CW = pixels per chunk
+  int nb_act, act_wrap;
+  StreamDesc s[kMaxStreams];
+  // statistics / affine
+  const float* stats;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  int act;
+  float alpha;
+  float* sums;   // in_bwd: [B][C][2]
+  GradSrc g[2];  // fold information of the gradient streams (extras are read directly from global)
+  sg_bf16* dst;  // frame (apply modes) or plain [B][H][W][C] (gather)
+  FrameMap dmap;
+};
 
 __device__ __forceinline__ float rw_act_fwd(float v, int act, float a) {
   if (act == SG_ACT_RELU) return fmaxf(v, 0.f);
@@ -89,9 +123,9 @@ __device__ __forceinline__ void dst_store8(const DstRow& r, const FrameMap& m, i
   }
 }
 
-// ---- source row of a gradient buffer (bf16; fp32 sources never reach these kernels) -------------------------
+// ---- folded-border extras of a gradient source (everything except the primary read) ---------------------------
 struct SrcRow {
-  const sg_bf16* base[3];  // row i (+ folded border rows), at logical column 0
+  const sg_bf16* base[3];
   int n;
 };
 __device__ __forceinline__ void src_row_init(SrcRow& r, const GradSrc& g, int b, int i, int H, int C, int c0) {
@@ -106,7 +140,9 @@ __device__ __forceinline__ void src_row_init(SrcRow& r, const GradSrc& g, int b,
   r.base[0] = img + (int64_t(i + g.oy) * g.Ws + g.ox) * C;
   for (int k = 0; k < nm; ++k) r.base[1 + k] = img + (int64_t(mr[k] + g.oy) * g.Ws + g.ox) * C;
 }
-// everything except the primary (row 0, column j) read
+__device__ __forceinline__ bool src_has_extra(const SrcRow& r, const GradSrc& g, int j, int W) {
+  return r.n > 1 || (g.fold > 0 && r.n > 0 && (j <= g.fold || j >= W - 1 - g.fold));
+}
 __device__ __forceinline__ void src_extra8(const SrcRow& r, const GradSrc& g, int j, int W, int C, float* acc) {
   int mc[2];
   const int nc = (g.fold > 0 && (j <= g.fold || j >= W - 1 - g.fold)) ? mirrors(j, W, g.fold, mc) : 0;
@@ -119,236 +155,253 @@ __device__ __forceinline__ void src_extra8(const SrcRow& r, const GradSrc& g, in
       for (int e = 0; e < 8; ++e) acc[e] += t[e];
     }
 }
-__device__ __forceinline__ bool src_has_extra(const SrcRow& r, const GradSrc& g, int j, int W) {
-  return r.n > 1 || (g.fold > 0 && r.n > 0 && (j <= g.fold || j >= W - 1 - g.fold));
-}
-
-static inline int rows_per_block(int H, int B) {
-  // ~5 blocks per SM over the grid
-  int rpb = (H * B + 148 * 5 - 1) / (148 * 5);
-  return rpb < 1 ? 1 : rpb;
-}
 
 // =======================================================================================================
-// forward: z = act((y - mean) * gamma * rstd + beta) (+ residual)  ->  next frame
-__global__ void __launch_bounds__(kRowThreads) in_apply_rows_kernel(const InApplyParams p, const int rpb) {
+template <int MODE>
+__global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const RowStreamParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+  __shared__ float sred[1024];  // MODE == RS_BWD_REDUCE: 2 * C partial sums (C <= 512)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
-  const int C8 = p.C >> 3;
-  const int cg = threadIdx.x % C8, lj = threadIdx.x / C8, ppi = kRowThreads / C8;
-  const int c0 = cg * 8;
-  const float n = float(p.H * p.W);
-  float mean[8], scale[8], beta[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = c0 + e;
-    float mu = 0.f, rs = 1.f;
-    if (p.stats != nullptr) {
-      const float2 s = reinterpret_cast<const float2*>(p.stats)[int64_t(b) * p.C + c];
-      mu = s.x / n;
-      rs = rsqrtf(fmaxf(s.y / n - mu * mu, 0.f) + p.eps);
+  const int ba = b < p.nb_act ? b : b - p.act_wrap;
+  const int cpr = (p.W + p.CW - 1) / p.CW;  // chunks per row
+  const int nchunks = p.H * cpr;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumers / 32);
     }
-    mean[e] = mu;
-    scale[e] = (p.gamma ? p.gamma[c] : 1.f) * rs;
-    beta[e] = p.beta ? p.beta[c] : 0.f;  // z = (y - mean)*scale + beta: exactly beta when H*W == 1
+    fence_barrier_init();
   }
-  const int r0 = blockIdx.x * rpb, r1 = min(p.H, r0 + rpb);
-  constexpr int U = 4;
-  for (int i = r0; i < r1; ++i) {
-    const sg_bf16* yrow = p.Y + (int64_t(b) * p.H + i) * p.W * p.C + c0;
-    const sg_bf16* rrow =
-        p.res ? p.res + (int64_t(b) * p.rmap.frame_pix + int64_t(i + p.rmap.pt) * p.rmap.P + p.rmap.pl) * p.rmap.C + c0
-              : nullptr;  // residual frames are single-plane (generator blocks)
-    DstRow dr;
-    dst_row_init(dr, p.dst, p.dmap, b, i, c0);
-    for (int j0 = lj; j0 < p.W; j0 += U * ppi) {
-      uint4 raw[U], rr[U];
+  if (MODE == RS_BWD_REDUCE)
+    for (int t = threadIdx.x; t < 2 * p.C; t += kStreamThreads) sred[t] = 0.f;
+  __syncthreads();
+
+  if (warp == kConsumers / 32) {
+    // ------------------------------------------------------------ producer: bulk copies, kStages chunks ahead
+    if (lane == 0) {
+      int k = 0;
+      for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++k) {
+        const int s = k % kStages;
+        mbar_wait(&empty_bar[s], ((k / kStages) & 1) ^ 1, 41);
+        const int i = c / cpr, j0 = (c - i * cpr) * p.CW;
+        const int cw = min(p.CW, p.W - j0);
+        const uint32_t bytes = uint32_t(cw) * p.C * 2;
+        uint32_t total = 0;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u * ppi;
-        if (j < p.W) {
-          raw[u] = __ldg(reinterpret_cast<const uint4*>(yrow + int64_t(j) * p.C));
-          if (rrow) rr[u] = __ldg(reinterpret_cast<const uint4*>(rrow + int64_t(j) * p.rmap.C));
+        for (int q = 0; q < kMaxStreams; ++q) total += p.s[q].base ? bytes : 0;
+        mbar_arrive_expect_tx(&full_bar[s], total);
+#pragma unroll
+        for (int q = 0; q < kMaxStreams; ++q) {
+          const StreamDesc& d = p.s[q];
+          if (d.base == nullptr) continue;
+          const sg_bf16* src = d.base + int64_t(d.act_index ? ba : b) * d.img_stride + int64_t(i + d.oy) * d.row_stride +
+                               int64_t(j0 + d.ox) * p.C;
+          bulk_load_1d(smem + (s * kMaxStreams + q) * kChunkBytes, src, bytes, &full_bar[s]);
         }
       }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------- consumers
+  const int C8 = p.C >> 3;
+  const int cg = threadIdx.x % C8;  // constant per thread: kConsumers is a multiple of C8
+  const int c0 = cg * 8;
+  const int px0 = threadIdx.x / C8, pstep = kConsumers / C8;
+  const float n = float(p.H * p.W);
+  float mean[8], rstd[8], scale[8], beta[8], a1[8], a2[8];
+  if (MODE != RS_GATHER) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u * ppi;
-        if (j >= p.W) break;
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      float mu = 0.f, rs = 1.f;
+      if (p.stats != nullptr) {
+        const float2 s = reinterpret_cast<const float2*>(p.stats)[int64_t(ba) * p.C + c];
+        mu = s.x / n;
+        rs = rsqrtf(fmaxf(s.y / n - mu * mu, 0.f) + p.eps);
+      }
+      mean[e] = mu;
+      rstd[e] = rs;
+      scale[e] = (p.gamma ? p.gamma[c] : 1.f) * rs;
+      beta[e] = p.beta ? p.beta[c] : 0.f;  // z = (y - mean)*scale + beta: exactly beta when H*W == 1
+      a1[e] = a2[e] = 0.f;
+      if (MODE == RS_BWD_APPLY) {
+        const float2 q = reinterpret_cast<const float2*>(p.sums)[int64_t(b) * p.C + c];
+        a1[e] = q.x / n;  // mean of dzh
+        a2[e] = q.y / n;  // mean of dzh * xhat
+      }
+    }
+  }
+  int k = 0;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++k) {
+    const int s = k % kStages;
+    const int i = c / cpr, j0 = (c - i * cpr) * p.CW;
+    const int cw = min(p.CW, p.W - j0);
+    DstRow dr;
+    SrcRow e1, e2;
+    if (MODE == RS_APPLY || MODE == RS_BWD_APPLY) dst_row_init(dr, p.dst, p.dmap, b, i, c0);
+    if (MODE == RS_BWD_REDUCE || MODE == RS_BWD_APPLY) {
+      src_row_init(e1, p.g[0], b, i, p.H, p.C, c0);
+      src_row_init(e2, p.g[1], b, i, p.H, p.C, c0);
+    }
+    if (MODE == RS_GATHER) {
+      src_row_init(e1, p.g[0], b, i, p.H, p.C, c0);
+      src_row_init(e2, p.g[1], b, i, p.H, p.C, c0);
+    }
+    mbar_wait(&full_bar[s], (k / kStages) & 1, 42);
+    const uint4* s0 = reinterpret_cast<const uint4*>(smem + (s * kMaxStreams + 0) * kChunkBytes);
+    const uint4* s1 = reinterpret_cast<const uint4*>(smem + (s * kMaxStreams + 1) * kChunkBytes);
+    const uint4* s2 = reinterpret_cast<const uint4*>(smem + (s * kMaxStreams + 2) * kChunkBytes);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int px = px0; px < cw; px += pstep) {
+      const int v = px * C8 + cg;
+      const int j = j0 + px;
+      if (MODE == RS_APPLY) {
         float y[8];
-        unpack8(raw[u], y);
+        unpack8(s0[v], y);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = rw_act_fwd(fmaf(y[e] - mean[e], scale[e], beta[e]), p.act, p.act_alpha);
-        if (rrow) {
+        for (int e = 0; e < 8; ++e) y[e] = rw_act_fwd(fmaf(y[e] - mean[e], scale[e], beta[e]), p.act, p.alpha);
+        if (p.s[1].base) {
           float r[8];
-          unpack8(rr[u], r);
+          unpack8(s1[v], r);
 #pragma unroll
           for (int e = 0; e < 8; ++e) y[e] += r[e];
         }
         dst_store8(dr, p.dmap, j, pack8(y));
-      }
-    }
-  }
-}
-void launch_in_apply(const InApplyParams& p, cudaStream_t st) {
-  const int rpb = rows_per_block(p.H, p.B);
-  dim3 grid((p.H + rpb - 1) / rpb, p.B);
-  in_apply_rows_kernel<<<grid, kRowThreads, 0, st>>>(p, rpb);
-}
-
-// =======================================================================================================
-// backward.  reduce: sums[b][c] += (sum dzh, sum dzh * xhat);  apply: dy = scale*((dzh - m1) - xhat*m2) -> dY frame
-template <bool kApply>
-__global__ void __launch_bounds__(kRowThreads, 2) in_bwd_rows_kernel(const InBwdParams p, const int rpb) {
-  extern __shared__ float sred[];
-  const int b = blockIdx.y;
-  const int ba = b < p.nb_act ? b : b - p.act_wrap;
-  const int C8 = p.C >> 3;
-  const int cg = threadIdx.x % C8, lj = threadIdx.x / C8, ppi = kRowThreads / C8;
-  const int c0 = cg * 8;
-  const float n = float(p.H * p.W);
-  // zpre = (y - mean)*scale + beta;  xhat = (y - mean)*rstd.  The apply form keeps a single-pixel norm
-  // (xhat == 0, dzh == m1) back-propagating exactly zero, as the reference does at 128x128 (Appendix B).
-  float mean[8], rstd[8], scale[8], beta[8], a1[8], a2[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = c0 + e;
-    const float2 s = reinterpret_cast<const float2*>(p.stats)[int64_t(ba) * p.C + c];
-    const float mu = s.x / n;
-    mean[e] = mu;
-    rstd[e] = rsqrtf(fmaxf(s.y / n - mu * mu, 0.f) + p.eps);
-    scale[e] = p.gamma[c] * rstd[e];
-    beta[e] = p.beta[c];
-    if (kApply) {
-      const float2 q = reinterpret_cast<const float2*>(p.sums)[int64_t(b) * p.C + c];
-      a1[e] = q.x / n;
-      a2[e] = q.y / n;
-    } else {
-      a1[e] = a2[e] = 0.f;
-    }
-  }
-  if (!kApply) {
-    for (int t = threadIdx.x; t < 2 * p.C; t += kRowThreads) sred[t] = 0.f;
-    __syncthreads();
-  }
-  const int r0 = blockIdx.x * rpb, r1 = min(p.H, r0 + rpb);
-  constexpr int U = 2;
-  for (int i = r0; i < r1; ++i) {
-    const sg_bf16* yrow = p.Y + (int64_t(ba) * p.H + i) * p.W * p.C + c0;
-    SrcRow s1, s2;
-    src_row_init(s1, p.g1, b, i, p.H, p.C, c0);
-    src_row_init(s2, p.g2, b, i, p.H, p.C, c0);
-    DstRow dr;
-    if (kApply) dst_row_init(dr, p.dst, p.dmap, b, i, c0);
-    for (int j0 = lj; j0 < p.W; j0 += U * ppi) {
-      uint4 raw[U], g1[U], g2[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u * ppi;
-        g1[u] = make_uint4(0, 0, 0, 0);
-        g2[u] = make_uint4(0, 0, 0, 0);
-        if (j < p.W) {
-          raw[u] = __ldg(reinterpret_cast<const uint4*>(yrow + int64_t(j) * p.C));
-          if (s1.n) g1[u] = __ldg(reinterpret_cast<const uint4*>(s1.base[0] + int64_t(j) * p.C));
-          if (s2.n) g2[u] = __ldg(reinterpret_cast<const uint4*>(s2.base[0] + int64_t(j) * p.C));
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u * ppi;
-        if (j >= p.W) break;
-        float y[8], d[8], t[8];
-        unpack8(raw[u], y);
-        unpack8(g1[u], d);
-        unpack8(g2[u], t);
+      } else if (MODE == RS_GATHER) {
+        float d[8], t[8];
+        unpack8(p.s[0].base ? s0[v] : zero, d);
+        unpack8(p.s[1].base ? s1[v] : zero, t);
 #pragma unroll
         for (int e = 0; e < 8; ++e) d[e] += t[e];
-        if (src_has_extra(s1, p.g1, j, p.W)) src_extra8(s1, p.g1, j, p.W, p.C, d);
-        if (src_has_extra(s2, p.g2, j, p.W)) src_extra8(s2, p.g2, j, p.W, p.C, d);
+        if (src_has_extra(e1, p.g[0], j, p.W)) src_extra8(e1, p.g[0], j, p.W, p.C, d);
+        if (src_has_extra(e2, p.g[1], j, p.W)) src_extra8(e2, p.g[1], j, p.W, p.C, d);
+        *reinterpret_cast<uint4*>(p.dst + ((int64_t(b) * p.H + i) * p.W + j) * p.C + c0) = pack8(d);
+      } else {
+        float y[8], d[8], t[8];
+        unpack8(s0[v], y);
+        unpack8(p.s[1].base ? s1[v] : zero, d);
+        unpack8(p.s[2].base ? s2[v] : zero, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] += t[e];
+        if (src_has_extra(e1, p.g[0], j, p.W)) src_extra8(e1, p.g[0], j, p.W, p.C, d);
+        if (src_has_extra(e2, p.g[1], j, p.W)) src_extra8(e2, p.g[1], j, p.W, p.C, d);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
+          // zpre = (y - mean)*scale + beta;  xhat = (y - mean)*rstd.  The apply form keeps a single-pixel norm
+          // (xhat == 0, dzh == m1) back-propagating exactly zero, as the reference does at 128x128 (Appendix B).
           const float yc = y[e] - mean[e];
-          const float dz = d[e] * rw_act_grad(fmaf(yc, scale[e], beta[e]), p.act, p.act_alpha);
+          const float dz = d[e] * rw_act_grad(fmaf(yc, scale[e], beta[e]), p.act, p.alpha);
           const float xh = yc * rstd[e];
-          if (kApply) {
+          if (MODE == RS_BWD_APPLY) {
             d[e] = scale[e] * ((dz - a1[e]) - xh * a2[e]);
           } else {
             a1[e] += dz;
             a2[e] += dz * xh;
           }
         }
-        if (kApply) dst_store8(dr, p.dmap, j, pack8(d));
+        if (MODE == RS_BWD_APPLY) dst_store8(dr, p.dmap, j, pack8(d));
       }
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
-  if (!kApply) {
+  if (MODE == RS_BWD_REDUCE) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       atomicAdd(&sred[(c0 + e) * 2], a1[e]);
       atomicAdd(&sred[(c0 + e) * 2 + 1], a2[e]);
     }
-    __syncthreads();
-    for (int t = threadIdx.x; t < 2 * p.C; t += kRowThreads) atomicAdd(p.sums + int64_t(b) * p.C * 2 + t, sred[t]);
+    named_bar_sync(2, kConsumers);
+    for (int t = threadIdx.x; t < 2 * p.C; t += kConsumers) atomicAdd(p.sums + int64_t(b) * p.C * 2 + t, sred[t]);
   }
-}
-void launch_in_bwd_reduce(const InBwdParams& p, cudaStream_t st) {
-  const int rpb = rows_per_block(p.H, p.B);
-  dim3 grid((p.H + rpb - 1) / rpb, p.B);
-  in_bwd_rows_kernel<false><<<grid, kRowThreads, 2 * p.C * sizeof(float), st>>>(p, rpb);
-}
-void launch_in_bwd_apply(const InBwdParams& p, cudaStream_t st) {
-  const int rpb = rows_per_block(p.H, p.B);
-  dim3 grid((p.H + rpb - 1) / rpb, p.B);
-  in_bwd_rows_kernel<true><<<grid, kRowThreads, 0, st>>>(p, rpb);
 }
 
-// =======================================================================================================
-// out[b,i,j,:] = g1 + g2   (plain bf16 [B][H][W][C]); either source may fold a reflected border back
-__global__ void __launch_bounds__(kRowThreads) grad_gather_rows_kernel(const GradSrc g1, const GradSrc g2, int H, int W,
-                                                                      int C, sg_bf16* out, int rpb) {
-  const int b = blockIdx.y;
-  const int C8 = C >> 3;
-  const int cg = threadIdx.x % C8, lj = threadIdx.x / C8, ppi = kRowThreads / C8;
-  const int c0 = cg * 8;
-  const int r0 = blockIdx.x * rpb, r1 = min(H, r0 + rpb);
-  constexpr int U = 4;
-  for (int i = r0; i < r1; ++i) {
-    SrcRow s1, s2;
-    src_row_init(s1, g1, b, i, H, C, c0);
-    src_row_init(s2, g2, b, i, H, C, c0);
-    sg_bf16* orow = out + (int64_t(b) * H + i) * W * C + c0;
-    for (int j0 = lj; j0 < W; j0 += U * ppi) {
-      uint4 a[U], c[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u * ppi;
-        a[u] = make_uint4(0, 0, 0, 0);
-        c[u] = make_uint4(0, 0, 0, 0);
-        if (j < W) {
-          if (s1.n) a[u] = __ldg(reinterpret_cast<const uint4*>(s1.base[0] + int64_t(j) * C));
-          if (s2.n) c[u] = __ldg(reinterpret_cast<const uint4*>(s2.base[0] + int64_t(j) * C));
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = j0 + u * ppi;
-        if (j >= W) break;
-        float d[8], t[8];
-        unpack8(a[u], d);
-        unpack8(c[u], t);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d[e] += t[e];
-        if (src_has_extra(s1, g1, j, W)) src_extra8(s1, g1, j, W, C, d);
-        if (src_has_extra(s2, g2, j, W)) src_extra8(s2, g2, j, W, C, d);
-        *reinterpret_cast<uint4*>(orow + int64_t(j) * C) = pack8(d);
-      }
-    }
+template <int MODE>
+static void launch_row_stream(RowStreamParams& p, cudaStream_t st) {
+  p.CW = kChunkBytes / (p.C * 2);
+  if (p.CW > p.W) p.CW = p.W;
+  static bool attr_set = false;
+  const size_t smem = size_t(kStages) * kMaxStreams * kChunkBytes + 128;
+  if (!attr_set) {
+    cudaFuncSetAttribute(row_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    attr_set = true;
   }
+  // one persistent block per SM; blocks never span images (per-image statistics)
+  int gx = 148 / p.B;
+  if (gx < 1) gx = 1;
+  const int nchunks = p.H * ((p.W + p.CW - 1) / p.CW);
+  if (gx > nchunks) gx = nchunks;
+  dim3 grid(gx, p.B);
+  row_stream_kernel<MODE><<<grid, kStreamThreads, smem, st>>>(p);
 }
-void launch_grad_gather(const GradSrc& g1, const GradSrc& g2, int B, int H, int W, int C, sg_bf16* out,
-                        cudaStream_t st) {
-  const int rpb = rows_per_block(H, B);
-  dim3 grid((H + rpb - 1) / rpb, B);
-  grad_gather_rows_kernel<<<grid, kRowThreads, 0, st>>>(g1, g2, H, W, C, out, rpb);
+
+static StreamDesc plain_stream(const sg_bf16* base, int H, int W, int C, int act_index) {
+  StreamDesc d;
+  d.base = base; d.img_stride = int64_t(H) * W * C; d.row_stride = int64_t(W) * C; d.oy = 0; d.ox = 0; d.act_index = act_index;
+  return d;
+}
+static StreamDesc grad_stream(const GradSrc& g, int C) {
+  StreamDesc d;
+  d.base = reinterpret_cast<const sg_bf16*>(g.ptr);
+  d.img_stride = int64_t(g.Hs) * g.Ws * C; d.row_stride = int64_t(g.Ws) * C; d.oy = g.oy; d.ox = g.ox; d.act_index = 0;
+  return d;
+}
+static StreamDesc null_stream() {
+  StreamDesc d;
+  d.base = nullptr; d.img_stride = d.row_stride = 0; d.oy = d.ox = d.act_index = 0;
+  return d;
+}
+
+void launch_in_apply(const InApplyParams& a, cudaStream_t st) {
+  RowStreamParams p = {};
+  p.B = a.B; p.H = a.H; p.W = a.W; p.C = a.C; p.nb_act = a.B; p.act_wrap = 0;
+  p.s[0] = plain_stream(a.Y, a.H, a.W, a.C, 0);
+  p.s[1] = null_stream();
+  if (a.res != nullptr) {  // residual frames are single-plane (generator blocks)
+    p.s[1].base = a.res; p.s[1].img_stride = a.rmap.frame_pix * a.rmap.C; p.s[1].row_stride = int64_t(a.rmap.P) * a.rmap.C;
+    p.s[1].oy = a.rmap.pt; p.s[1].ox = a.rmap.pl;
+  }
+  p.s[2] = null_stream();
+  p.stats = a.stats; p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.act = a.act; p.alpha = a.act_alpha;
+  p.dst = a.dst; p.dmap = a.dmap;
+  launch_row_stream<RS_APPLY>(p, st);
+}
+
+static void bwd_params(const InBwdParams& a, RowStreamParams& p) {
+  p.B = a.B; p.H = a.H; p.W = a.W; p.C = a.C; p.nb_act = a.nb_act; p.act_wrap = a.act_wrap;
+  p.s[0] = plain_stream(a.Y, a.H, a.W, a.C, 1);
+  p.s[1] = a.g1.ptr ? grad_stream(a.g1, a.C) : null_stream();
+  p.s[2] = a.g2.ptr ? grad_stream(a.g2, a.C) : null_stream();
+  p.g[0] = a.g1; p.g[1] = a.g2;
+  p.stats = a.stats; p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.act = a.act; p.alpha = a.act_alpha;
+  p.sums = a.sums; p.dst = a.dst; p.dmap = a.dmap;
+}
+void launch_in_bwd_reduce(const InBwdParams& a, cudaStream_t st) {
+  RowStreamParams p = {};
+  bwd_params(a, p);
+  launch_row_stream<RS_BWD_REDUCE>(p, st);
+}
+void launch_in_bwd_apply(const InBwdParams& a, cudaStream_t st) {
+  RowStreamParams p = {};
+  bwd_params(a, p);
+  launch_row_stream<RS_BWD_APPLY>(p, st);
+}
+
+void launch_grad_gather(const GradSrc& g1, const GradSrc& g2, int B, int H, int W, int C, sg_bf16* out, cudaStream_t st) {
+  RowStreamParams p = {};
+  p.B = B; p.H = H; p.W = W; p.C = C; p.nb_act = B; p.act_wrap = 0;
+  p.s[0] = g1.ptr ? grad_stream(g1, C) : null_stream();
+  p.s[1] = g2.ptr ? grad_stream(g2, C) : null_stream();
+  p.s[2] = null_stream();
+  p.g[0] = g1; p.g[1] = g2;
+  p.dst = out;
+  launch_row_stream<RS_GATHER>(p, st);
 }
 
 }  // namespace sggan

@@ -16,7 +16,7 @@ namespace sggan {
 
 // Written by a kernel whose mbarrier wait exceeded the watchdog (debug aid: a wrong
 // descriptor or byte count otherwise hangs the GPU box until the job limit).
-__device__ int g_tc_watchdog_flag = 0;
+static __device__ int g_tc_watchdog_flag = 0;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -80,6 +80,14 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+
+// 1-D bulk copy global -> shared (no tensor map): `bytes` multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 // ---------------------------------------------------------------- TMEM
