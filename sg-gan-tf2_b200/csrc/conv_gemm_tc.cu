@@ -79,7 +79,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int a_stage_bytes = (MT + kHaloRows) * 128, b_stage_bytes = BN * 128;
   uint8_t* smA = smem;
   uint8_t* smB = smem + sa_stages * a_stage_bytes;
-  const int m0 = blockIdx.x * MT, n0 = blockIdx.y * BN, b = blockIdx.z;
+  const int mstep = p.shift_kw > 0 ? MT - (p.shift_kw - 1) : MT;
+  const int m0 = blockIdx.x * mstep, n0 = blockIdx.y * BN, b = blockIdx.z;
   const int cchunks = p.Cin / kChunkK;
   const int agroups = p.nruns * cchunks;  // A tiles this CTA consumes
 
@@ -178,6 +179,33 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool has_stats = p.stats != nullptr;
     const int act = p.act;
     const float alpha = p.act_alpha;
+    if (p.shift_kw > 0) {
+      // ---- shift-sum epilogue: stage the (kw, co) partial products of all MT rows, then add across rows
+      float* S = reinterpret_cast<float*>(smem);  // [MT][33]
+      if (half < NA) {
+        float v[32];
+        tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(half * BN), v);
+        float* srow = S + (half * kTileM + row) * 33;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) srow[e] = v[e];
+      }
+      named_bar_sync(1, 256);
+      const int r = et;
+      if (r < mstep) {
+        const int m = m0 + r;
+        const int i = m / p.P, j = m - i * p.P;
+        if (m < p.M && i < p.Hv && j < p.Wv) {
+          const int64_t ob = (int64_t(b) * p.omap.frame_pix + frame_pixel(p.omap, i, j)) * p.omap.C;
+          for (int co = 0; co < p.Cout; ++co) {
+            float x = sbias[co];
+            for (int kw = 0; kw < p.shift_kw; ++kw) x += S[(r + kw) * 33 + kw * 4 + co];
+            x = apply_act(x, act, alpha);
+            if (p.out_f32) reinterpret_cast<float*>(p.out)[ob + co] = x;
+            else reinterpret_cast<__nv_bfloat16*>(p.out)[ob + co] = __float2bfloat16_rn(x);
+          }
+        }
+      }
+    } else
     for (int a = 0; a < NA; ++a) {
       const int m = m0 + a * kTileM + row;
       const int i = m / p.P, j = m - i * p.P;
@@ -273,7 +301,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // =============================================================================================
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
-                     const WgradParams p, const int stages, const uint32_t tmem_cols) {
+                     const WgradParams p, const int stages, const uint32_t tmem_cols, const int NA) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full_bar[kMaxStages];
@@ -283,8 +311,11 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
-  const int stage_bytes = kABytes + BN * 128;
-  const int mtiles = p.x_pair ? 1 : p.Cx / kTileM;
+  // NA accumulators (128 x-channels each) share every dY tile: the kernel is L2-bandwidth bound, and two
+  // accumulators cut the bytes per FLOP by a quarter
+  const int a_bytes = NA * kABytes;
+  const int stage_bytes = a_bytes + BN * 128;
+  const int mtiles = p.x_pair ? 1 : p.Cx / (kTileM * NA);
   const int mt = blockIdx.x % mtiles, tap = blockIdx.x / mtiles;
   const int n0 = blockIdx.y * BN;
   const int nchunk = (p.Mpix + 63) / 64;  // 64-pixel K chunks per image
@@ -315,7 +346,7 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (lane == 0) {
       const int xoff = p.x_off[tap], yoff = p.y_off[tap];
       const int xoff2 = p.x_pair ? p.x_off2[tap] : xoff;
-      const int xc0 = p.x_pair ? 0 : mt * kTileM, xc1 = p.x_pair ? 0 : mt * kTileM + 64;
+      const int xc0 = p.x_pair ? 0 : mt * kTileM * NA;
       for (int ks = 0; ks < ksteps; ++ks) {
         const int s = ks % stages;
         const uint32_t ph = (ks / stages) & 1;
@@ -324,10 +355,14 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int b = c / nchunk, mc = (c - b * nchunk) * 64;
         uint8_t* sa = smem + s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-        tma_load_3d(&tmX, &full_bar[s], sa, xc0, mc + xoff, b);
-        tma_load_3d(&tmX, &full_bar[s], sa + 8192, xc1, mc + xoff2, b);
+        if (p.x_pair) {
+          tma_load_3d(&tmX, &full_bar[s], sa, 0, mc + xoff, b);
+          tma_load_3d(&tmX, &full_bar[s], sa + 8192, 0, mc + xoff2, b);
+        } else {
+          for (int h = 0; h < 2 * NA; ++h) tma_load_3d(&tmX, &full_bar[s], sa + h * 8192, xc0 + h * 64, mc + xoff, b);
+        }
         for (int h = 0; h < BN / 64; ++h)
-          tma_load_3d(&tmY, &full_bar[s], sa + kABytes + h * 8192, n0 + h * 64, mc + yoff, b);
+          tma_load_3d(&tmY, &full_bar[s], sa + a_bytes + h * 8192, n0 + h * 64, mc + yoff, b);
       }
     }
   } else if (warp == 1) {
@@ -339,12 +374,14 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         mbar_wait(&full_bar[s], ph, 12);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * stage_bytes);
-        const uint64_t adesc = desc_mnmajor_sw128(sa, 8192);
-        const uint64_t bdesc = desc_mnmajor_sw128(sa + kABytes, 8192);
+        const uint64_t bdesc = desc_mnmajor_sw128(sa + a_bytes, 8192);
+        for (int a = 0; a < NA; ++a) {
+          const uint64_t adesc = desc_mnmajor_sw128(sa + a * kABytes, 8192);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 16 pixels (= 16 rows of 128 B) per MMA
-          umma_bf16(tmem_acc, adesc + uint64_t(k * (2048 >> 4)), bdesc + uint64_t(k * (2048 >> 4)), idesc,
-                    (ks | k) != 0);
+          for (int k = 0; k < 4; ++k)  // 16 pixels (= 16 rows of 128 B) per MMA
+            umma_bf16(tmem_acc + uint32_t(a * BN), adesc + uint64_t(k * (2048 >> 4)), bdesc + uint64_t(k * (2048 >> 4)),
+                      idesc, (ks | k) != 0);
+        }
         umma_commit(&empty_bar[s]);
       }
       umma_commit(&acc_bar);
@@ -354,30 +391,43 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tc_fence_after();
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int xg = mt * kTileM + row;
-    float* dst = p.dW + int64_t(tap) * p.dw_tap_stride + int64_t(xg) * p.dw_sx;
-    // y channels contiguous in dW and 16-byte aligned rows: 128-bit vector reductions
+    float* obase = p.part ? p.part + int64_t(blockIdx.z) * p.part_stride : p.dW;
+    for (int a = 0; a < NA; ++a) {
+    const int xg = (mt * NA + a) * kTileM + row;
+    float* dst = obase + int64_t(tap) * p.dw_tap_stride + int64_t(xg) * p.dw_sx;
+    // y channels contiguous in dW and 16-byte aligned rows: 128-bit vector accesses
     const bool vec = (p.dw_sy == 1) && ((p.dw_sx & 3) == 0) && ((p.dw_tap_stride & 3) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(p.dW) & 15) == 0);
+                     ((p.part_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(obase) & 15) == 0);
+    const bool plain = p.part != nullptr;
     for (int c0 = 0; c0 < BN; c0 += 32) {
       float v[32];
-      tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c0), v);  // warp-collective: no divergence here
+      tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(a * BN + c0), v);  // warp-collective: no divergence here
       if (xg < p.nx_valid) {
         if (vec && n0 + c0 + 32 <= p.ny_valid) {
           float* d4 = dst + n0 + c0;
+          if (plain) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d4 + 4 * g), "f"(v[4 * g]),
-                         "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
-                         : "memory");
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(d4 + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d4 + 4 * g), "f"(v[4 * g]),
+                           "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
+                           : "memory");
+          }
         } else {
           const int64_t sy = p.dw_sy;
           float* d1 = dst + int64_t(n0 + c0) * sy;
 #pragma unroll
           for (int e = 0; e < 32; ++e)
-            if (n0 + c0 + e < p.ny_valid) atomicAdd(d1 + e * sy, v[e]);
+            if (n0 + c0 + e < p.ny_valid) {
+              if (plain) d1[e * sy] = v[e];
+              else atomicAdd(d1 + e * sy, v[e]);
+            }
         }
       }
+    }
     }
     tc_fence_before();
   }
@@ -390,11 +440,6 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 
 // =============================================================================================
 // Host side
-static int wgrad_stages_for(int bn) {
-  int st = kSmemBudget / (kABytes + bn * 128);
-  return st > kMaxStages ? kMaxStages : st;
-}
-
 // Sort the taps by pixel offset and group consecutive offsets into runs (at most kHaloRows taps each).
 static void build_runs(ConvGemmParams& p) {
   std::vector<std::pair<int, int>> t;
@@ -435,7 +480,12 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
   L->tmem_cols = tmem_cols_for((p.MT / 128) * p.BN);
   L->smem = size_t(sa) * a_stage + size_t(sb) * b_stage + 1024;
   if (L->smem < size_t(p.BN) * 129 * 4 + 1024) L->smem = size_t(p.BN) * 129 * 4 + 1024;  // epilogue statistics tile
-  L->grid_x = (p.M + p.MT - 1) / p.MT;
+  if (p.shift_kw > 0 && L->smem < size_t(p.MT) * 33 * 4 + 1024) L->smem = size_t(p.MT) * 33 * 4 + 1024;
+  {
+    const int mstep = p.shift_kw > 0 ? p.MT - (p.shift_kw - 1) : p.MT;
+    L->grid_x = (p.M + mstep - 1) / mstep;
+  }
+  if (p.shift_kw > 0 && (p.BN != 32 || p.shift_kw * 4 > 32 || p.Cout > 4 || p.stats != nullptr)) return -14;
   L->grid_y = p.CoutPad / p.BN;
   L->grid_z = p.B;
   const uint64_t rs = uint64_t(p.a_row_stride) * 2, fs = uint64_t(p.a_frame_pix) * p.a_row_stride * 2;
@@ -468,12 +518,21 @@ int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L) {
   if (!(p.BN == 64 || p.BN == 128 || p.BN == 256) || p.Cy % p.BN != 0) return -21;
   if (p.ntaps < 1 || p.ntaps > SGGAN_MAX_TAPS || p.ksplit < 1) return -22;
   L->p = p;
-  L->stages = wgrad_stages_for(p.BN);
-  L->tmem_cols = tmem_cols_for(p.BN);
-  L->smem = size_t(L->stages) * (kABytes + p.BN * 128) + 1024;
-  L->grid_x = (p.x_pair ? 1 : p.Cx / 128) * p.ntaps;
+  L->na = (!p.x_pair && p.Cx % 256 == 0) ? 2 : 1;
+  {
+    int st = kSmemBudget / (L->na * kABytes + p.BN * 128);
+    L->stages = st > kMaxStages ? kMaxStages : st;
+  }
+  L->tmem_cols = tmem_cols_for(L->na * p.BN);
+  L->smem = size_t(L->stages) * (L->na * kABytes + p.BN * 128) + 1024;
+  L->grid_x = (p.x_pair ? 1 : p.Cx / (128 * L->na)) * p.ntaps;
   L->grid_y = p.Cy / p.BN;
-  L->grid_z = p.ksplit;
+  {
+    const int total = p.B * ((p.Mpix + 63) / 64);
+    const int per = (total + p.ksplit - 1) / p.ksplit;
+    L->p.ksplit = (total + per - 1) / per;  // every slice has work (the reduce adds all of them)
+  }
+  L->grid_z = L->p.ksplit;
   int r = make_tmap_bf16_3d(&L->tmX, p.X, p.Cx, p.x_frame_pix, p.B, uint64_t(p.x_row_stride) * 2,
                             uint64_t(p.x_frame_pix) * p.x_row_stride * 2, 64, 64);
   if (r) return -1000 - r;
@@ -492,9 +551,34 @@ int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L) {
 
 int run_wgrad_gemm(const WgradLaunch& L, cudaStream_t st) {
   dim3 grid(L.grid_x, L.grid_y, L.grid_z);
-  wgrad_gemm_tc_kernel<<<grid, kWgradThreads, L.smem, st>>>(L.tmX, L.tmY, L.p, L.stages, L.tmem_cols);
+  wgrad_gemm_tc_kernel<<<grid, kWgradThreads, L.smem, st>>>(L.tmX, L.tmY, L.p, L.stages, L.tmem_cols, L.na);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : -4000 - int(e);
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int64_t stride,
+                                                           int64_t n, float* dW) {
+  const int64_t n4 = n >> 2;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    float4 acc = reinterpret_cast<float4*>(dW)[i];
+    for (int z = 0; z < nsplit; ++z) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(part + z * stride) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dW)[i] = acc;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      float a = dW[i];
+      for (int z = 0; z < nsplit; ++z) a += part[z * stride + i];
+      dW[i] = a;
+    }
+}
+void launch_wgrad_reduce(const WgradLaunch& L, int64_t numel, cudaStream_t st) {
+  int blocks = int((numel / 4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(L.p.part, L.p.ksplit, L.p.part_stride, numel, L.p.dW);
 }
 
 int read_tc_watchdog() {

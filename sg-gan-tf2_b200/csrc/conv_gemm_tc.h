@@ -22,6 +22,7 @@ struct WgradLaunch {
   CUtensorMap tmX, tmY;
   int grid_x, grid_y, grid_z;
   int stages;
+  int na;  // accumulators (128 x-channels each) per CTA
   unsigned tmem_cols;
   size_t smem;
 };
@@ -31,6 +32,8 @@ int prepare_conv_gemm(const ConvGemmParams& p, ConvGemmLaunch* L);
 int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st);
 int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L);
 int run_wgrad_gemm(const WgradLaunch& L, cudaStream_t st);
+// dW[i] += sum over split-K slices (fixed order) of the partial tiles, i < numel
+void launch_wgrad_reduce(const WgradLaunch& L, int64_t numel, cudaStream_t st);
 int read_tc_watchdog();
 
 }  // namespace sggan

@@ -119,7 +119,7 @@ int layer_geometry(Layer& l) {
       break;
     case LT_OUT7:
       l.CoutN = 32; l.CinN = l.Cin;
-      l.packf.mode = 0; l.packf.T = k * k; l.packf.N = 32; l.packf.K = l.Cin;
+      l.packf.mode = 7; l.packf.T = k; l.packf.N = 32; l.packf.K = l.Cin;  // rows = (kw, co) pairs, one slab per kh
       l.packd.mode = 5; l.packd.T = k; l.packd.N = l.Cin; l.packd.K = 64;
       l.unpack_mode = 1; l.wscratch_elems = ((k + 1) / 2) * 128 * 64;
       break;
@@ -173,8 +173,13 @@ static int layer_prepare_fwd_impl(Layer& l, const float* bias, void* out, const 
     return 0;
   };
   switch (l.type) {
-    case LT_S1:
     case LT_OUT7:
+      // one tap per filter row; the kw taps live in N and are added across rows by the shift-sum epilogue
+      p.Cin = l.Cin; p.ntaps = k; p.shift_kw = k;
+      for (int kh = 0; kh < k; ++kh) { p.tap_off[kh] = kh * P; p.tap_w[kh] = uint8_t(kh); }
+      p.M = l.Hout * P; p.Hv = l.Hout; p.Wv = l.Wout;
+      return push(p);
+    case LT_S1:
       p.Cin = l.Cin; p.ntaps = k * k;
       for (int kh = 0; kh < k; ++kh)
         for (int kw = 0; kw < k; ++kw) { p.tap_off[kh * k + kw] = kh * P + kw; p.tap_w[kh * k + kw] = uint8_t(kh * k + kw); }
@@ -298,7 +303,7 @@ int layer_prepare_dgrad(Layer& l, int b0, int nimg, bool dry) {
 }
 
 // wgrad launches over the first nimg images; dW = gradient of the layer's kernel (Keras layout).
-int layer_prepare_wgrad(Layer& l, float* dW, int nimg, bool dry) {
+int layer_prepare_wgrad(Layer& l, float* dW, int nimg, bool dry, float* part, size_t part_elems) {
   l.wgrad.clear();
   const int k = l.k, P = l.P;
   WgradParams p;
@@ -333,13 +338,18 @@ int layer_prepare_wgrad(Layer& l, float* dW, int nimg, bool dry) {
   }
   auto finish = [&](WgradParams& q) -> int {
     q.Mpix = Mpix;
-    const int tiles = (q.x_pair ? 1 : q.Cx / 128) * q.ntaps * (q.Cy / q.BN);
+    const int na = (!q.x_pair && q.Cx % 256 == 0) ? 2 : 1;  // as chosen by prepare_wgrad_gemm
+    const int tiles = (q.x_pair ? 1 : q.Cx / (128 * na)) * q.ntaps * (q.Cy / q.BN);
     const int chunks = nimg * ((Mpix + 63) / 64);
     // one CTA per SM holds a whole accumulator: fill exactly one wave of 148 SMs (no tail round)
     int ks = tiles >= 148 ? 1 : 148 / tiles;
     if (ks > chunks / 8) ks = chunks / 8;
     if (ks < 1) ks = 1;
     q.ksplit = ks;
+    if (part != nullptr && !q.x_pair) {
+      const int64_t numel = int64_t(q.ntaps) * q.dw_tap_stride;
+      if (size_t(numel) * size_t(ks) <= part_elems && (numel & 3) == 0) { q.part = part; q.part_stride = numel; }
+    }
     WgradLaunch L;
     if (dry) { L.p = q; l.wgrad.push_back(L); return 0; }
     int r = prepare_wgrad_gemm(q, &L);
@@ -528,7 +538,7 @@ int Engine::prepare_layer(Net& n, int li) {
   else r = layer_prepare_dgrad(l, 0, l.nbv, dry);
   if (r) return r;
   float* dW = n.g ? n.g + n.T[l.ti_w].offset : nullptr;
-  return layer_prepare_wgrad(l, dW, l.nb, dry);
+  return layer_prepare_wgrad(l, dW, l.nb, dry, wg_part, wg_part_elems);
 }
 
 int Engine::build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t stream, bool dry_run, size_t* need) {
@@ -567,6 +577,12 @@ int Engine::build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t
   dGl = (float*)a.take(size_t(B) * H * W * 3 * 4);
   const Layer& rb = G.L[3];
   for (int i = 0; i < 2; ++i) resG[i] = (sg_bf16*)a.take(size_t(B) * rb.Hin * rb.Win * rb.Cin * 2);
+  wg_part_elems = size_t(160) * 256 * 256;  // one (2 x 128) x 256 fp32 tile per CTA of a single-wave split-K launch
+  wg_part = (float*)a.take(wg_part_elems * 4);
+  for (int i = 0; i < 2; ++i) {
+    pack_jobs[i] = (PackParams*)a.take(kMaxPackJobs * sizeof(PackParams));
+    pack_starts[i] = (int*)a.take((kMaxPackJobs + 1) * sizeof(int));
+  }
   if (need) *need = a.off + 256;
   if (dry) return 0;
   if (a.off > ws_bytes) { err = "workspace too small"; return SGGAN_E_WORKSPACE; }
@@ -575,6 +591,7 @@ int Engine::build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t
   if (cudaMemsetAsync(ws, 0, a.off, st) != cudaSuccess) { err = "cudaMemset of the workspace failed"; return SGGAN_E_CUDA; }
   for (size_t i = 0; i < G.L.size(); ++i)
     if ((r = prepare_layer(G, int(i)))) { err = "generator layer " + std::to_string(i) + " prepare failed: " + std::to_string(r); return SGGAN_E_CUDA; }
+  if ((r = upload_pack_jobs(SGGAN_NET_G)) || (r = upload_pack_jobs(SGGAN_NET_D))) { err = "weight-pack job table upload failed"; return r; }
   for (size_t i = 0; i < D.L.size(); ++i)
     if ((r = prepare_layer(D, int(i)))) { err = "discriminator layer " + std::to_string(i) + " prepare failed: " + std::to_string(r); return SGGAN_E_CUDA; }
   return 0;
@@ -582,18 +599,41 @@ int Engine::build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t
 
 // ---------------------------------------------------------------------------------------------
 int Engine::pack_weights(int net) {
+  // one launch per net: the job table (one PackParams per weight slab) was uploaded by build()
+  launch_pack_weights_batch(pack_jobs[net], pack_starts[net], pack_njobs[net], pack_blocks[net], st);
+  ++nlaunch;
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+
+int Engine::upload_pack_jobs(int net) {
   Net& n = net == SGGAN_NET_G ? G : D;
+  std::vector<PackParams> jobs;
+  std::vector<int> starts;
+  int blocks = 0;
+  auto add = [&](PackParams q) {
+    starts.push_back(blocks);
+    blocks += int((int64_t(q.T) * q.N * q.K + 255) / 256);
+    jobs.push_back(q);
+  };
   for (auto& l : n.L) {
     PackParams pf = l.packf;
     pf.src = n.p + n.T[l.ti_w].offset; pf.dst = l.Wf;
-    launch_pack_weights(pf, st); ++nlaunch;
+    add(pf);
     if (l.packd.T) {
       PackParams pd = l.packd;
       pd.src = n.p + n.T[l.ti_w].offset; pd.dst = l.Wd;
-      launch_pack_weights(pd, st); ++nlaunch;
+      add(pd);
     }
   }
-  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+  starts.push_back(blocks);
+  if (jobs.size() > kMaxPackJobs) return SGGAN_E_INVALID;
+  pack_njobs[net] = int(jobs.size());
+  pack_blocks[net] = blocks;
+  if (cudaMemcpyAsync(pack_jobs[net], jobs.data(), jobs.size() * sizeof(PackParams), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(pack_starts[net], starts.data(), starts.size() * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaStreamSynchronize(st) != cudaSuccess)  // the host vectors go out of scope
+    return SGGAN_E_CUDA;
+  return 0;
 }
 
 int Engine::run_conv_list(const std::vector<ConvGemmLaunch>& v) {
@@ -610,6 +650,7 @@ int Engine::run_wgrad(Layer& l, Net& n) {
     int r = run_wgrad_gemm(L, st);
     ++nlaunch;
     if (r) { err = "wgrad launch failed " + std::to_string(r); return SGGAN_E_CUDA; }
+    if (L.p.part != nullptr) { launch_wgrad_reduce(L, int64_t(L.p.ntaps) * L.p.dw_tap_stride, st); ++nlaunch; }
   }
   if (l.unpack_mode >= 0) {
     launch_unpack_wgrad(l.wscratch, n.g + n.T[l.ti_w].offset, l.unpack_mode, l.k, l.k, l.Cin, l.Cout, 64, st);

@@ -80,6 +80,12 @@ struct Engine {
   // misc buffers
   float *fake, *h4, *logits, *loss, *dD, *edge_w, *dGl;
   sg_bf16* resG[2];
+  static constexpr size_t kMaxPackJobs = 64;
+  PackParams* pack_jobs[2];
+  int* pack_starts[2];
+  int pack_njobs[2], pack_blocks[2];
+  float* wg_part;  // split-K partial tiles of the weight-gradient GEMMs (shared by all layers)
+  size_t wg_part_elems;
   uint8_t *zero_begin, *zero_end;
   int64_t step;
   int nlaunch;
@@ -92,6 +98,7 @@ struct Engine {
 
   int build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t stream, bool dry_run, size_t* need);
   int pack_weights(int net);
+  int upload_pack_jobs(int net);
   int gen_forward(const float* real_A, float* fake_out);
   int disc_forward_2b(const float* real_img, const float* fake_img, int nimg_each);
   int disc_forward_user(const float* x, const float* mask, float* logits_out);

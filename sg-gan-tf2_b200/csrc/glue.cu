@@ -312,28 +312,32 @@ __device__ float block_sum(float v, float* sh) {
   return r;  // valid in warp 0
 }
 
-// One block: the logits are KB-sized (B x 5 x 13 at 256x512).
-__global__ void __launch_bounds__(256) disc_loss_kernel(const DiscLossParams p) {
+// The logits are KB-sized (B x 5 x 13 at 256x512): two small multi-block launches.
+__global__ void disc_logits_kernel(const DiscLossParams p) {
+  const int Ho = max(p.Hd, p.hm), Wo = max(p.Wd, p.wm);
+  const int npos = Ho * Wo;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * p.B * npos) return;
+  const int b = idx / npos, r = idx - b * npos, I = r / Wo, J = r - I * Wo;
+  const int ih = p.Hd == 1 ? 0 : I, jh = p.Wd == 1 ? 0 : J, im = p.hm == 1 ? 0 : I, jm = p.wm == 1 ? 0 : J;
+  const float* h = p.h4 + ((int64_t(b) * p.Hd + ih) * p.Wd + jh) * p.Cs;
+  const float* mk = p.mask + ((int64_t(b % p.B) * p.hm + im) * p.wm + jm) * p.Cs;
+  float s = 0.f;
+  for (int c = 0; c < p.Cs; ++c) s += h[c] * mk[c];
+  p.logits[idx] = s;
+}
+__global__ void __launch_bounds__(256) disc_loss_grad_kernel(const DiscLossParams p) {
   __shared__ float sh[32];
   extern __shared__ float sbias[];
   const int Ho = max(p.Hd, p.hm), Wo = max(p.Wd, p.wm);
   const int B2 = 2 * p.B, npos = Ho * Wo;
   const float N = float(p.B) * npos;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
   for (int t = threadIdx.x; t < p.Cs; t += blockDim.x) sbias[t] = 0.f;
-  // 1. masked logits
-  for (int idx = threadIdx.x; idx < B2 * npos; idx += blockDim.x) {
-    const int b = idx / npos, r = idx - b * npos, I = r / Wo, J = r - I * Wo;
-    const int ih = p.Hd == 1 ? 0 : I, jh = p.Wd == 1 ? 0 : J, im = p.hm == 1 ? 0 : I, jm = p.wm == 1 ? 0 : J;
-    const float* h = p.h4 + ((int64_t(b) * p.Hd + ih) * p.Wd + jh) * p.Cs;
-    const float* mk = p.mask + ((int64_t(b % p.B) * p.hm + im) * p.wm + jm) * p.Cs;
-    float s = 0.f;
-    for (int c = 0; c < p.Cs; ++c) s += h[c] * mk[c];
-    p.logits[idx] = s;
-  }
   __syncthreads();
-  // 2. losses
+  // losses
   float lg = 0.f, ld = 0.f;
-  for (int idx = threadIdx.x; idx < B2 * npos; idx += blockDim.x) {
+  for (int idx = gtid; idx < B2 * npos; idx += gstride) {
     const int b = idx / npos;
     const float x = p.logits[idx];
     if (p.lsgan) {
@@ -351,9 +355,9 @@ __global__ void __launch_bounds__(256) disc_loss_kernel(const DiscLossParams p) 
     atomicAdd(p.loss + 0, lg / N);
     atomicAdd(p.loss + 1, ld * p.disc_scale / N);
   }
-  // 3. d logits -> d h4 (3B virtual images) and bias gradient
+  // d logits -> d h4 (3B virtual images: real-D, fake-D, fake-G) and the bias gradient (first 2B)
   const int tot = 3 * p.B * p.Hd * p.Wd * p.Cs;
-  for (int idx = threadIdx.x; idx < tot; idx += blockDim.x) {
+  for (int idx = gtid; idx < tot; idx += gstride) {
     const int c = idx % p.Cs;
     int r = idx / p.Cs;
     const int jh = r % p.Wd;
@@ -377,10 +381,17 @@ __global__ void __launch_bounds__(256) disc_loss_kernel(const DiscLossParams p) 
     if (v < B2) atomicAdd(&sbias[c], g);
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < p.Cs; t += blockDim.x) atomicAdd(p.dbias + t, sbias[t]);
+  for (int t = threadIdx.x; t < p.Cs; t += blockDim.x)
+    if (sbias[t] != 0.f) atomicAdd(p.dbias + t, sbias[t]);
 }
 void launch_disc_loss(const DiscLossParams& p, cudaStream_t st) {
-  disc_loss_kernel<<<1, 256, p.Cs * sizeof(float), st>>>(p);
+  const int Ho = p.Hd > p.hm ? p.Hd : p.hm, Wo = p.Wd > p.wm ? p.Wd : p.wm;
+  const int nlog = 2 * p.B * Ho * Wo;
+  disc_logits_kernel<<<(nlog + 127) / 128, 128, 0, st>>>(p);
+  const int tot = 3 * p.B * p.Hd * p.Wd * p.Cs;
+  int blocks = (tot + 255) / 256;
+  if (blocks > 148) blocks = 148;
+  disc_loss_grad_kernel<<<blocks, 256, p.Cs * sizeof(float), st>>>(p);
 }
 
 __global__ void mask_reduce_kernel(const float* __restrict__ x, const float* __restrict__ mask, int B, int Hd, int Wd,
@@ -597,8 +608,8 @@ void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float 
 //  mode 4 window fwd, stride 1 (generator c1):   t=kh        n=co  k=q*8+ci, kw=q
 //  mode 5 window dgrad (generator output conv):  t=kh        n=ci  k=q*8+co, kw=KW-1-q
 //  mode 6 window fwd, stride 2 (disc. h0):       t=kh*2+bp   n=co  k=q*8+ci, kw=2q+bp
-__global__ void pack_weights_kernel(const PackParams p) {
-  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+//  mode 7 shift-sum fwd (generator output conv): t=kh        n=kw*4+co  k=ci
+__device__ __forceinline__ void pack_one(const PackParams& p, int64_t idx) {
   const int64_t tot = int64_t(p.T) * p.N * p.K;
   if (idx >= tot) return;
   const int k = int(idx % p.K), n = int((idx / p.K) % p.N), t = int(idx / (int64_t(p.K) * p.N));
@@ -613,10 +624,32 @@ __global__ void pack_weights_kernel(const PackParams p) {
       if (q < p.KW && ci < Ci && n < Co) v = p.src[((int64_t(t) * p.KW + q) * Ci + ci) * Co + n]; break; }
     case 5: { const int q = k >> 3, co = k & 7;
       if (q < p.KW && co < Co && n < Ci) v = p.src[((int64_t(t) * p.KW + (p.KW - 1 - q)) * Ci + n) * Co + co]; break; }
+    case 7: { const int kw = n >> 2, co = n & 3;  // shift-sum output conv: t = kh, n = kw*4 + co, k = ci
+      if (kw < p.KW && co < Co && k < Ci) v = p.src[((int64_t(t) * p.KW + kw) * Ci + k) * Co + co]; break; }
     case 6: { const int kh = t >> 1, bp = t & 1, q = k >> 3, ci = k & 7, kw = 2 * q + bp;
       if (kw < p.KW && ci < Ci && n < Co) v = p.src[((int64_t(kh) * p.KW + kw) * Ci + ci) * Co + n]; break; }
   }
   reinterpret_cast<__nv_bfloat16*>(p.dst)[idx] = __float2bfloat16_rn(v);
+}
+__global__ void pack_weights_kernel(const PackParams p) { pack_one(p, int64_t(blockIdx.x) * blockDim.x + threadIdx.x); }
+__global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackParams* __restrict__ jobs,
+                                                                 const int* __restrict__ starts, int njobs) {
+  __shared__ PackParams sp;
+  __shared__ int sj;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;  // last job whose first block is <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (starts[mid] <= int(blockIdx.x)) lo = mid; else hi = mid - 1;
+    }
+    sj = lo;
+    sp = jobs[lo];
+  }
+  __syncthreads();
+  pack_one(sp, int64_t(int(blockIdx.x) - starts[sj]) * 256 + threadIdx.x);
+}
+void launch_pack_weights_batch(const PackParams* jobs, const int* starts, int njobs, int total_blocks, cudaStream_t st) {
+  pack_weights_batch_kernel<<<total_blocks, 256, 0, st>>>(jobs, starts, njobs);
 }
 void launch_pack_weights(const PackParams& p, cudaStream_t st) {
   const int64_t tot = int64_t(p.T) * p.N * p.K;

@@ -98,6 +98,8 @@ struct PackParams {
   int KH, KW, Cin, Cout;
 };
 void launch_pack_weights(const PackParams& p, cudaStream_t st);
+// all slabs of a net in ONE launch: jobs / starts (prefix sums of 256-thread blocks, njobs+1 entries) live on the device
+void launch_pack_weights_batch(const PackParams* jobs, const int* starts, int njobs, int total_blocks, cudaStream_t st);
 // window-wgrad scratch [pairs][128][ncol] -> Keras-layout gradient; mode 0 c1, 1 out conv, 2 h0.
 void launch_unpack_wgrad(const float* scratch, float* dW, int mode, int KH, int KW, int Cin, int Cout, int ncol,
                          cudaStream_t st);

@@ -88,6 +88,12 @@ struct ConvGemmParams {
   int stats_t0;       // first tile index of this launch
   int act;
   float act_alpha;
+  // Shift-sum mode (the 7x7, 64 -> 3 output convolution): the N dimension holds (kw, co) pairs (co padded to
+  // 4), each filter ROW is one tap, and the epilogue adds the kw partial products of neighbouring rows:
+  //   out[m, co] = act(bias[co] + sum_kw acc[m + kw, kw*4 + co]).  CTA tiles then advance by MT - (shift_kw-1).
+  // 7x fewer tensor-core instructions than one tap per (kh, kw) at N = 32 (tcgen05.mma has a ~156-cycle
+  // floor per instruction regardless of N).
+  int shift_kw;
   long long* dbg;  // optional per-CTA clock64 stamps [grid][8] (tests/gpu/tc_probe.cu); null in production
 };
 
@@ -118,6 +124,11 @@ struct WgradParams {
   float* dW;
   int64_t dw_tap_stride, dw_sx, dw_sy;
   int ksplit;
+  // Split-K partials: when `part` is set, slice z of the K range stores its tile with plain 128-bit stores to
+  // part + z * part_stride (same element strides as dW) and launch_wgrad_reduce adds the slices in a fixed
+  // order (deterministic, and ~5x cheaper than 128 KB of fp32 atomics per CTA).  Null: red.global into dW.
+  float* part;
+  int64_t part_stride;
 };
 
 // ---------------------------------------------------------------------------------------------
