@@ -52,25 +52,16 @@ struct RowStreamParams {
   FrameMap dmap;
 };
 
-__device__ __forceinline__ float rw_act_fwd(float v, int act, float a) {
-  if (act == SG_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == SG_ACT_LRELU) return v > 0.f ? v : a * v;
-  if (act == SG_ACT_TANH) return tanhf(v);
-  return v;
-}
-__device__ __forceinline__ float rw_act_grad(float zpre, int act, float a) {
-  if (act == SG_ACT_RELU) return zpre > 0.f ? 1.f : 0.f;
-  if (act == SG_ACT_LRELU) return zpre > 0.f ? 1.f : a;
-  return 1.f;
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 u;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(saddr));
+  return u;
 }
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float2 t = __bfloat1622float2(h[k]);
-    f[2 * k] = t.x;
-    f[2 * k + 1] = t.y;
-  }
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
   uint4 u;
@@ -209,11 +200,15 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   }
 
   // -------------------------------------------------------------- consumers
+  // Thread t owns vector t (16 B = 8 channels) of every 512-vector slab of a chunk: its channel group is
+  // fixed, its pixel advances by 512/C8 per slab, so all addressing is incremental.
   const int C8 = p.C >> 3;
-  const int cg = threadIdx.x % C8;  // constant per thread: kConsumers is a multiple of C8
+  const int cg = threadIdx.x % C8;
   const int c0 = cg * 8;
-  const int px0 = threadIdx.x / C8, pstep = kConsumers / C8;
+  const int px0 = threadIdx.x / C8, pstep = kConsumers / C8;  // pstep is even (C8 <= 64)
   const float n = float(p.H * p.W);
+  // activation as a slope for the non-positive side: relu 0, leaky alpha, identity 1 (tanh never reaches the glue)
+  const float gneg = p.act == SG_ACT_RELU ? 0.f : (p.act == SG_ACT_LRELU ? p.alpha : 1.f);
   float mean[8], rstd[8], scale[8], beta[8], a1[8], a2[8];
   if (MODE != RS_GATHER) {
 #pragma unroll
@@ -221,9 +216,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       const int c = c0 + e;
       float mu = 0.f, rs = 1.f;
       if (p.stats != nullptr) {
-        const float2 s = reinterpret_cast<const float2*>(p.stats)[int64_t(ba) * p.C + c];
-        mu = s.x / n;
-        rs = rsqrtf(fmaxf(s.y / n - mu * mu, 0.f) + p.eps);
+        const float2 st = reinterpret_cast<const float2*>(p.stats)[int64_t(ba) * p.C + c];
+        mu = st.x / n;
+        rs = rsqrtf(fmaxf(st.y / n - mu * mu, 0.f) + p.eps);
       }
       mean[e] = mu;
       rstd[e] = rs;
@@ -237,66 +232,96 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       }
     }
   }
+  const bool has0 = p.s[0].base != nullptr, has1 = p.s[1].base != nullptr, has2 = p.s[2].base != nullptr;
+  const int W = p.W, C = p.C, CW = p.CW;
+  const int src_band = (MODE == RS_APPLY) ? 0 : max(p.g[0].ptr ? p.g[0].fold : 0, p.g[1].ptr ? p.g[1].fold : 0);
+  const int dst_band = ((MODE == RS_APPLY || MODE == RS_BWD_APPLY) && p.dmap.kind == 0) ? p.dmap.reflect : 0;
+  const int band = max(src_band, dst_band);
+  const int dC = (MODE == RS_GATHER) ? C : p.dmap.C;
+  const int dkind = (MODE == RS_GATHER) ? 0 : p.dmap.kind;
+  const uint32_t sbase = smem_u32(smem) + threadIdx.x * 16;
   int k = 0;
   for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++k) {
     const int s = k % kStages;
-    const int i = c / cpr, j0 = (c - i * cpr) * p.CW;
-    const int cw = min(p.CW, p.W - j0);
+    const int i = c / cpr, j0 = (c - i * cpr) * CW;
+    const int cw = min(CW, W - j0);
     DstRow dr;
     SrcRow e1, e2;
+    e1.n = e2.n = 0;
+    dr.n = 1;
     if (MODE == RS_APPLY || MODE == RS_BWD_APPLY) dst_row_init(dr, p.dst, p.dmap, b, i, c0);
-    if (MODE == RS_BWD_REDUCE || MODE == RS_BWD_APPLY) {
-      src_row_init(e1, p.g[0], b, i, p.H, p.C, c0);
-      src_row_init(e2, p.g[1], b, i, p.H, p.C, c0);
+    if (MODE != RS_APPLY) {
+      src_row_init(e1, p.g[0], b, i, p.H, C, c0);
+      src_row_init(e2, p.g[1], b, i, p.H, C, c0);
     }
+    // pixels [lo, hi) of this chunk need no border bookkeeping
+    int lo = 0, hi = cw;
+    if (dr.n > 1 || e1.n > 1 || e2.n > 1) {
+      hi = 0;
+    } else if (band > 0) {
+      lo = min(cw, max(0, band + 1 - j0));
+      hi = max(lo, min(cw, W - 1 - band - j0));
+    }
+    // incremental destination pointer of this thread (element units)
+    sg_bf16* dptr;
+    int dstep;
     if (MODE == RS_GATHER) {
-      src_row_init(e1, p.g[0], b, i, p.H, p.C, c0);
-      src_row_init(e2, p.g[1], b, i, p.H, p.C, c0);
+      dptr = p.dst + ((int64_t(b) * p.H + i) * W + j0 + px0) * C + c0;
+      dstep = pstep * C;
+    } else if (dkind == 0) {
+      dptr = dr.base[0] + (j0 + px0) * dC;
+      dstep = pstep * dC;
+    } else {  // phase planes: the column parity of this thread is fixed because pstep is even
+      dptr = dr.base[(j0 + px0) & 1] + ((j0 + px0) >> 1) * dC;
+      dstep = (pstep >> 1) * dC;
     }
     mbar_wait(&full_bar[s], (k / kStages) & 1, 42);
-    const uint4* s0 = reinterpret_cast<const uint4*>(smem + (s * kMaxStreams + 0) * kChunkBytes);
-    const uint4* s1 = reinterpret_cast<const uint4*>(smem + (s * kMaxStreams + 1) * kChunkBytes);
-    const uint4* s2 = reinterpret_cast<const uint4*>(smem + (s * kMaxStreams + 2) * kChunkBytes);
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int px = px0; px < cw; px += pstep) {
-      const int v = px * C8 + cg;
+    uint32_t sa = sbase + s * (kMaxStreams * kChunkBytes);
+    for (int px = px0; px < cw; px += pstep, sa += kConsumers * 16, dptr += dstep) {
+      const bool lean = px >= lo && px < hi;
       const int j = j0 + px;
+      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
+      if (has0) r0 = lds128(sa);
+      if (has1) r1 = lds128(sa + kChunkBytes);
+      if (has2) r2 = lds128(sa + 2 * kChunkBytes);
+      float y[8], d[8];
       if (MODE == RS_APPLY) {
-        float y[8];
-        unpack8(s0[v], y);
+        unpack8(r0, y);
+        unpack8(r1, d);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) y[e] = rw_act_fwd(fmaf(y[e] - mean[e], scale[e], beta[e]), p.act, p.alpha);
-        if (p.s[1].base) {
-          float r[8];
-          unpack8(s1[v], r);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) y[e] += r[e];
+        for (int e = 0; e < 8; ++e) {
+          const float z = fmaf(y[e] - mean[e], scale[e], beta[e]);
+          y[e] = (z > 0.f ? z : z * gneg) + d[e];
         }
-        dst_store8(dr, p.dmap, j, pack8(y));
+        if (lean) *reinterpret_cast<uint4*>(dptr) = pack8(y);
+        else dst_store8(dr, p.dmap, j, pack8(y));
       } else if (MODE == RS_GATHER) {
-        float d[8], t[8];
-        unpack8(p.s[0].base ? s0[v] : zero, d);
-        unpack8(p.s[1].base ? s1[v] : zero, t);
+        unpack8(r0, d);
+        unpack8(r1, y);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) d[e] += t[e];
-        if (src_has_extra(e1, p.g[0], j, p.W)) src_extra8(e1, p.g[0], j, p.W, p.C, d);
-        if (src_has_extra(e2, p.g[1], j, p.W)) src_extra8(e2, p.g[1], j, p.W, p.C, d);
-        *reinterpret_cast<uint4*>(p.dst + ((int64_t(b) * p.H + i) * p.W + j) * p.C + c0) = pack8(d);
+        for (int e = 0; e < 8; ++e) d[e] += y[e];
+        if (!lean) {
+          if (src_has_extra(e1, p.g[0], j, W)) src_extra8(e1, p.g[0], j, W, C, d);
+          if (src_has_extra(e2, p.g[1], j, W)) src_extra8(e2, p.g[1], j, W, C, d);
+        }
+        *reinterpret_cast<uint4*>(dptr) = pack8(d);
       } else {
-        float y[8], d[8], t[8];
-        unpack8(s0[v], y);
-        unpack8(p.s[1].base ? s1[v] : zero, d);
-        unpack8(p.s[2].base ? s2[v] : zero, t);
+        float t[8];
+        unpack8(r0, y);
+        unpack8(r1, d);
+        unpack8(r2, t);
 #pragma unroll
         for (int e = 0; e < 8; ++e) d[e] += t[e];
-        if (src_has_extra(e1, p.g[0], j, p.W)) src_extra8(e1, p.g[0], j, p.W, p.C, d);
-        if (src_has_extra(e2, p.g[1], j, p.W)) src_extra8(e2, p.g[1], j, p.W, p.C, d);
+        if (!lean) {
+          if (src_has_extra(e1, p.g[0], j, W)) src_extra8(e1, p.g[0], j, W, C, d);
+          if (src_has_extra(e2, p.g[1], j, W)) src_extra8(e2, p.g[1], j, W, C, d);
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           // zpre = (y - mean)*scale + beta;  xhat = (y - mean)*rstd.  The apply form keeps a single-pixel norm
           // (xhat == 0, dzh == m1) back-propagating exactly zero, as the reference does at 128x128 (Appendix B).
           const float yc = y[e] - mean[e];
-          const float dz = d[e] * rw_act_grad(fmaf(yc, scale[e], beta[e]), p.act, p.alpha);
+          const float dz = fmaf(yc, scale[e], beta[e]) > 0.f ? d[e] : d[e] * gneg;
           const float xh = yc * rstd[e];
           if (MODE == RS_BWD_APPLY) {
             d[e] = scale[e] * ((dz - a1[e]) - xh * a2[e]);
@@ -305,7 +330,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
             a2[e] += dz * xh;
           }
         }
-        if (MODE == RS_BWD_APPLY) dst_store8(dr, p.dmap, j, pack8(d));
+        if (MODE == RS_BWD_APPLY) {
+          if (lean) *reinterpret_cast<uint4*>(dptr) = pack8(d);
+          else dst_store8(dr, p.dmap, j, pack8(d));
+        }
       }
     }
     __syncwarp();
