@@ -153,13 +153,16 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
-  __shared__ float sred[1024];  // MODE == RS_BWD_REDUCE: 2 * C partial sums (C <= 512)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int ba = b < p.nb_act ? b : b - p.act_wrap;
   const int cpr = (p.W + p.CW - 1) / p.CW;  // chunks per row
   const int nchunks = p.H * cpr;
+  // each block owns a contiguous range of chunks, so consecutive chunks mostly share their image row and the
+  // per-row bookkeeping (border rows, base pointers) is amortised
+  const int cper = (nchunks + gridDim.x - 1) / gridDim.x;
+  const int cbeg = blockIdx.x * cper, cend = min(nchunks, cbeg + cper);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -168,15 +171,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     }
     fence_barrier_init();
   }
-  if (MODE == RS_BWD_REDUCE)
-    for (int t = threadIdx.x; t < 2 * p.C; t += kStreamThreads) sred[t] = 0.f;
   __syncthreads();
 
   if (warp == kConsumers / 32) {
     // ------------------------------------------------------------ producer: bulk copies, kStages chunks ahead
     if (lane == 0) {
       int k = 0;
-      for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++k) {
+      for (int c = cbeg; c < cend; ++c, ++k) {
         const int s = k % kStages;
         mbar_wait(&empty_bar[s], ((k / kStages) & 1) ^ 1, 41);
         const int i = c / cpr, j0 = (c - i * cpr) * p.CW;
@@ -241,18 +242,22 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   const int dkind = (MODE == RS_GATHER) ? 0 : p.dmap.kind;
   const uint32_t sbase = smem_u32(smem) + threadIdx.x * 16;
   int k = 0;
-  for (int c = blockIdx.x; c < nchunks; c += gridDim.x, ++k) {
+  int cur_i = -1;
+  DstRow dr;
+  SrcRow e1, e2;
+  e1.n = e2.n = 0;
+  dr.n = 1;
+  for (int c = cbeg; c < cend; ++c, ++k) {
     const int s = k % kStages;
     const int i = c / cpr, j0 = (c - i * cpr) * CW;
     const int cw = min(CW, W - j0);
-    DstRow dr;
-    SrcRow e1, e2;
-    e1.n = e2.n = 0;
-    dr.n = 1;
-    if (MODE == RS_APPLY || MODE == RS_BWD_APPLY) dst_row_init(dr, p.dst, p.dmap, b, i, c0);
-    if (MODE != RS_APPLY) {
-      src_row_init(e1, p.g[0], b, i, p.H, C, c0);
-      src_row_init(e2, p.g[1], b, i, p.H, C, c0);
+    if (i != cur_i) {  // new image row: resolve border rows and base pointers once
+      cur_i = i;
+      if (MODE == RS_APPLY || MODE == RS_BWD_APPLY) dst_row_init(dr, p.dst, p.dmap, b, i, c0);
+      if (MODE != RS_APPLY) {
+        src_row_init(e1, p.g[0], b, i, p.H, C, c0);
+        src_row_init(e2, p.g[1], b, i, p.H, C, c0);
+      }
     }
     // pixels [lo, hi) of this chunk need no border bookkeeping
     int lo = 0, hi = cw;
@@ -340,13 +345,21 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
   if (MODE == RS_BWD_REDUCE) {
+    // threads that share a channel group differ in px0 (kConsumers / C8 of them): stage their partials in the
+    // (now idle) pipeline buffers as [px0][2C] and add them in a fixed order
+    float* red = reinterpret_cast<float*>(smem);
+    named_bar_sync(2, kConsumers);  // every consumer is past its last chunk: the stage buffers are free
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sred[(c0 + e) * 2], a1[e]);
-      atomicAdd(&sred[(c0 + e) * 2 + 1], a2[e]);
+      red[px0 * 2 * C + (c0 + e) * 2] = a1[e];
+      red[px0 * 2 * C + (c0 + e) * 2 + 1] = a2[e];
     }
     named_bar_sync(2, kConsumers);
-    for (int t = threadIdx.x; t < 2 * p.C; t += kConsumers) atomicAdd(p.sums + int64_t(b) * p.C * 2 + t, sred[t]);
+    for (int t = threadIdx.x; t < 2 * C; t += kConsumers) {
+      float acc = 0.f;
+      for (int q = 0; q < pstep; ++q) acc += red[q * 2 * C + t];
+      atomicAdd(p.sums + int64_t(b) * C * 2 + t, acc);
+    }
   }
 }
 
