@@ -39,7 +39,10 @@ constexpr int kABytes = kTileM * kChunkK * 2;  // 16 KB: one 128-row A box
 constexpr int kHaloRows = 8;                   // one extra swizzle atom of rows covers runs of up to 8 taps
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 200 * 1024;  // pipeline bytes (leaves room for alignment slack)
-constexpr int kConvThreads = 352;  // 3 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;                           // two warps per TMEM lane quarter (16 measured no faster:
+                                                       // the epilogue is bound by TMEM / smem / store traffic)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kConvThreads = 96 + kEpiThreads;  // 3 control warps + epilogue warps
 constexpr int kWgradThreads = 192;
 
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
@@ -163,17 +166,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (dbg) dbg[2] = clock64();
     }
   } else {
-    // ------------------------------------------------------------ epilogue (8 warps = 256 threads)
-    // Two warps share each TMEM lane quarter and split the 32-column chunks between them, so every
-    // scheduler has two epilogue warps to interleave.  The per-element work is kept branch-free: bias
+    // ------------------------------------------------------------ epilogue (kEpiWarps warps)
+    // The warps that share a TMEM lane quarter split the 32-column chunks between them, so every
+    // scheduler has several epilogue warps to interleave.  The per-element work is kept branch-free: bias
     // comes from smem (zero padded), padded weight rows make columns >= Cout exactly zero, the
     // activation is chosen once per chunk.
     mbar_wait(&acc_bar, 0, 3);
     tc_fence_after();
     const int q = warp & 3;
-    const int half = (warp - 3) >> 2;
+    const int half = (warp - 3) >> 2;  // 0 .. kEpiWarps/4 - 1: which share of the 32-column chunks
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 96;  // 0..255
+    const int et = threadIdx.x - 96;  // 0 .. kEpiThreads - 1
     if (dbg && et == 0) dbg[3] = clock64();
     float* tsm = reinterpret_cast<float*>(smem);  // [BN][129] transposed fp32 tile for the statistics
     const bool has_stats = p.stats != nullptr;
@@ -189,7 +192,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int e = 0; e < 32; ++e) srow[e] = v[e];
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, kEpiThreads);
       const int r = et;
       if (r < mstep) {
         const int m = m0 + r;
@@ -214,7 +217,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int64_t obase = (int64_t(b) * p.omap.frame_pix + (valid ? frame_pixel(p.omap, oi, oj) : 0)) * p.omap.C;
       const bool vec_ok = (!p.out_f32) && ((p.omap.C & 7) == 0);
       const float msk = valid ? 1.f : 0.f;
-      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+      for (int c0 = half * 32; c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
         float v[32];
         tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(a * BN + c0), v);
         const int nb = n0 + c0;
@@ -268,8 +271,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (has_stats) {
-        named_bar_sync(1, 256);
-        for (int c = et; c < BN; c += 256) {
+        named_bar_sync(1, kEpiThreads);
+        for (int c = et; c < BN; c += kEpiThreads) {
           const int n = n0 + c;
           if (n >= p.Cout) continue;
           const float* col = tsm + c * 129;
@@ -284,7 +287,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           float2* dst = reinterpret_cast<float2*>(p.stats) + (int64_t(b) * p.stats_T + tile) * p.Cout + n;
           *dst = make_float2(s1 + s1b, s2 + s2b);
         }
-        if (a + 1 < NA) named_bar_sync(1, 256);  // tsm is rewritten by the next accumulator
+        if (a + 1 < NA) named_bar_sync(1, kEpiThreads);  // tsm is rewritten by the next accumulator
       }
       if (dbg && et == 0) dbg[4 + a] = clock64();
     }

@@ -22,7 +22,7 @@ namespace sggan {
 constexpr int kConsumers = 512;                 // 16 consumer warps
 constexpr int kStreamThreads = kConsumers + 32;  // + 1 producer warp
 constexpr int kStages = 4;
-constexpr int kChunkBytes = 16384;  // per stream and stage
+constexpr int kPipeBytes = 196608;  // shared memory of the whole pipeline: kStages x streams x chunk
 constexpr int kMaxStreams = 3;
 
 enum { RS_APPLY = 0, RS_BWD_REDUCE = 1, RS_BWD_APPLY = 2, RS_GATHER = 3 };
@@ -37,6 +37,8 @@ struct StreamDesc {
 
 struct RowStreamParams {
   int B, H, W, C, CW;  // CW = pixels per chunk
+  int ns;              // active streams (a prefix of s[])
+  int chunk_bytes;     // bytes per stream and stage: the pipeline memory is split over kStages x ns chunks
   int nb_act, act_wrap;
   StreamDesc s[kMaxStreams];
   // statistics / affine
@@ -177,24 +179,21 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     // ------------------------------------------------------------ producer: bulk copies, kStages chunks ahead
     if (lane == 0) {
       int k = 0;
+      int i = cbeg / cpr, jc = cbeg - i * cpr;
       for (int c = cbeg; c < cend; ++c, ++k) {
         const int s = k % kStages;
         mbar_wait(&empty_bar[s], ((k / kStages) & 1) ^ 1, 41);
-        const int i = c / cpr, j0 = (c - i * cpr) * p.CW;
+        const int j0 = jc * p.CW;
         const int cw = min(p.CW, p.W - j0);
         const uint32_t bytes = uint32_t(cw) * p.C * 2;
-        uint32_t total = 0;
-#pragma unroll
-        for (int q = 0; q < kMaxStreams; ++q) total += p.s[q].base ? bytes : 0;
-        mbar_arrive_expect_tx(&full_bar[s], total);
-#pragma unroll
-        for (int q = 0; q < kMaxStreams; ++q) {
+        mbar_arrive_expect_tx(&full_bar[s], bytes * p.ns);
+        for (int q = 0; q < p.ns; ++q) {
           const StreamDesc& d = p.s[q];
-          if (d.base == nullptr) continue;
           const sg_bf16* src = d.base + int64_t(d.act_index ? ba : b) * d.img_stride + int64_t(i + d.oy) * d.row_stride +
                                int64_t(j0 + d.ox) * p.C;
-          bulk_load_1d(smem + (s * kMaxStreams + q) * kChunkBytes, src, bytes, &full_bar[s]);
+          bulk_load_1d(smem + (s * p.ns + q) * p.chunk_bytes, src, bytes, &full_bar[s]);
         }
+        if (++jc == cpr) { jc = 0; ++i; }
       }
     }
     return;
@@ -233,7 +232,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       }
     }
   }
-  const bool has0 = p.s[0].base != nullptr, has1 = p.s[1].base != nullptr, has2 = p.s[2].base != nullptr;
+  const bool has0 = p.ns > 0, has1 = p.ns > 1, has2 = p.ns > 2;
+  const uint32_t chunk_bytes = p.chunk_bytes, stage_bytes = p.ns * p.chunk_bytes;
   const int W = p.W, C = p.C, CW = p.CW;
   const int src_band = (MODE == RS_APPLY) ? 0 : max(p.g[0].ptr ? p.g[0].fold : 0, p.g[1].ptr ? p.g[1].fold : 0);
   const int dst_band = ((MODE == RS_APPLY || MODE == RS_BWD_APPLY) && p.dmap.kind == 0) ? p.dmap.reflect : 0;
@@ -247,9 +247,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   SrcRow e1, e2;
   e1.n = e2.n = 0;
   dr.n = 1;
-  for (int c = cbeg; c < cend; ++c, ++k) {
+  int i = cbeg / cpr, jc = cbeg - i * cpr;
+  for (int c = cbeg; c < cend; ++c, ++k, jc = (jc + 1 == cpr ? 0 : jc + 1), i += (jc == 0)) {
     const int s = k % kStages;
-    const int i = c / cpr, j0 = (c - i * cpr) * CW;
+    const int j0 = jc * CW;
     const int cw = min(CW, W - j0);
     if (i != cur_i) {  // new image row: resolve border rows and base pointers once
       cur_i = i;
@@ -281,14 +282,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       dstep = (pstep >> 1) * dC;
     }
     mbar_wait(&full_bar[s], (k / kStages) & 1, 42);
-    uint32_t sa = sbase + s * (kMaxStreams * kChunkBytes);
+    uint32_t sa = sbase + s * stage_bytes;
     for (int px = px0; px < cw; px += pstep, sa += kConsumers * 16, dptr += dstep) {
       const bool lean = px >= lo && px < hi;
       const int j = j0 + px;
       uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
       if (has0) r0 = lds128(sa);
-      if (has1) r1 = lds128(sa + kChunkBytes);
-      if (has2) r2 = lds128(sa + 2 * kChunkBytes);
+      if (has1) r1 = lds128(sa + chunk_bytes);
+      if (has2) r2 = lds128(sa + 2 * chunk_bytes);
       float y[8], d[8];
       if (MODE == RS_APPLY) {
         unpack8(r0, y);
@@ -365,10 +366,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
 
 template <int MODE>
 static void launch_row_stream(RowStreamParams& p, cudaStream_t st) {
-  p.CW = kChunkBytes / (p.C * 2);
+  p.ns = 0;
+  while (p.ns < kMaxStreams && p.s[p.ns].base != nullptr) ++p.ns;  // active streams are a prefix
+  p.CW = kPipeBytes / (kStages * p.ns) / (p.C * 2);
   if (p.CW > p.W) p.CW = p.W;
+  p.chunk_bytes = p.CW * p.C * 2;
   static bool attr_set = false;
-  const size_t smem = size_t(kStages) * kMaxStreams * kChunkBytes + 128;
+  const size_t smem = size_t(kPipeBytes) + 128;
   if (!attr_set) {
     cudaFuncSetAttribute(row_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     attr_set = true;
