@@ -116,6 +116,19 @@ int sggan_conv2d_fwd(const float* x, const float* kernel, const float* bias, flo
 /* ops.deconv2d (ops.py:30-34) / Conv2DTranspose(3, strides 2, 'same'): kernel (kh,kw,Cout,Cin). */
 int sggan_deconv2d_fwd(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W,
                        int Cin, int Cout, void* workspace, size_t workspace_bytes, void* stream);
+/* Gradients of the same two operators (what gen_tape / disc_tape.gradient compute, model.py:196-197), through the
+ * step's own dgrad / wgrad tensor-core kernels: dy [B,Ho,Wo,Cout] -> dx (shape of x), dw (shape of kernel), db [Cout]
+ * (db may be null).  sggan_conv2d_bwd_workspace(..., stride = -2, ...) sizes the transposed-convolution case. */
+size_t sggan_conv2d_bwd_workspace(int B, int H, int W, int Cin, int Cout, int k, int stride, int padding);
+int sggan_conv2d_bwd(const float* x, const float* kernel, const float* dy, float* dx, float* dw, float* db, int B, int H,
+                     int W, int Cin, int Cout, int k, int stride, int padding, void* workspace, size_t workspace_bytes,
+                     void* stream);
+int sggan_deconv2d_bwd(const float* x, const float* kernel, const float* dy, float* dx, float* dw, float* db, int B, int H,
+                       int W, int Cin, int Cout, void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of InstanceNormalization (+ activation): dz = gradient w.r.t. act(norm(x)); outputs dx, dgamma, dbeta. */
+int sggan_instance_norm_bwd(const float* x, const float* gamma, const float* beta, const float* dz, float* dx,
+                            float* dgamma, float* dbeta, int B, int H, int W, int C, float eps, int act, float alpha,
+                            void* workspace, size_t workspace_bytes, void* stream);
 /* ops.instance_norm (ops.py:13-22) / tfa InstanceNormalization, optionally fused activation
  * (0 none, 1 relu, 2 leaky(alpha), 3 tanh) and residual add.  C multiple of 64. */
 int sggan_instance_norm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y,

@@ -15,7 +15,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsggan_sm100.so")
+LIB_PATH = os.environ.get("SGGAN_LIB", os.path.join(_HERE, "libsggan_sm100.so"))  # SGGAN_LIB: A/B-test a variant build
 
 NET_G, NET_D = 0, 1
 LOSS_P2P, LOSS_SGGAN = 0, 1
@@ -67,6 +67,10 @@ SYMBOLS = {
     "sggan_conv2d_workspace": (_SZ, [_I] * 8),
     "sggan_conv2d_fwd": (_I, [_P, _P, _P, _P] + [_I] * 8 + [_P, _SZ, _P]),
     "sggan_deconv2d_fwd": (_I, [_P, _P, _P, _P] + [_I] * 5 + [_P, _SZ, _P]),
+    "sggan_conv2d_bwd_workspace": (_SZ, [_I] * 8),
+    "sggan_conv2d_bwd": (_I, [_P] * 6 + [_I] * 8 + [_P, _SZ, _P]),
+    "sggan_deconv2d_bwd": (_I, [_P] * 6 + [_I] * 5 + [_P, _SZ, _P]),
+    "sggan_instance_norm_bwd": (_I, [_P] * 7 + [_I] * 4 + [_F, _I, _F, _P, _SZ, _P]),
     "sggan_instance_norm_fwd": (_I, [_P] * 5 + [_I] * 4 + [_F, _I, _F, _P, _SZ, _P]),
     "sggan_lrelu": (_I, [_P, _P, _I64, _F, _P]),
     "sggan_mask_reduce": (_I, [_P, _P, _P] + [_I] * 6 + [_P]),

@@ -18,6 +18,8 @@ static thread_local std::string g_err;
 namespace sggan {
 int layer_geometry(Layer& l);
 int layer_prepare_fwd(Layer& l, const float* bias, void* out, const FrameMap& omap, int out_f32, bool dry);
+int layer_prepare_dgrad(Layer& l, int b0, int nimg, bool dry);
+int layer_prepare_wgrad(Layer& l, float* dW, int nimg, bool dry, float* part, size_t part_elems);
 }  // namespace sggan
 
 static Net& net_of(sggan_handle* h, int net) { return net == SGGAN_NET_G ? h->e.G : h->e.D; }
@@ -264,6 +266,122 @@ int sggan_deconv2d_fwd(const float* x, const float* kernel, const float* bias, f
   Layer l;
   if (conv_layer_for_op(l, B, H, W, Cin, Cout, 3, 2, 1, true)) { g_err = "unsupported deconv2d shape"; return SGGAN_E_INVALID; }
   return conv_op_run(l, x, kernel, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- backward of one convolution / transposed convolution through the step's own dgrad + wgrad kernels -------------
+static const size_t kOpPartElems = size_t(160) * 256 * 256;
+struct ConvBwdLayout { size_t wd, x, dy, dx, dxp, part, db, total; };
+static ConvBwdLayout conv_bwd_layout(const Layer& l) {
+  ConvBwdLayout o;
+  size_t off = 0;
+  o.wd = off; off = align256(off + size_t(l.packd.T) * l.packd.N * l.packd.K * 2);
+  o.x = off; off = align256(off + size_t(l.nb) * l.xmap.frame_pix * l.xmap.C * 2 + 4096);
+  o.dy = off; off = align256(off + size_t(l.nb) * l.dymap.frame_pix * l.dymap.C * 2 + 4096);
+  o.dx = off; off = align256(off + size_t(l.nb) * l.dxH * l.dxW * l.Cin * 2);
+  o.dxp = off; off = align256(off + size_t(l.nb) * l.Hin * l.Win * l.Cin * 2);
+  o.part = off; off = align256(off + kOpPartElems * 4);
+  o.total = off;
+  return o;
+}
+size_t sggan_conv2d_bwd_workspace(int B, int H, int W, int Cin, int Cout, int k, int stride, int padding) {
+  Layer l;
+  if (conv_layer_for_op(l, B, H, W, Cin, Cout, k, stride, padding, stride == -2)) return 0;
+  return conv_bwd_layout(l).total;
+}
+__global__ void colsum_kernel(const float* __restrict__ dy, int64_t rows, int C, float* db) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) s += dy[r * C + c];
+  atomicAdd(db + c, s);
+}
+static int conv_bwd_run(Layer& l, const float* x, const float* kernel, const float* dy, float* dx, float* dw, float* db,
+                        void* ws, size_t ws_bytes, cudaStream_t st) {
+  const ConvBwdLayout o = conv_bwd_layout(l);
+  if (!ws || ws_bytes < o.total) { g_err = "operator workspace too small"; return SGGAN_E_WORKSPACE; }
+  uint8_t* base = (uint8_t*)ws;
+  if (cudaMemsetAsync(ws, 0, o.total, st) != cudaSuccess) return SGGAN_E_CUDA;
+  l.Wd = (sg_bf16*)(base + o.wd); l.X = (sg_bf16*)(base + o.x); l.dY = (sg_bf16*)(base + o.dy); l.dX = base + o.dx;
+  sg_bf16* dxp = (sg_bf16*)(base + o.dxp);
+  PackParams pd = l.packd;
+  pd.src = kernel; pd.dst = l.Wd;
+  launch_pack_weights(pd, st);
+  launch_f32_to_frame(x, l.nb, l.Hin, l.Win, l.Cin, l.X, l.xmap, st);
+  launch_f32_to_frame(dy, l.nb, l.Hout, l.Wout, l.Cout, l.dY, l.dymap, st);
+  int r = layer_prepare_dgrad(l, 0, l.nb, false);
+  if (r) { g_err = "dgrad prepare failed " + std::to_string(r); return SGGAN_E_CUDA; }
+  const int64_t nw = int64_t(l.k) * l.k * l.Cin * l.Cout;
+  if (cudaMemsetAsync(dw, 0, nw * 4, st) != cudaSuccess) return SGGAN_E_CUDA;
+  r = layer_prepare_wgrad(l, dw, l.nb, false, (float*)(base + o.part), kOpPartElems);
+  if (r) { g_err = "wgrad prepare failed " + std::to_string(r); return SGGAN_E_CUDA; }
+  for (auto& L : l.dgrad)
+    if ((r = run_conv_gemm(L, st))) { g_err = "dgrad launch failed " + std::to_string(r); return SGGAN_E_CUDA; }
+  for (auto& L : l.wgrad) {
+    if ((r = run_wgrad_gemm(L, st))) { g_err = "wgrad launch failed " + std::to_string(r); return SGGAN_E_CUDA; }
+    if (L.p.part) launch_wgrad_reduce(L, int64_t(L.p.ntaps) * L.p.dw_tap_stride, st);
+  }
+  // dX: crop / fold the padded gradient back to the input grid, then widen to fp32
+  GradSrc g;
+  g.ptr = l.dX; g.f32 = 0; g.Hs = l.dxH; g.Ws = l.dxW; g.oy = l.dx_oy; g.ox = l.dx_ox; g.fold = l.dx_fold;
+  GradSrc none;
+  memset(&none, 0, sizeof(none));
+  launch_grad_gather(g, none, l.nb, l.Hin, l.Win, l.Cin, dxp, st);
+  launch_bf16_to_f32(dxp, dx, int64_t(l.nb) * l.Hin * l.Win * l.Cin, st);
+  if (db != nullptr) {
+    if (cudaMemsetAsync(db, 0, size_t(l.Cout) * 4, st) != cudaSuccess) return SGGAN_E_CUDA;
+    const int64_t rows = int64_t(l.nb) * l.Hout * l.Wout;
+    dim3 grid((l.Cout + 63) / 64, unsigned(rows < 256 ? rows : 256));
+    colsum_kernel<<<grid, 64, 0, st>>>(dy, rows, l.Cout, db);
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+int sggan_conv2d_bwd(const float* x, const float* kernel, const float* dy, float* dx, float* dw, float* db, int B, int H,
+                     int W, int Cin, int Cout, int k, int stride, int padding, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  Layer l;
+  if (conv_layer_for_op(l, B, H, W, Cin, Cout, k, stride, padding, false)) { g_err = "unsupported conv2d shape"; return SGGAN_E_INVALID; }
+  return conv_bwd_run(l, x, kernel, dy, dx, dw, db, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int sggan_deconv2d_bwd(const float* x, const float* kernel, const float* dy, float* dx, float* dw, float* db, int B, int H,
+                       int W, int Cin, int Cout, void* workspace, size_t workspace_bytes, void* stream) {
+  Layer l;
+  if (conv_layer_for_op(l, B, H, W, Cin, Cout, 3, 2, 1, true)) { g_err = "unsupported deconv2d shape"; return SGGAN_E_INVALID; }
+  return conv_bwd_run(l, x, kernel, dy, dx, dw, db, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// instance norm (+ activation) backward through the step's reduce / apply kernels
+int sggan_instance_norm_bwd(const float* x, const float* gamma, const float* beta, const float* dz, float* dx,
+                            float* dgamma, float* dbeta, int B, int H, int W, int C, float eps, int act, float alpha,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C % 64) { g_err = "C must be a multiple of 64"; return SGGAN_E_INVALID; }
+  const size_t n = size_t(B) * H * W * C;
+  const size_t need = align256(n * 2) * 3 + 2 * align256(size_t(B) * C * 8);
+  if (!workspace || workspace_bytes < need) { g_err = "operator workspace too small"; return SGGAN_E_WORKSPACE; }
+  uint8_t* base = (uint8_t*)workspace;
+  sg_bf16* xb = (sg_bf16*)base;
+  sg_bf16* gb = (sg_bf16*)(base + align256(n * 2));
+  sg_bf16* ob = (sg_bf16*)(base + 2 * align256(n * 2));
+  float* stats = (float*)(base + 3 * align256(n * 2));
+  float* sums = (float*)(base + 3 * align256(n * 2) + align256(size_t(B) * C * 8));
+  launch_f32_to_bf16(x, xb, n, st);
+  launch_f32_to_bf16(dz, gb, n, st);
+  if (cudaMemsetAsync(stats, 0, 2 * align256(size_t(B) * C * 8), st) != cudaSuccess) return SGGAN_E_CUDA;
+  launch_in_stats(xb, B, H * W, C, stats, st);
+  InBwdParams p;
+  memset(&p, 0, sizeof(p));
+  FrameMap pm;
+  memset(&pm, 0, sizeof(pm));
+  pm.frame_pix = int64_t(H) * W; pm.C = C; pm.H = H; pm.W = W; pm.P = W;
+  p.Y = xb; p.B = B; p.H = H; p.W = W; p.C = C; p.nb_act = B; p.act_wrap = 0; p.stats = stats; p.gamma = gamma; p.beta = beta;
+  p.eps = eps; p.act = act; p.act_alpha = alpha;
+  p.g1.ptr = gb; p.g1.f32 = 0; p.g1.Hs = H; p.g1.Ws = W;
+  p.sums = sums; p.dst = ob; p.dmap = pm;
+  launch_in_bwd_reduce(p, st);
+  launch_in_bwd_apply(p, st);
+  launch_in_param_grad(sums, B, C, dgamma, dbeta, st);
+  launch_bf16_to_f32(ob, dx, n, st);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
 
 int sggan_instance_norm_fwd(const float* x, const float* gamma, const float* beta, const float* residual, float* y,

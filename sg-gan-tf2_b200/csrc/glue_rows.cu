@@ -19,9 +19,15 @@
 
 namespace sggan {
 
-constexpr int kConsumers = 512;                 // 16 consumer warps
+#ifndef SG_CONSUMERS
+#define SG_CONSUMERS 512
+#endif
+#ifndef SG_STAGES
+#define SG_STAGES 4
+#endif
+constexpr int kConsumers = SG_CONSUMERS;         // consumer threads (16 warps)
 constexpr int kStreamThreads = kConsumers + 32;  // + 1 producer warp
-constexpr int kStages = 4;
+constexpr int kStages = SG_STAGES;
 constexpr int kPipeBytes = 196608;  // shared memory of the whole pipeline: kStages x streams x chunk
 constexpr int kMaxStreams = 3;
 

@@ -83,6 +83,46 @@ def deconv2d_raw(x, kernel, bias=None):
     return y
 
 
+def conv2d_bwd_raw(x, kernel, dy, stride=1, padding="SAME", transposed=False):
+    """Gradients (dx, dw, db) of conv2d_raw / deconv2d_raw w.r.t. input, kernel and bias for an upstream dy."""
+    x, dy = L.as_cuda_f32(x), L.as_cuda_f32(dy)
+    kernel = L.as_cuda_f32(kernel, x.device)
+    B, H, W, Cin = x.shape
+    k = kernel.shape[0]
+    Cout = kernel.shape[2] if transposed else kernel.shape[3]
+    pad = _PAD[padding.upper()]
+    nbytes = L.lib().sggan_conv2d_bwd_workspace(B, H, W, Cin, Cout, k, -2 if transposed else stride, pad)
+    if nbytes == 0:
+        raise L.SgganError("conv2d_bwd: unsupported shape")
+    dx = torch.empty_like(x)
+    dw = torch.empty(tuple(kernel.shape), dtype=torch.float32, device=x.device)
+    db = torch.empty(Cout, dtype=torch.float32, device=x.device)
+    ws = _workspace(nbytes, x.device)
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    if transposed:
+        L.check(L.lib().sggan_deconv2d_bwd(P(x), P(kernel), P(dy), P(dx), P(dw), P(db), B, H, W, Cin, Cout, P(ws), ws.numel(),
+                                           L.stream_ptr()))
+    else:
+        L.check(L.lib().sggan_conv2d_bwd(P(x), P(kernel), P(dy), P(dx), P(dw), P(db), B, H, W, Cin, Cout, k, stride, pad, P(ws),
+                                         ws.numel(), L.stream_ptr()))
+    return dx, dw, db
+
+
+def instance_norm_bwd_raw(x, gamma, beta, dz, eps=1e-3, act=None, alpha=0.3):
+    """Gradients (dx, dgamma, dbeta) of act(instance_norm(x)) for an upstream dz."""
+    x, dz = L.as_cuda_f32(x), L.as_cuda_f32(dz)
+    B, H, W, Cc = x.shape
+    gamma, beta = L.as_cuda_f32(gamma, x.device), L.as_cuda_f32(beta, x.device)
+    dx = torch.empty_like(x)
+    dg = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    dbt = torch.empty(Cc, dtype=torch.float32, device=x.device)
+    ws = _workspace(x.numel() * 6 + 2 * B * Cc * 8 + 8192, x.device)
+    P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    L.check(L.lib().sggan_instance_norm_bwd(P(x), P(gamma), P(beta), P(dz), P(dx), P(dg), P(dbt), B, H, W, Cc, eps, _ACT[act],
+                                            alpha, P(ws), ws.numel(), L.stream_ptr()))
+    return dx, dg, dbt
+
+
 def instance_norm_raw(x, gamma, beta, eps=1e-3, act=None, alpha=0.3, residual=None):
     x = L.as_cuda_f32(x)
     B, H, W, Cc = x.shape

@@ -67,6 +67,51 @@ def test_deconv2d(ops, O, B, H, W, Cin, Cout):
     assert rel(y, ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride,pad", [
+    (2, 16, 24, 128, 128, 3, 1, "REFLECT"), (1, 20, 36, 128, 256, 3, 1, "SAME"), (2, 9, 13, 256, 128, 3, 1, "VALID"),
+    (2, 16, 32, 64, 128, 3, 2, "SAME"), (1, 15, 31, 128, 128, 3, 2, "VALID"), (1, 32, 64, 256, 256, 3, 2, "VALID"),
+    (1, 64, 128, 256, 256, 3, 1, "REFLECT"), (1, 12, 20, 128, 64, 7, 1, "REFLECT"),
+])
+def test_conv2d_backward(ops, O, B, H, W, Cin, Cout, k, stride, pad):
+    """dgrad + wgrad tensor-core kernels (and the reflect-border fold) against autograd of the oracle conv."""
+    g = torch.Generator().manual_seed(B * 77 + H + Cout + k)
+    x = (torch.rand(B, H, W, Cin, generator=g) * 2 - 1).bfloat16().float().requires_grad_(True)
+    w = ((torch.rand(k, k, Cin, Cout, generator=g) * 2 - 1) * (1.0 / (k * k * Cin) ** 0.5)).bfloat16().float().requires_grad_(True)
+    xr = O.reflect_pad(x, (k - 1) // 2) if pad == "REFLECT" else x
+    y = O.conv2d(xr, w, None, stride, "VALID" if pad == "REFLECT" else pad)
+    dy = (torch.rand(y.shape, generator=g) * 2 - 1).bfloat16().float()
+    gx, gw = torch.autograd.grad(y, (x, w), dy)
+    dx, dw, db = ops.conv2d_bwd_raw(x.detach(), w.detach(), dy, stride=stride, padding=pad)
+    assert rel(dx, gx) < 1e-2 and rel(dw, gw) < 5e-3
+    assert rel(db, dy.sum(dim=(0, 1, 2))) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 12, 128, 64), (2, 16, 32, 256, 128)])
+def test_deconv2d_backward(ops, O, B, H, W, Cin, Cout):
+    g = torch.Generator().manual_seed(5 + W)
+    x = (torch.rand(B, H, W, Cin, generator=g) * 2 - 1).bfloat16().float().requires_grad_(True)
+    w = ((torch.rand(3, 3, Cout, Cin, generator=g) * 2 - 1) * (1.0 / (9 * Cin) ** 0.5)).bfloat16().float().requires_grad_(True)
+    y = O.conv2d_transpose(x, w, None, 2)
+    dy = (torch.rand(y.shape, generator=g) * 2 - 1).bfloat16().float()
+    gx, gw = torch.autograd.grad(y, (x, w), dy)
+    dx, dw, db = ops.conv2d_bwd_raw(x.detach(), w.detach(), dy, transposed=True)
+    assert rel(dx, gx) < 1e-2 and rel(dw, gw) < 5e-3
+
+
+@pytest.mark.parametrize("act", [None, "relu", "lrelu"])
+def test_instance_norm_backward(ops, O, act):
+    g = torch.Generator().manual_seed(21)
+    x = (torch.randn(2, 12, 20, 128, generator=g) * 2 + 0.5).bfloat16().float().requires_grad_(True)
+    gam = (torch.rand(128, generator=g) + 0.5).requires_grad_(True)
+    bet = (torch.rand(128, generator=g) - 0.5).requires_grad_(True)
+    z = O.instance_norm(x, gam, bet, 1e-3)
+    z = torch.relu(z) if act == "relu" else (O.lrelu(z, 0.3) if act == "lrelu" else z)
+    dz = torch.randn(z.shape, generator=g).bfloat16().float()
+    gx, gg, gb = torch.autograd.grad(z, (x, gam, bet), dz)
+    dx, dg, dbt = ops.instance_norm_bwd_raw(x.detach(), gam.detach(), bet.detach(), dz, eps=1e-3, act=act, alpha=0.3)
+    assert rel(dx, gx) < 1e-2 and rel(dg, gg) < 2e-3 and rel(dbt, gb) < 2e-3
+
+
 def test_unsupported_shapes_fail_loudly(ops, L):
     x = torch.rand(1, 8, 8, 48)
     with pytest.raises(L.SgganError):
