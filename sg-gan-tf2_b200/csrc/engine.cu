@@ -612,7 +612,7 @@ int Engine::upload_pack_jobs(int net) {
   int blocks = 0;
   auto add = [&](PackParams q) {
     starts.push_back(blocks);
-    blocks += int((int64_t(q.T) * q.N * q.K + 255) / 256);
+    blocks += int((((int64_t(q.T) * q.N * q.K) >> 3) + 255) / 256);  // 8 elements per thread
     jobs.push_back(q);
   };
   for (auto& l : n.L) {

@@ -609,10 +609,7 @@ void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float 
 //  mode 5 window dgrad (generator output conv):  t=kh        n=ci  k=q*8+co, kw=KW-1-q
 //  mode 6 window fwd, stride 2 (disc. h0):       t=kh*2+bp   n=co  k=q*8+ci, kw=2q+bp
 //  mode 7 shift-sum fwd (generator output conv): t=kh        n=kw*4+co  k=ci
-__device__ __forceinline__ void pack_one(const PackParams& p, int64_t idx) {
-  const int64_t tot = int64_t(p.T) * p.N * p.K;
-  if (idx >= tot) return;
-  const int k = int(idx % p.K), n = int((idx / p.K) % p.N), t = int(idx / (int64_t(p.K) * p.N));
+__device__ __forceinline__ float pack_value(const PackParams& p, int t, int n, int k) {
   float v = 0.f;
   const int Ci = p.Cin, Co = p.Cout;
   switch (p.mode) {
@@ -629,7 +626,22 @@ __device__ __forceinline__ void pack_one(const PackParams& p, int64_t idx) {
     case 6: { const int kh = t >> 1, bp = t & 1, q = k >> 3, ci = k & 7, kw = 2 * q + bp;
       if (kw < p.KW && ci < Ci && n < Co) v = p.src[((int64_t(kh) * p.KW + kw) * Ci + ci) * Co + n]; break; }
   }
-  reinterpret_cast<__nv_bfloat16*>(p.dst)[idx] = __float2bfloat16_rn(v);
+  return v;
+}
+// one thread packs 8 consecutive k (K is a multiple of 64) and writes them with one 128-bit store
+__device__ __forceinline__ void pack_one(const PackParams& p, int64_t idx8) {
+  const int64_t tot8 = (int64_t(p.T) * p.N * p.K) >> 3;
+  if (idx8 >= tot8) return;
+  const int K8 = p.K >> 3;
+  const int k0 = int(idx8 % K8) * 8;
+  const int64_t tn = idx8 / K8;
+  const int n = int(tn % p.N), t = int(tn / p.N);
+  uint4 w;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&w);
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    h[e] = __floats2bfloat162_rn(pack_value(p, t, n, k0 + 2 * e), pack_value(p, t, n, k0 + 2 * e + 1));
+  reinterpret_cast<uint4*>(p.dst)[idx8] = w;
 }
 __global__ void pack_weights_kernel(const PackParams p) { pack_one(p, int64_t(blockIdx.x) * blockDim.x + threadIdx.x); }
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackParams* __restrict__ jobs,
@@ -646,14 +658,14 @@ __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackParam
     sp = jobs[lo];
   }
   __syncthreads();
-  pack_one(sp, int64_t(int(blockIdx.x) - starts[sj]) * 256 + threadIdx.x);
+  pack_one(sp, int64_t(int(blockIdx.x) - starts[sj]) * 256 + threadIdx.x);  // 256 threads x 8 elements per block
 }
 void launch_pack_weights_batch(const PackParams* jobs, const int* starts, int njobs, int total_blocks, cudaStream_t st) {
   pack_weights_batch_kernel<<<total_blocks, 256, 0, st>>>(jobs, starts, njobs);
 }
 void launch_pack_weights(const PackParams& p, cudaStream_t st) {
-  const int64_t tot = int64_t(p.T) * p.N * p.K;
-  pack_weights_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(p);
+  const int64_t tot8 = (int64_t(p.T) * p.N * p.K) >> 3;
+  pack_weights_kernel<<<unsigned((tot8 + 255) / 256), 256, 0, st>>>(p);
 }
 
 // scratch [pair][128 rows][ncol] from the window wgrad launches -> Keras [KH][KW][Cin][Cout] (+=)

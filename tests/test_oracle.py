@@ -148,13 +148,14 @@ def test_networks_and_step(O, golden):
 
 def test_discriminator_broadcast_128(O):
     # the reference-consistent case: 128x128 -> 1x1 logits against the loader's 4x4 mask
+    torch.manual_seed(3)
     dw = O.init_weights(O.discriminator_spec(segment_class=3), 2, randomize_affine=True)
     x = torch.rand(2, 128, 128, 3)
     mask = (torch.rand(2, 4, 4, 3) > 0.5).float()
     out = O.discriminator(x, mask, dw)
     assert tuple(out.shape) == (2, 4, 4, 1)
     out2 = O.discriminator(torch.rand(2, 128, 128, 3), mask, dw)
-    assert torch.allclose(out, out2)  # h33 has H*W == 1: the output does not depend on the image
+    assert torch.allclose(out, out2, atol=1e-6)  # h33 has H*W == 1: the output does not depend on the image
 
 
 def test_mask_construction_integer(O, golden):
