@@ -28,6 +28,7 @@
 #include "tmap.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <utility>
 #include <vector>
 
@@ -42,7 +43,8 @@ constexpr int kSmemBudget = 200 * 1024;  // pipeline bytes (leaves room for alig
 constexpr int kEpiWarps = 8;                           // two warps per TMEM lane quarter (16 measured no faster:
                                                        // the epilogue is bound by TMEM / smem / store traffic)
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kConvThreads = 96 + kEpiThreads;  // 3 control warps + epilogue warps
+constexpr int kStatThreads = 128;                      // statistics + bulk-store warps of the staged epilogue
+constexpr int kConvThreads = 96 + kEpiThreads + kStatThreads;  // 3 control warps + epilogue warps + statistics warps
 constexpr int kWgradThreads = 192;
 
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
@@ -63,13 +65,49 @@ static inline uint32_t tmem_cols_for(int n) {
   return c;
 }
 
+// Column sums (sum, sum of squares) of a staged bf16 tile S[128][BN] (row pitch `pitch` bytes) by `nthr`
+// threads (tid in [0, nthr)); each thread owns a column pair over 128 / parts rows, the parts are added in
+// a fixed order through `comb` ([parts][BN], synchronised on named barrier `bar_id`).  gst -> [BN] float2.
+__device__ __forceinline__ void staged_stats(const uint8_t* S, int pitch, int BN, int nthr, int tid, float2* comb,
+                                             int bar_id, float2* gst) {
+  const int pw = pitch >> 2, cpairs = BN >> 1;
+  const int parts = nthr / cpairs, rows_per = kTileM / parts;
+  const int cp = tid % cpairs, part = tid / cpairs;
+  const uint32_t* col = reinterpret_cast<const uint32_t*>(S + part * rows_per * pitch) + cp;
+  float s1l = 0.f, s2l = 0.f, s1h = 0.f, s2h = 0.f, t1l = 0.f, t2l = 0.f, t1h = 0.f, t2h = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < rows_per; r += 2) {
+    const uint32_t w0 = col[r * pw], w1 = col[(r + 1) * pw];
+    const float x0 = __uint_as_float(w0 << 16), y0 = __uint_as_float(w0 & 0xffff0000u);
+    const float x1 = __uint_as_float(w1 << 16), y1 = __uint_as_float(w1 & 0xffff0000u);
+    s1l += x0; s2l += x0 * x0; s1h += y0; s2h += y0 * y0;
+    t1l += x1; t2l += x1 * x1; t1h += y1; t2h += y1 * y1;
+  }
+  if (parts == 1) {
+    gst[2 * cp] = make_float2(s1l + t1l, s2l + t2l);
+    gst[2 * cp + 1] = make_float2(s1h + t1h, s2h + t2h);
+  } else {
+    comb[part * BN + 2 * cp] = make_float2(s1l + t1l, s2l + t2l);
+    comb[part * BN + 2 * cp + 1] = make_float2(s1h + t1h, s2h + t2h);
+    named_bar_sync(bar_id, nthr);
+    if (tid < BN) {
+      float2 acc = comb[tid];
+      for (int pp = 1; pp < parts; ++pp) {
+        const float2 o = comb[pp * BN + tid];
+        acc.x += o.x; acc.y += o.y;
+      }
+      gst[tid] = acc;
+    }
+  }
+}
+
 // =============================================================================================
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA8,
                     const __grid_constant__ CUtensorMap tmB, const ConvGemmParams p, const int sa_stages,
                     const int sb_stages, const uint32_t tmem_cols) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
   __shared__ uint64_t a_full[kMaxStages], a_empty[kMaxStages], b_full[kMaxStages], b_empty[kMaxStages];
   __shared__ uint64_t acc_bar;
   __shared__ uint32_t tmem_base_sh;
@@ -86,6 +124,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int m0 = blockIdx.x * mstep, n0 = blockIdx.y * BN, b = blockIdx.z;
   const int cchunks = p.Cin / kChunkK;
   const int agroups = p.nruns * cchunks;  // A tiles this CTA consumes
+  // staged epilogue (see below): bf16 output and a full tile of channels
+  const bool staged = p.shift_kw == 0 && !p.out_f32 && (p.omap.C & 7) == 0 && n0 + BN <= p.Cout;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < sa_stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -165,6 +205,41 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       umma_commit(&acc_bar);  // accumulators complete
       if (dbg) dbg[2] = clock64();
     }
+  } else if (warp >= 3 + kEpiWarps) {
+    // ------------------------------------------------------------ statistics + store warps (staged epilogue)
+    // While the epilogue warps drain the NEXT accumulator out of TMEM, these four warps finish the tile
+    // that was just staged in shared memory: one bulk async copy per valid output position, and the
+    // column sums for the instance-norm statistics (the epilogue warps finish the last tile themselves).
+    if (staged) {
+      const int t = threadIdx.x - (96 + kEpiThreads);  // 0 .. 127
+      const int pitch = BN * 2 + 16;
+      uint8_t* aux = smem + NA * kTileM * pitch;
+      float2* comb0 = reinterpret_cast<float2*>(aux);                     // 2 KB: partial sums of these warps
+      const long long* rowoff = reinterpret_cast<const long long*>(aux + 6144);  // [NA][128] output offsets
+      // all but the last accumulator: the epilogue warps finish the last one themselves
+      for (int a = 0; a + 1 < NA; ++a) {
+        named_bar_sync(2 + a, kEpiThreads + kStatThreads);
+        const uint8_t* S = smem + a * kTileM * pitch;
+#ifndef SG_EXP_NOSTORE
+        {
+          const long long off = rowoff[a * kTileM + t];
+          if (off >= 0) {
+            bulk_store_1d(reinterpret_cast<__nv_bfloat16*>(p.out) + off, S + t * pitch, uint32_t(BN * 2));
+            bulk_commit_group();
+          }
+        }
+#endif
+#ifndef SG_EXP_NOSTATS
+        if (p.stats != nullptr) {
+          const int tile = p.stats_t0 + blockIdx.x * NA + a;
+          staged_stats(S, pitch, BN, kStatThreads, t, comb0, 4,
+                       reinterpret_cast<float2*>(p.stats) + (int64_t(b) * p.stats_T + tile) * p.Cout + n0);
+        }
+#endif
+      }
+      bulk_wait_group_read0();  // shared memory must outlive the reads of the copies
+      if (dbg && t == 0) dbg[7] = clock64();
+    }
   } else {
     // ------------------------------------------------------------ epilogue (kEpiWarps warps)
     // The warps that share a TMEM lane quarter split the 32-column chunks between them, so every
@@ -208,6 +283,80 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+    } else if (staged) {
+      // ---- staged epilogue (bf16 output, full channel tile): the tile is written row-major into shared
+      // memory (the pipeline buffers are idle by now).  Every valid output position then leaves as ONE
+      // bulk async copy of BN * 2 bytes, and the statistics are column sums of the staged bf16 values.  All
+      // but the last accumulator are handed to the statistics warps, so that work overlaps the TMEM drain
+      // of the next accumulator.  No strided global stores, no fp32 transposition tile.
+      const int pitch = BN * 2 + 16;  // bytes; +16 keeps the 16-byte row writes of a quarter warp on distinct banks
+      uint8_t* aux = smem + NA * kTileM * pitch;  // 2 KB + 4 KB partial sums, 2 KB output offsets
+      long long* rowoff = reinterpret_cast<long long*>(aux + 6144);
+      for (int a = 0; a < NA; ++a) {
+        uint8_t* S = smem + a * kTileM * pitch;
+        const int m = m0 + a * kTileM + row;
+        const int i = m / p.P, j = m - i * p.P;
+        const int oi = i * p.o_scale + p.o_a, oj = j * p.o_scale + p.o_b;
+        const bool valid = (m < p.M) && (i < p.Hv) && (j < p.Wv) && (oi < p.omap.H) && (oj < p.omap.W);
+        for (int c0 = half * 32; c0 < BN; c0 += 32 * (kEpiWarps / 4)) {
+          float v[32];
+          tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(a * BN + c0), v);
+          const float4* sb4 = reinterpret_cast<const float4*>(sbias + c0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bb = sb4[g];
+            v[4 * g] += bb.x; v[4 * g + 1] += bb.y; v[4 * g + 2] += bb.z; v[4 * g + 3] += bb.w;
+          }
+          if (act == SG_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+          } else if (act == SG_ACT_LRELU) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], alpha * v[e]);
+          } else if (act == SG_ACT_TANH) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = tanhf(v[e]);
+          }
+          uint4* srow = reinterpret_cast<uint4*>(S + row * pitch + c0 * 2);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            w.x = valid ? pack_bf16x2(v[8 * g], v[8 * g + 1]) : 0u;  // rows outside the image count as zeros
+            w.y = valid ? pack_bf16x2(v[8 * g + 2], v[8 * g + 3]) : 0u;
+            w.z = valid ? pack_bf16x2(v[8 * g + 4], v[8 * g + 5]) : 0u;
+            w.w = valid ? pack_bf16x2(v[8 * g + 6], v[8 * g + 7]) : 0u;
+            srow[g] = w;
+          }
+        }
+        if (half == 0) {
+          const int64_t obase = (int64_t(b) * p.omap.frame_pix + (valid ? frame_pixel(p.omap, oi, oj) : 0)) * p.omap.C;
+          rowoff[a * kTileM + row] = valid ? obase + n0 : -1;
+        }
+        fence_proxy_async_smem();  // bulk copies (async proxy) read what this thread just wrote
+        if (a + 1 < NA) named_bar_arrive(2 + a, kEpiThreads + kStatThreads);  // hand over; go on with the next accumulator
+        if (dbg && et == 0) dbg[4 + a] = clock64();
+      }
+      named_bar_sync(1, kEpiThreads);  // the last tile is completely staged
+#ifndef SG_EXP_NOSTORE
+      if (half == 0) {
+        const long long off = rowoff[(NA - 1) * kTileM + row];
+        if (off >= 0) {
+          bulk_store_1d(reinterpret_cast<__nv_bfloat16*>(p.out) + off, smem + ((NA - 1) * kTileM + row) * pitch,
+                        uint32_t(BN * 2));
+          bulk_commit_group();
+        }
+      }
+#endif
+#ifndef SG_EXP_NOSTATS
+      if (has_stats) {
+        const int tile = p.stats_t0 + blockIdx.x * NA + (NA - 1);
+        staged_stats(smem + (NA - 1) * kTileM * pitch, pitch, BN, kEpiThreads, et,
+                     reinterpret_cast<float2*>(aux + 2048), 1,
+                     reinterpret_cast<float2*>(p.stats) + (int64_t(b) * p.stats_T + tile) * p.Cout + n0);
+      }
+#endif
+      bulk_wait_group_read0();
+      tc_fence_before();
     } else
     for (int a = 0; a < NA; ++a) {
       const int m = m0 + a * kTileM + row;
@@ -248,11 +397,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             v[2 * e2 + 1] = __uint_as_float(pk[e2] & 0xffff0000u);
           }
         }
+#ifndef SG_EXP_NOSTATS
         if (has_stats) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) tsm[(c0 + e) * 129 + row] = v[e] * msk;
         }
+#endif
+#ifdef SG_EXP_NOSTORE
+        if (valid && pk[0] == 0x12345678u) {
+#else
         if (valid) {
+#endif
           if (vec_ok && nb + 32 <= p.Cout) {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + nb);
 #pragma unroll
@@ -270,6 +425,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
+#ifndef SG_EXP_NOSTATS
       if (has_stats) {
         named_bar_sync(1, kEpiThreads);
         for (int c = et; c < BN; c += kEpiThreads) {
@@ -289,6 +445,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (a + 1 < NA) named_bar_sync(1, kEpiThreads);  // tsm is rewritten by the next accumulator
       }
+#endif
       if (dbg && et == 0) dbg[4 + a] = clock64();
     }
     tc_fence_before();
@@ -302,11 +459,261 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // =============================================================================================
+// CTA-pair variant for the 256-channel layers (the residual blocks: 80 % of the step's FLOPs).
+//
+// A cluster of two CTAs runs tcgen05.mma.cta_group::2 with M = 256 (128 output positions per CTA, any
+// two 128-row tiles of the batch), N = 256: each CTA stages only HALF of every weight tile (its 128 of
+// the 256 output channels), so the weight stream per SM -- what bounds the single-CTA kernel in L2 --
+// halves without needing a second accumulator.  That frees TMEM for DOUBLE BUFFERING (2 x 256 columns):
+// the kernel is persistent, and the epilogue of tile k (TMEM -> bias/act/statistics -> bf16 stores,
+// ~9k cycles) runs while the MMAs of tile k + 1 are issued.  The single-CTA kernel spends ~29 % of its
+// time in that epilogue with the tensor pipe idle.
+//
+// Barriers: a_full / b_full live in the leader CTA (rank 0) and count the TMA bytes of BOTH CTAs;
+// a_empty / b_empty / acc_full exist in both CTAs and are signalled by multicast tcgen05.commit;
+// acc_empty lives in the leader and collects one arrival per epilogue warp of both CTAs.
+constexpr int kPairEpiTile = 32 * 33 * 4;                       // one warp's transposition tile
+constexpr int kPairEpiBytes = kEpiWarps * kPairEpiTile + 2 * 4 * 256 * 8;  // + red[2][4][256] float2
+constexpr int kPairAStages = 3, kPairBStages = 7;
+constexpr int kPairAStage = (kTileM + kHaloRows) * 128, kPairBStage = 128 * 128;
+constexpr int kPairSmem = kPairAStages * kPairAStage + kPairBStages * kPairBStage + kPairEpiBytes + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA8,
+                      const __grid_constant__ CUtensorMap tmBh, const ConvGemmParams p, const int T128,
+                      const int npairs) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
+  __shared__ uint64_t a_full[kPairAStages], a_empty[kPairAStages], b_full[kPairBStages], b_empty[kPairBStages];
+  __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ __align__(16) float sbias[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
+  uint8_t* smA = smem;
+  uint8_t* smB = smem + kPairAStages * kPairAStage;
+  float* epi = reinterpret_cast<float*>(smB + kPairBStages * kPairBStage);
+  const int cchunks = p.Cin / kChunkK;
+  const int total_tiles = p.B * T128;
+  // debug stamps, 16 per CTA: [0] start, [1] set-up done, [2+k] MMAs of tile k issued (leader),
+  // [8+k] epilogue of tile k done, [15] end
+  long long* dbg = p.dbg ? p.dbg + int64_t(blockIdx.x) * 16 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kPairAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kPairBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA8);
+    tma_prefetch_desc(&tmBh);
+  }
+  if (warp == 1) tmem_alloc_pair(&tmem_base_sh, 512);
+  for (int t = threadIdx.x; t < 256; t += kConvThreads)
+    sbias[t] = (p.bias != nullptr && t < p.Cout) ? __ldg(p.bias + t) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_sh;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ A producer (both CTAs: own 128 rows)
+    if (lane == 0) {
+      int g = 0;
+      for (int j = cl; j < npairs; j += ncl) {
+        const int gt = 2 * j + int(rank);
+        const int gtc = gt < total_tiles ? gt : 0;
+        const int b = gtc / T128, m0 = (gtc - b * T128) * kTileM;
+        for (int r = 0; r < p.nruns; ++r)
+          for (int cc = 0; cc < cchunks; ++cc, ++g) {
+            const int s = g % kPairAStages;
+            mbar_wait(&a_empty[s], ((g / kPairAStages) & 1) ^ 1, 1);
+            uint8_t* sa = smA + s * kPairAStage;
+            const int row0 = m0 + p.run_off[r];
+            if (rank == 0) mbar_arrive_expect_tx(&a_full[s], 2 * kPairAStage);
+            const uint32_t bar = mapa_u32(smem_u32(&a_full[s]), 0);
+            tma_load_3d_pair(&tmA, bar, sa, cc * kChunkK, row0, b);
+            tma_load_3d_pair(&tmA8, bar, sa + kABytes, cc * kChunkK, row0 + kTileM, b);
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ B producer (both CTAs: own 128 channels)
+    if (lane == 0) {
+      int it = 0;
+      for (int j = cl; j < npairs; j += ncl)
+        for (int r = 0, t0 = 0; r < p.nruns; t0 += p.run_len[r], ++r)
+          for (int cc = 0; cc < cchunks; ++cc)
+            for (int q = 0; q < p.run_len[r]; ++q, ++it) {
+              const int s = it % kPairBStages;
+              mbar_wait(&b_empty[s], ((it / kPairBStages) & 1) ^ 1, 4);
+              if (rank == 0) mbar_arrive_expect_tx(&b_full[s], 2 * kPairBStage);
+              tma_load_2d_pair(&tmBh, mapa_u32(smem_u32(&b_full[s]), 0), smB + s * kPairBStage, cc * kChunkK,
+                               int(p.run_w[t0 + q]) * p.CoutPad + int(rank) * 128);
+            }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = idesc_bf16_f32(256, 256, 0, 0);
+      int it = 0, g = 0, k = 0;
+      for (int j = cl; j < npairs; j += ncl, ++k) {
+        const int buf = k & 1;
+        mbar_wait(&acc_empty[buf], ((k >> 1) & 1) ^ 1, 6);  // both CTAs drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_acc + uint32_t(buf * 256);
+        uint32_t acc = 0;
+        for (int r = 0; r < p.nruns; ++r)
+          for (int cc = 0; cc < cchunks; ++cc, ++g) {
+            const int sa_i = g % kPairAStages;
+            mbar_wait(&a_full[sa_i], (g / kPairAStages) & 1, 2);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smA + sa_i * kPairAStage);
+            for (int q = 0; q < p.run_len[r]; ++q, ++it) {
+              const int sb_i = it % kPairBStages;
+              mbar_wait(&b_full[sb_i], (it / kPairBStages) & 1, 5);
+              tc_fence_after();
+              const uint64_t bdesc = desc_kmajor_sw128(smem_u32(smB + sb_i * kPairBStage));
+              const uint64_t adesc = desc_kmajor_sw128(a_base + uint32_t(q) * 128u);
+#pragma unroll
+              for (int kk = 0; kk < kChunkK / 16; ++kk) {
+                umma_bf16_pair(d, adesc + uint64_t(kk * 2), bdesc + uint64_t(kk * 2), idesc, acc);
+                acc = 1;
+              }
+              umma_commit_pair(&b_empty[sb_i]);
+            }
+            umma_commit_pair(&a_empty[sa_i]);
+          }
+        umma_commit_pair(&acc_full[buf]);
+        if (dbg && k < 6) dbg[2 + k] = clock64();
+      }
+    }
+  } else if (warp < 3 + kEpiWarps) {
+    // ------------------------------------------------------------ epilogue (both CTAs: own 128 x 256 tile)
+    const int q = warp & 3;
+    const int half = (warp - 3) >> 2;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 96;
+    float* tsw = epi + (warp - 3) * (32 * 33);
+    float2* red = reinterpret_cast<float2*>(epi + kEpiWarps * 32 * 33);  // [2][4][256]
+    const bool has_stats = p.stats != nullptr;
+    const int act = p.act;
+    const float alpha = p.act_alpha;
+    const bool vec_ok = (!p.out_f32) && ((p.omap.C & 7) == 0);
+    const uint32_t empty_addr0 = mapa_u32(smem_u32(&acc_empty[0]), 0), empty_addr1 = mapa_u32(smem_u32(&acc_empty[1]), 0);
+    int k = 0;
+    for (int j = cl; j < npairs; j += ncl, ++k) {
+      const int buf = k & 1;
+      const int gt = 2 * j + int(rank);
+      const bool tile_ok = gt < total_tiles;
+      const int gtc = tile_ok ? gt : 0;
+      const int b = gtc / T128, t128 = gtc - b * T128;
+      const int m = t128 * kTileM + row;
+      const int i = m / p.P, jj = m - i * p.P;
+      const int oi = i * p.o_scale + p.o_a, oj = jj * p.o_scale + p.o_b;
+      const bool valid = tile_ok && (m < p.M) && (i < p.Hv) && (jj < p.Wv) && (oi < p.omap.H) && (oj < p.omap.W);
+      const int64_t obase = (int64_t(b) * p.omap.frame_pix + (valid ? frame_pixel(p.omap, oi, oj) : 0)) * p.omap.C;
+      const float msk = valid ? 1.f : 0.f;
+      mbar_wait(&acc_full[buf], (k >> 1) & 1, 3);
+      tc_fence_after();
+      for (int c0 = half * 32; c0 < 256; c0 += 32 * (kEpiWarps / 4)) {
+        float v[32];
+        tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(buf * 256 + c0), v);
+        const float4* sb4 = reinterpret_cast<const float4*>(sbias + c0);
+#pragma unroll
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const float4 bb = sb4[g4];
+          v[4 * g4] += bb.x; v[4 * g4 + 1] += bb.y; v[4 * g4 + 2] += bb.z; v[4 * g4 + 3] += bb.w;
+        }
+        if (act == SG_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+        } else if (act == SG_ACT_LRELU) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], alpha * v[e]);
+        } else if (act == SG_ACT_TANH) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = tanhf(v[e]);
+        }
+        uint32_t pk[16];
+        if (!p.out_f32) {
+#pragma unroll
+          for (int e2 = 0; e2 < 16; ++e2) {
+            pk[e2] = pack_bf16x2(v[2 * e2], v[2 * e2 + 1]);
+            v[2 * e2] = __uint_as_float(pk[e2] << 16);
+            v[2 * e2 + 1] = __uint_as_float(pk[e2] & 0xffff0000u);
+          }
+        }
+        if (valid) {
+          if (vec_ok && c0 + 32 <= p.Cout) {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + c0);
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) dst[g4] = make_uint4(pk[4 * g4], pk[4 * g4 + 1], pk[4 * g4 + 2], pk[4 * g4 + 3]);
+          } else if (p.out_f32) {
+            float* dst = reinterpret_cast<float*>(p.out) + obase;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c0 + e < p.Cout) dst[c0 + e] = v[e];
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + obase;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c0 + e < p.Cout) dst[c0 + e] = __float2bfloat16_rn(v[e]);
+          }
+        }
+        if (has_stats) {
+          // column sums over this warp's 32 rows through a private transposition tile (pitch 33: no conflicts)
+#pragma unroll
+          for (int e = 0; e < 32; ++e) tsw[e * 33 + lane] = v[e] * msk;
+          __syncwarp();
+          float s1 = 0.f, s2 = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; r += 2) {
+            const float x = tsw[lane * 33 + r], y = tsw[lane * 33 + r + 1];
+            s1 += x; s2 += x * x;
+            s1b += y; s2b += y * y;
+          }
+          red[(buf * 4 + q) * 256 + c0 + lane] = make_float2(s1 + s1b, s2 + s2b);
+          __syncwarp();
+        }
+      }
+      // this warp's share of the accumulator has been read: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0);
+      if (has_stats) {
+        named_bar_sync(1, kEpiThreads);  // also orders the re-use of red[buf] two tiles later
+        if (tile_ok && et < p.Cout) {
+          const float2 r0 = red[(buf * 4 + 0) * 256 + et], r1 = red[(buf * 4 + 1) * 256 + et];
+          const float2 r2 = red[(buf * 4 + 2) * 256 + et], r3 = red[(buf * 4 + 3) * 256 + et];
+          float2* dst = reinterpret_cast<float2*>(p.stats) + (int64_t(b) * p.stats_T + p.stats_t0 + t128) * p.Cout + et;
+          *dst = make_float2((r0.x + r1.x) + (r2.x + r3.x), (r0.y + r1.y) + (r2.y + r3.y));
+        }
+      }
+      if (dbg && et == 0 && k < 6) dbg[8 + k] = clock64();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be reading this CTA's smem / signalling its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_acc, 512);
+  }
+  if (dbg && threadIdx.x == 0) dbg[15] = clock64();
+}
+
+// =============================================================================================
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                      const WgradParams p, const int stages, const uint32_t tmem_cols, const int NA) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
   __shared__ uint64_t acc_bar;
@@ -483,6 +890,10 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
   L->tmem_cols = tmem_cols_for((p.MT / 128) * p.BN);
   L->smem = size_t(sa) * a_stage + size_t(sb) * b_stage + 1024;
   if (L->smem < size_t(p.BN) * 129 * 4 + 1024) L->smem = size_t(p.BN) * 129 * 4 + 1024;  // epilogue statistics tile
+  {
+    const size_t staged = size_t(p.MT) * (p.BN * 2 + 16) + 8192 + 1024;  // staged epilogue: bf16 tiles + partial sums + offsets
+    if (L->smem < staged) L->smem = staged;
+  }
   if (p.shift_kw > 0 && L->smem < size_t(p.MT) * 33 * 4 + 1024) L->smem = size_t(p.MT) * 33 * 4 + 1024;
   {
     const int mstep = p.shift_kw > 0 ? p.MT - (p.shift_kw - 1) : p.MT;
@@ -491,6 +902,24 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
   if (p.shift_kw > 0 && (p.BN != 32 || p.shift_kw * 4 > 32 || p.Cout > 4 || p.stats != nullptr)) return -14;
   L->grid_y = p.CoutPad / p.BN;
   L->grid_z = p.B;
+  L->stat_tiles = L->grid_x * (p.MT / 128);
+  // CTA-pair persistent kernel for the 256-channel layers when there is at least one tile per SM
+  L->pair = 0;
+  {
+    const int T128 = (p.M + 127) / 128;
+    // opt-in (SGGAN_CONV_PAIR=1): measured on B200 the pair kernel hides its epilogue completely but its
+    // MMAs retire at ~208 cycles each (178 for back-to-back cta_group::2 MMAs plus the multicast commits)
+    // against ~168 in the single-CTA kernel, so both end within 2 % of each other (kernels)
+    const char* env = getenv("SGGAN_CONV_PAIR");
+    const bool allow = env && env[0] == '1';
+    if (allow && p.BN == 256 && p.CoutPad == 256 && p.shift_kw == 0 && int64_t(T128) * p.B >= 148) {
+      L->pair = 1;
+      L->T128 = T128;
+      L->npairs = (T128 * p.B + 1) / 2;
+      L->stat_tiles = T128;
+      L->p.MT = 128;
+    }
+  }
   const uint64_t rs = uint64_t(p.a_row_stride) * 2, fs = uint64_t(p.a_frame_pix) * p.a_row_stride * 2;
   int r = make_tmap_bf16_3d(&L->tmA, p.A, p.Cin, p.a_frame_pix, p.B, rs, fs, 64, 128);
   if (r) return -1000 - r;
@@ -498,17 +927,30 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
   if (r) return -1500 - r;
   r = make_tmap_bf16_2d(&L->tmB, p.Wt, p.Cin, uint64_t(p.wt_taps) * p.CoutPad, uint64_t(p.Cin) * 2, 64, p.BN);
   if (r) return -2000 - r;
+  if (L->pair) {
+    r = make_tmap_bf16_2d(&L->tmBh, p.Wt, p.Cin, uint64_t(p.wt_taps) * p.CoutPad, uint64_t(p.Cin) * 2, 64, 128);
+    if (r) return -2500 - r;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmemBudget + 1024);
     if (e != cudaSuccess) return -3000 - int(e);
+    e = cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
+    if (e != cudaSuccess) return -3100 - int(e);
     attr_set = true;
   }
   return 0;
 }
 
 int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
+  if (L.pair) {
+    const int clusters = L.npairs < 74 ? L.npairs : 74;  // one CTA pair per TPC (148 SMs)
+    conv_gemm_pair_kernel<<<dim3(2 * clusters), kConvThreads, kPairSmem, st>>>(L.tmA, L.tmA8, L.tmBh, L.p, L.T128,
+                                                                              L.npairs);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -4100 - int(e);
+  }
   dim3 grid(L.grid_x, L.grid_y, L.grid_z);
   conv_gemm_tc_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tmA, L.tmA8, L.tmB, L.p, L.sa_stages, L.sb_stages,
                                                           L.tmem_cols);

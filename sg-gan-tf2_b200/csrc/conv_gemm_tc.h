@@ -16,6 +16,9 @@ struct ConvGemmLaunch {
   int sa_stages, sb_stages;  // depth of the A ring and of the B ring
   unsigned tmem_cols;
   size_t smem;
+  int stat_tiles;          // 128-row statistics tiles per image this launch writes
+  int pair, T128, npairs;  // CTA-pair persistent kernel (256-channel layers): tiles per image, pair tiles in all
+  CUtensorMap tmBh;        // half weight tile (128 of the 256 output channels) for the pair kernel
 };
 struct WgradLaunch {
   WgradParams p;

@@ -148,7 +148,7 @@ int layer_prepare_fwd(Layer& l, const float* bias, void* out, const FrameMap& om
   int r = layer_prepare_fwd_impl(l, bias, out, omap, out_f32, dry);
   if (r || dry) return r;
   int T = 0;
-  for (auto& L : l.fwd) { L.p.stats_t0 = T; T += L.grid_x * (L.p.MT / 128); }
+  for (auto& L : l.fwd) { L.p.stats_t0 = T; T += L.stat_tiles; }
   for (auto& L : l.fwd) L.p.stats_T = T;
   l.stats_T = T;
   if (l.has_norm && T > l.stats_T_max) return SGGAN_E_WORKSPACE;

@@ -159,7 +159,7 @@ __device__ __forceinline__ void src_extra8(const SrcRow& r, const GradSrc& g, in
 template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const RowStreamParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // pointer arithmetic keeps the shared address space
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -122,8 +122,9 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
     printf("prepare_conv_gemm failed %d\n", r);
     return 1;
   }
-  L.p.stats_T = L.grid_x * (L.p.MT / 128);
+  L.p.stats_T = L.stat_tiles;
   L.p.stats_t0 = 0;
+  if (L.pair) printf("CTA-pair persistent kernel: %d tiles/image, %d pair tiles\n", L.T128, L.npairs);
   printf("grid %d x %d x %d, MT %d, runs %d, stages A %d B %d, smem %zu, tmem cols %u\n", L.grid_x, L.grid_y, L.grid_z,
          L.p.MT, L.p.nruns, L.sa_stages, L.sb_stages, L.smem, L.tmem_cols);
   r = run_conv_gemm(L, 0);
@@ -209,6 +210,27 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
     if (ndiff || sd != 0.0) ++bad;
   }
   if (iters > 0) {
+    if (L.pair) {  // stamps of the persistent CTA-pair kernel
+      const int nct = 148;
+      long long* dDbg;
+      CK(cudaMalloc(&dDbg, size_t(nct) * 16 * sizeof(long long)));
+      CK(cudaMemset(dDbg, 0, size_t(nct) * 16 * sizeof(long long)));
+      ConvGemmLaunch Ld = L;
+      Ld.p.dbg = dDbg;
+      run_conv_gemm(Ld, 0);
+      CK(cudaDeviceSynchronize());
+      std::vector<long long> h(size_t(nct) * 16);
+      CK(cudaMemcpy(h.data(), dDbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+      for (int c = 0; c < 4; ++c) {
+        const long long* t = &h[size_t(c) * 16];
+        printf("PAIR cta %d: setup %lld | mma-issued", c, t[1] - t[0]);
+        for (int k = 0; k < 6; ++k) if (t[2 + k]) printf(" %lld", t[2 + k] - t[0]);
+        printf(" | epi-done");
+        for (int k = 0; k < 6; ++k) if (t[8 + k]) printf(" %lld", t[8 + k] - t[0]);
+        printf(" | end %lld\n", t[15] - t[0]);
+      }
+      CK(cudaFree(dDbg));
+    } else
     {  // per-phase clock64 stamps of one launch
       const int nct = L.grid_x * L.grid_y * L.grid_z;
       long long* dDbg;
@@ -230,8 +252,15 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
         s[4] += L.p.MT == 256 ? double(t[5] - t[4]) : 0.0;
         s[5] += double(t[6] - t[0]);  // whole CTA
       }
-      printf("PHASES (avg SM cycles per CTA over %d CTAs): setup %.0f | mma-issue %.0f | drain %.0f | epi0 %.0f | epi1 %.0f | total %.0f\n",
-             nct, s[0] / nct, s[1] / nct, s[2] / nct, s[3] / nct, s[4] / nct, s[5] / nct);
+      double st_end = 0, cta_end = 0;
+      for (int c = 0; c < nct; ++c) {
+        const long long* t = &h[size_t(c) * 8];
+        st_end += t[7] ? double(t[7] - t[3]) : 0.0;  // statistics warps done, relative to the epilogue start
+        cta_end += double(t[6] - t[3]);
+      }
+      printf("PHASES (avg SM cycles per CTA over %d CTAs): setup %.0f | mma-issue %.0f | drain %.0f | epi0 %.0f | epi1 %.0f | total %.0f"
+             " || from epilogue start: stat warps done %.0f, CTA done %.0f\n",
+             nct, s[0] / nct, s[1] / nct, s[2] / nct, s[3] / nct, s[4] / nct, s[5] / nct, st_end / nct, cta_end / nct);
       CK(cudaFree(dDbg));
     }
     cudaEvent_t e0, e1;
@@ -497,6 +526,87 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_mma, int N, int 
   }
 }
 
+// Same for a CTA pair: tcgen05.mma.cta_group::2, M = 256 over two CTAs, each CTA holding 128 A rows and N/2 B rows.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+mma_rate_pair_kernel(int n_mma, int N, int nacc, int per_commit, long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar, bar2;
+  __shared__ uint32_t tbase;
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = threadIdx.x; i < (16384 + N * 64) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  fence_proxy_async_smem();
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&bar2, 1);
+    fence_barrier_init();
+  }
+  uint32_t cols = 32;
+  while ((int)cols < nacc * N) cols <<= 1;
+  if (warp == 0) tmem_alloc_pair(&tbase, cols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    if (rank == 0) {
+      const uint32_t idesc = idesc_bf16_f32(256, N, 0, 0);
+      const uint64_t adesc = desc_kmajor_sw128(smem_u32(smem));
+      const uint64_t bdesc = desc_kmajor_sw128(smem_u32(smem) + 16384);
+      for (int i = 0; i < n_mma; ++i) {
+        umma_bf16_pair(tbase + uint32_t((i % nacc) * N), adesc + uint64_t((i & 3) * 2), bdesc + uint64_t((i & 3) * 2), idesc, 1);
+        if (per_commit > 0 && (i % per_commit) == per_commit - 1) umma_commit_pair(&bar2);
+      }
+      umma_commit_pair(&bar);
+    }
+    mbar_wait(&bar, 0, 31);
+    const long long t1 = clock64();
+    cycles_out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc_pair(tbase, cols);
+  }
+}
+
+static int run_mma_rate_pair() {
+  long long* d;
+  CK(cudaMalloc(&d, 148 * sizeof(long long)));
+  CK(cudaFuncSetAttribute(mma_rate_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  for (int grid : {2, 148})
+    for (int N : {256, 128, 64})
+      for (int nacc : {1, 2})
+        for (int pc : {0, 4}) {
+          if (nacc * N > 512) continue;
+          const int n_mma = 4096;
+          cudaEvent_t e0, e1;
+          CK(cudaEventCreate(&e0));
+          CK(cudaEventCreate(&e1));
+          mma_rate_pair_kernel<<<grid, 128, 58 * 1024>>>(n_mma, N, nacc, pc, d);
+          CK(cudaEventRecord(e0));
+          mma_rate_pair_kernel<<<grid, 128, 58 * 1024>>>(n_mma, N, nacc, pc, d);
+          CK(cudaEventRecord(e1));
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) {
+            printf("mma_rate_pair: CUDA error %s\n", cudaGetErrorString(e));
+            return 1;
+          }
+          float ms;
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+          long long cyc;
+          CK(cudaMemcpy(&cyc, d, sizeof(cyc), cudaMemcpyDeviceToHost));
+          const double flops = 2.0 * 256 * N * 16 * double(n_mma) * (grid / 2);
+          printf("MMA_RATE_PAIR grid %3d N %3d nacc %d commit/%d: %.1f cycles/MMA (ideal %d per SM), kernel %.3f ms, %.1f TFLOP/s\n",
+                 grid, N, nacc, pc, double(cyc) / n_mma, N / 2, ms, flops / ms * 1e-9);
+        }
+  return 0;
+}
+
 static int run_mma_rate() {
   long long* d;
   CK(cudaMalloc(&d, 148 * sizeof(long long)));
@@ -553,6 +663,12 @@ int main(int argc, char** argv) {
   } else if (!strcmp(t, "conv_res")) {
     ConvCase c = {8, 64, 128, 256, 256, 256, 256, 3, SG_ACT_NONE, 0, 1};
     rc = run_conv_case(c, 20, false);
+  } else if (!strcmp(t, "conv_pair_check")) {
+    ConvCase c = {2, 80, 128, 64, 256, 256, 256, 3, SG_ACT_LRELU, 0, 1};
+    rc = run_conv_case(c, 0, true);
+  } else if (!strcmp(t, "conv_pair_odd")) {  // odd tile count: the last pair has a dummy peer
+    ConvCase c = {3, 51, 126, 64, 256, 256, 256, 3, SG_ACT_NONE, 0, 1};
+    rc = run_conv_case(c, 0, true);
   } else if (!strcmp(t, "conv_res128")) {
     ConvCase c = {8, 64, 128, 256, 256, 256, 128, 3, SG_ACT_NONE, 0, 1};
     rc = run_conv_case(c, 20, false);
@@ -572,6 +688,8 @@ int main(int argc, char** argv) {
     rc = run_wgrad_case(2, 6, 20, 128, 64, 64, 3, 3, 0, true);
   } else if (!strcmp(t, "wgrad_res")) {
     rc = run_wgrad_case(8, 64, 128, 256, 256, 256, 3, 8, 10, false);
+  } else if (!strcmp(t, "mma_rate_pair")) {
+    rc = run_mma_rate_pair();
   } else if (!strcmp(t, "mma_rate")) {
     rc = run_mma_rate();
   } else if (!strcmp(t, "conv_overhead")) {
