@@ -156,7 +156,7 @@ __device__ __forceinline__ void src_extra8(const SrcRow& r, const GradSrc& g, in
 }
 
 // =======================================================================================================
-template <int MODE>
+template <int MODE, int NS>
 __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const RowStreamParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // pointer arithmetic keeps the shared address space
@@ -192,12 +192,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
         const int j0 = jc * p.CW;
         const int cw = min(p.CW, p.W - j0);
         const uint32_t bytes = uint32_t(cw) * p.C * 2;
-        mbar_arrive_expect_tx(&full_bar[s], bytes * p.ns);
-        for (int q = 0; q < p.ns; ++q) {
+        mbar_arrive_expect_tx(&full_bar[s], bytes * NS);
+        for (int q = 0; q < NS; ++q) {
           const StreamDesc& d = p.s[q];
           const sg_bf16* src = d.base + int64_t(d.act_index ? ba : b) * d.img_stride + int64_t(i + d.oy) * d.row_stride +
                                int64_t(j0 + d.ox) * p.C;
-          bulk_load_1d(smem + (s * p.ns + q) * p.chunk_bytes, src, bytes, &full_bar[s]);
+          bulk_load_1d(smem + (s * NS + q) * p.chunk_bytes, src, bytes, &full_bar[s]);
         }
         if (++jc == cpr) { jc = 0; ++i; }
       }
@@ -238,21 +238,83 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       }
     }
   }
-  const bool has0 = p.ns > 0, has1 = p.ns > 1, has2 = p.ns > 2;
-  const uint32_t chunk_bytes = p.chunk_bytes, stage_bytes = p.ns * p.chunk_bytes;
+  const uint32_t chunk_bytes = p.chunk_bytes, stage_bytes = NS * p.chunk_bytes;
   const int W = p.W, C = p.C, CW = p.CW;
   const int src_band = (MODE == RS_APPLY) ? 0 : max(p.g[0].ptr ? p.g[0].fold : 0, p.g[1].ptr ? p.g[1].fold : 0);
   const int dst_band = ((MODE == RS_APPLY || MODE == RS_BWD_APPLY) && p.dmap.kind == 0) ? p.dmap.reflect : 0;
   const int band = max(src_band, dst_band);
   const int dC = (MODE == RS_GATHER) ? C : p.dmap.C;
   const int dkind = (MODE == RS_GATHER) ? 0 : p.dmap.kind;
+  const int pshift = 31 - __clz(pstep);  // pstep = 512 / C8 is a power of two
   const uint32_t sbase = smem_u32(smem) + threadIdx.x * 16;
-  int k = 0;
-  int cur_i = -1;
   DstRow dr;
   SrcRow e1, e2;
   e1.n = e2.n = 0;
   dr.n = 1;
+
+  // one pixel (8 channels) of this thread: `sa` = its vector in stream 0 of the stage, `dptr` = where the lean
+  // (no border bookkeeping) result goes, `j` = image column
+  auto pixel = [&](const bool lean, const uint32_t sa, sg_bf16* dptr, const int j) {
+    uint4 r0 = lds128(sa), r1 = make_uint4(0, 0, 0, 0), r2 = r1;
+    if (NS > 1) r1 = lds128(sa + chunk_bytes);
+    if (NS > 2) r2 = lds128(sa + 2 * chunk_bytes);
+    float y[8], d[8];
+    if (MODE == RS_APPLY) {
+      unpack8(r0, y);
+      unpack8(r1, d);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float z = fmaf(y[e] - mean[e], scale[e], beta[e]);
+        y[e] = (z > 0.f ? z : z * gneg) + d[e];
+      }
+      if (lean) *reinterpret_cast<uint4*>(dptr) = pack8(y);
+      else dst_store8(dr, p.dmap, j, pack8(y));
+    } else if (MODE == RS_GATHER) {
+      unpack8(r0, d);
+      unpack8(r1, y);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] += y[e];
+      if (!lean) {
+        if (src_has_extra(e1, p.g[0], j, W)) src_extra8(e1, p.g[0], j, W, C, d);
+        if (src_has_extra(e2, p.g[1], j, W)) src_extra8(e2, p.g[1], j, W, C, d);
+      }
+      *reinterpret_cast<uint4*>(dptr) = pack8(d);
+    } else {
+      unpack8(r0, y);
+      unpack8(r1, d);
+      if (NS > 2) {
+        float t[8];
+        unpack8(r2, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] += t[e];
+      }
+      if (!lean) {
+        if (src_has_extra(e1, p.g[0], j, W)) src_extra8(e1, p.g[0], j, W, C, d);
+        if (src_has_extra(e2, p.g[1], j, W)) src_extra8(e2, p.g[1], j, W, C, d);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        // zpre = (y - mean)*scale + beta;  xhat = (y - mean)*rstd.  The apply form keeps a single-pixel norm
+        // (xhat == 0, dzh == m1) back-propagating exactly zero, as the reference does at 128x128 (Appendix B).
+        const float yc = y[e] - mean[e];
+        const float dz = fmaf(yc, scale[e], beta[e]) > 0.f ? d[e] : d[e] * gneg;
+        const float xh = yc * rstd[e];
+        if (MODE == RS_BWD_APPLY) {
+          d[e] = scale[e] * ((dz - a1[e]) - xh * a2[e]);
+        } else {
+          a1[e] += dz;
+          a2[e] = fmaf(dz, xh, a2[e]);
+        }
+      }
+      if (MODE == RS_BWD_APPLY) {
+        if (lean) *reinterpret_cast<uint4*>(dptr) = pack8(d);
+        else dst_store8(dr, p.dmap, j, pack8(d));
+      }
+    }
+  };
+
+  int k = 0;
+  int cur_i = -1;
   int i = cbeg / cpr, jc = cbeg - i * cpr;
   for (int c = cbeg; c < cend; ++c, ++k, jc = (jc + 1 == cpr ? 0 : jc + 1), i += (jc == 0)) {
     const int s = k % kStages;
@@ -274,6 +336,10 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       lo = min(cw, max(0, band + 1 - j0));
       hi = max(lo, min(cw, W - 1 - band - j0));
     }
+    // this thread visits pixels px0 + t * pstep, t in [0, nt); t in [tlo, thi) are lean
+    const int nt = cw > px0 ? ((cw - px0 + pstep - 1) >> pshift) : 0;
+    const int tlo = min(nt, lo > px0 ? ((lo - px0 + pstep - 1) >> pshift) : 0);
+    const int thi = max(tlo, min(nt, hi > px0 ? ((hi - px0 + pstep - 1) >> pshift) : 0));
     // incremental destination pointer of this thread (element units)
     sg_bf16* dptr;
     int dstep;
@@ -289,107 +355,65 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     }
     mbar_wait(&full_bar[s], (k / kStages) & 1, 42);
     uint32_t sa = sbase + s * stage_bytes;
-    for (int px = px0; px < cw; px += pstep, sa += kConsumers * 16, dptr += dstep) {
-      const bool lean = px >= lo && px < hi;
-      const int j = j0 + px;
-      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0, r2 = r0;
-      if (has0) r0 = lds128(sa);
-      if (has1) r1 = lds128(sa + chunk_bytes);
-      if (has2) r2 = lds128(sa + 2 * chunk_bytes);
-      float y[8], d[8];
-      if (MODE == RS_APPLY) {
-        unpack8(r0, y);
-        unpack8(r1, d);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float z = fmaf(y[e] - mean[e], scale[e], beta[e]);
-          y[e] = (z > 0.f ? z : z * gneg) + d[e];
-        }
-        if (lean) *reinterpret_cast<uint4*>(dptr) = pack8(y);
-        else dst_store8(dr, p.dmap, j, pack8(y));
-      } else if (MODE == RS_GATHER) {
-        unpack8(r0, d);
-        unpack8(r1, y);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d[e] += y[e];
-        if (!lean) {
-          if (src_has_extra(e1, p.g[0], j, W)) src_extra8(e1, p.g[0], j, W, C, d);
-          if (src_has_extra(e2, p.g[1], j, W)) src_extra8(e2, p.g[1], j, W, C, d);
-        }
-        *reinterpret_cast<uint4*>(dptr) = pack8(d);
-      } else {
-        float t[8];
-        unpack8(r0, y);
-        unpack8(r1, d);
-        unpack8(r2, t);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d[e] += t[e];
-        if (!lean) {
-          if (src_has_extra(e1, p.g[0], j, W)) src_extra8(e1, p.g[0], j, W, C, d);
-          if (src_has_extra(e2, p.g[1], j, W)) src_extra8(e2, p.g[1], j, W, C, d);
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          // zpre = (y - mean)*scale + beta;  xhat = (y - mean)*rstd.  The apply form keeps a single-pixel norm
-          // (xhat == 0, dzh == m1) back-propagating exactly zero, as the reference does at 128x128 (Appendix B).
-          const float yc = y[e] - mean[e];
-          const float dz = fmaf(yc, scale[e], beta[e]) > 0.f ? d[e] : d[e] * gneg;
-          const float xh = yc * rstd[e];
-          if (MODE == RS_BWD_APPLY) {
-            d[e] = scale[e] * ((dz - a1[e]) - xh * a2[e]);
-          } else {
-            a1[e] += dz;
-            a2[e] += dz * xh;
-          }
-        }
-        if (MODE == RS_BWD_APPLY) {
-          if (lean) *reinterpret_cast<uint4*>(dptr) = pack8(d);
-          else dst_store8(dr, p.dmap, j, pack8(d));
-        }
-      }
-    }
+    int j = j0 + px0;
+    int t = 0;
+    for (; t < tlo; ++t, sa += kConsumers * 16, dptr += dstep, j += pstep) pixel(false, sa, dptr, j);
+#pragma unroll 2
+    for (; t < thi; ++t, sa += kConsumers * 16, dptr += dstep, j += pstep) pixel(true, sa, dptr, j);
+    for (; t < nt; ++t, sa += kConsumers * 16, dptr += dstep, j += pstep) pixel(false, sa, dptr, j);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
   if (MODE == RS_BWD_REDUCE) {
     // threads that share a channel group differ in px0 (kConsumers / C8 of them): stage their partials in the
-    // (now idle) pipeline buffers as [px0][2C] and add them in a fixed order
+    // (now idle) pipeline buffers as [px0][e][k][cg] (consecutive lanes -> consecutive words) and add them
+    // in a fixed order
     float* red = reinterpret_cast<float*>(smem);
     named_bar_sync(2, kConsumers);  // every consumer is past its last chunk: the stage buffers are free
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      red[px0 * 2 * C + (c0 + e) * 2] = a1[e];
-      red[px0 * 2 * C + (c0 + e) * 2 + 1] = a2[e];
+      red[((px0 * 8 + e) * 2 + 0) * C8 + cg] = a1[e];
+      red[((px0 * 8 + e) * 2 + 1) * C8 + cg] = a2[e];
     }
     named_bar_sync(2, kConsumers);
     for (int t = threadIdx.x; t < 2 * C; t += kConsumers) {
+      const int ch = t >> 1, kk = t & 1;
+      const int idx = (((ch & 7) * 2) + kk) * C8 + (ch >> 3);
       float acc = 0.f;
-      for (int q = 0; q < pstep; ++q) acc += red[q * 2 * C + t];
+      for (int q = 0; q < pstep; ++q) acc += red[q * 16 * C8 + idx];
       atomicAdd(p.sums + int64_t(b) * C * 2 + t, acc);
     }
   }
+}
+
+template <int MODE, int NS>
+static void launch_row_stream_ns(const RowStreamParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(row_stream_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    attr_set = true;
+  }
+  row_stream_kernel<MODE, NS><<<grid, kStreamThreads, smem, st>>>(p);
 }
 
 template <int MODE>
 static void launch_row_stream(RowStreamParams& p, cudaStream_t st) {
   p.ns = 0;
   while (p.ns < kMaxStreams && p.s[p.ns].base != nullptr) ++p.ns;  // active streams are a prefix
+  if (p.ns == 0) return;
   p.CW = kPipeBytes / (kStages * p.ns) / (p.C * 2);
   if (p.CW > p.W) p.CW = p.W;
   p.chunk_bytes = p.CW * p.C * 2;
-  static bool attr_set = false;
   const size_t smem = size_t(kPipeBytes) + 128;
-  if (!attr_set) {
-    cudaFuncSetAttribute(row_stream_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    attr_set = true;
-  }
   // one persistent block per SM; blocks never span images (per-image statistics)
   int gx = 148 / p.B;
   if (gx < 1) gx = 1;
   const int nchunks = p.H * ((p.W + p.CW - 1) / p.CW);
   if (gx > nchunks) gx = nchunks;
   dim3 grid(gx, p.B);
-  row_stream_kernel<MODE><<<grid, kStreamThreads, smem, st>>>(p);
+  if (p.ns == 1) launch_row_stream_ns<MODE, 1>(p, grid, smem, st);
+  else if (p.ns == 2) launch_row_stream_ns<MODE, 2>(p, grid, smem, st);
+  else launch_row_stream_ns<MODE, 3>(p, grid, smem, st);
 }
 
 static StreamDesc plain_stream(const sg_bf16* base, int H, int W, int C, int act_index) {
