@@ -709,6 +709,226 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // =============================================================================================
+// Transposed ("swap A/B") persistent kernel for layers with at most 128 output channels.
+//
+// tcgen05.mma costs ~156 cycles per instruction whatever N is (tc_probe mma_rate), so an M = 128 pixels x
+// N = Cout <= 128 instruction wastes half (Cout 128) or three quarters (Cout 64) of the tensor pipe.  Here
+// the roles are exchanged: the WEIGHT tile is the M operand (128 channel rows, zero/garbage rows above
+// Cout are never stored) and 256 PIXELS are the N operand, so every instruction is a full 128 x 256 x 16.
+// Both operands are K-major SWIZZLE_128B tiles either way, and the row-shifted descriptor that walks the
+// kw taps of a run now shifts the N operand.  The accumulator is D[channel lane][pixel column]:
+//   * bias / activation / instance-norm statistics are per LANE: plain register sums, no transposition;
+//   * the bf16 result is transposed through shared memory (2-byte stores, conflict-free) and copied out
+//     with coalesced 16-byte stores.
+// One 128 x 256 fp32 accumulator is 256 TMEM columns, so the kernel is persistent with TWO accumulators:
+// the epilogue of tile k overlaps the MMAs of tile k + 1, and barrier/TMEM set-up is paid once per SM
+// instead of once per tile (these layers have short K loops: set-up + epilogue used to be half their time).
+constexpr int kSwapPix = 256;
+constexpr int kSwapPStage = (kSwapPix + kHaloRows) * 128, kSwapWStage = 128 * 128;
+constexpr int kSwapWStages = 4;
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA8,
+                      const __grid_constant__ CUtensorMap tmW, const ConvGemmParams p, const int T256,
+                      const int p_stages) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t p_full[4], p_empty[4], w_full[kSwapWStages], w_empty[kSwapWStages];
+  __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_sh;
+  __shared__ float sbias[128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* smP = smem;
+  uint8_t* smW = smem + p_stages * kSwapPStage;
+  uint8_t* S = smW + kSwapWStages * kSwapWStage;          // staged bf16 tile [256 pixels][pitch]
+  const int pitch = p.Cout * 2 + 16;                        // Cout is a multiple of 8
+  long long* rowoff = reinterpret_cast<long long*>(S + kSwapPix * pitch);  // [256] output element offsets
+  float2* comb = reinterpret_cast<float2*>(rowoff + kSwapPix);             // [2][128] partial statistics
+  const int cchunks = p.Cin / kChunkK;
+  const int total_tiles = p.B * T256;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p_stages; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
+    for (int s = 0; s < kSwapWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA8);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_sh, 512);
+  if (threadIdx.x < 128) sbias[threadIdx.x] = (p.bias != nullptr && int(threadIdx.x) < p.Cout) ? __ldg(p.bias + threadIdx.x) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_sh;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ pixel-tile producer: one tile per (run, chunk)
+    if (lane == 0) {
+      int g = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int b = t / T256, m0 = (t - b * T256) * kSwapPix;
+        for (int r = 0; r < p.nruns; ++r)
+          for (int cc = 0; cc < cchunks; ++cc, ++g) {
+            const int s = g % p_stages;
+            mbar_wait(&p_empty[s], ((g / p_stages) & 1) ^ 1, 1);
+            uint8_t* sp = smP + s * kSwapPStage;
+            const int row0 = m0 + p.run_off[r];
+            mbar_arrive_expect_tx(&p_full[s], kSwapPStage);
+            tma_load_3d(&tmA, &p_full[s], sp, cc * kChunkK, row0, b);
+            tma_load_3d(&tmA, &p_full[s], sp + kABytes, cc * kChunkK, row0 + kTileM, b);
+            tma_load_3d(&tmA8, &p_full[s], sp + 2 * kABytes, cc * kChunkK, row0 + 2 * kTileM, b);
+          }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------ weight-tile producer: one tile per (tap, chunk)
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x)
+        for (int r = 0, t0 = 0; r < p.nruns; t0 += p.run_len[r], ++r)
+          for (int cc = 0; cc < cchunks; ++cc)
+            for (int q = 0; q < p.run_len[r]; ++q, ++it) {
+              const int s = it % kSwapWStages;
+              mbar_wait(&w_empty[s], ((it / kSwapWStages) & 1) ^ 1, 4);
+              mbar_arrive_expect_tx(&w_full[s], kSwapWStage);
+              tma_load_2d(&tmW, &w_full[s], smW + s * kSwapWStage, cc * kChunkK, int(p.run_w[t0 + q]) * p.CoutPad);
+            }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_f32(128, kSwapPix, 0, 0);
+      int it = 0, g = 0, k = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
+        const int buf = k & 1;
+        mbar_wait(&acc_empty[buf], ((k >> 1) & 1) ^ 1, 6);
+        tc_fence_after();
+        const uint32_t d = tmem_acc + uint32_t(buf * kSwapPix);
+        uint32_t acc = 0;
+        for (int r = 0; r < p.nruns; ++r)
+          for (int cc = 0; cc < cchunks; ++cc, ++g) {
+            const int sp_i = g % p_stages;
+            mbar_wait(&p_full[sp_i], (g / p_stages) & 1, 2);
+            tc_fence_after();
+            const uint32_t p_base = smem_u32(smP + sp_i * kSwapPStage);
+            for (int q = 0; q < p.run_len[r]; ++q, ++it) {
+              const int sw_i = it % kSwapWStages;
+              mbar_wait(&w_full[sw_i], (it / kSwapWStages) & 1, 5);
+              tc_fence_after();
+              const uint64_t wdesc = desc_kmajor_sw128(smem_u32(smW + sw_i * kSwapWStage));
+              const uint64_t pdesc = desc_kmajor_sw128(p_base + uint32_t(q) * 128u);  // tap q: q pixel rows in
+#pragma unroll
+              for (int kk = 0; kk < kChunkK / 16; ++kk) {
+                umma_bf16(d, wdesc + uint64_t(kk * 2), pdesc + uint64_t(kk * 2), idesc, acc);
+                acc = 1;
+              }
+              umma_commit(&w_empty[sw_i]);
+            }
+            umma_commit(&p_empty[sp_i]);
+          }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else if (warp < 3 + kEpiWarps) {
+    // ------------------------------------------------------------ epilogue: lane = output channel
+    const int q = warp & 3;
+    const int half = (warp - 3) >> 2;
+    const int ch = q * 32 + lane;
+    const int et = threadIdx.x - 96;
+    const bool has_stats = p.stats != nullptr;
+    const int act = p.act;
+    const float alpha = p.act_alpha;
+    const float bch = sbias[ch];
+    const int ppr = p.Cout >> 3;  // 16-byte pieces per output position
+    __nv_bfloat16* Sh = reinterpret_cast<__nv_bfloat16*>(S);
+    const int pitch_h = pitch >> 1;
+    int k = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
+      const int buf = k & 1;
+      const int b = t / T256, t256 = t - b * T256;
+      const int m0 = t256 * kSwapPix;
+      mbar_wait(&acc_full[buf], (k >> 1) & 1, 3);
+      tc_fence_after();
+      float s1 = 0.f, s2 = 0.f;
+      for (int c0 = half * 32; c0 < kSwapPix; c0 += 64) {
+        // validity of the 32 pixels of this chunk (the same for every channel lane)
+        const int m = m0 + c0 + lane;
+        const int i = m / p.P, j = m - i * p.P;
+        const int oi = i * p.o_scale + p.o_a, oj = j * p.o_scale + p.o_b;
+        const bool valid = (m < p.M) && (i < p.Hv) && (j < p.Wv) && (oi < p.omap.H) && (oj < p.omap.W);
+        const uint32_t mask = __ballot_sync(0xffffffffu, valid);
+        if (q == 0)
+          rowoff[c0 + lane] = valid ? (int64_t(b) * p.omap.frame_pix + frame_pixel(p.omap, oi, oj)) * p.omap.C : -1;
+        float v[32];
+        tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(buf * kSwapPix + c0), v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] += bch;
+        if (act == SG_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+        } else if (act == SG_ACT_LRELU) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], alpha * v[e]);
+        } else if (act == SG_ACT_TANH) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = tanhf(v[e]);
+        }
+        __nv_bfloat16* sp = Sh + c0 * pitch_h + ch;
+        if (ch < p.Cout) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v[e]);
+            sp[e * pitch_h] = h;
+            v[e] = __bfloat162float(h);  // statistics over the values as stored
+          }
+        }
+        if (has_stats) {
+          if (mask == 0xffffffffu) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) { s1 += v[e]; s2 = fmaf(v[e], v[e], s2); }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float x = (mask >> e) & 1u ? v[e] : 0.f;
+              s1 += x; s2 = fmaf(x, x, s2);
+            }
+          }
+        }
+      }
+      // this warp's share of the accumulator has been read: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (has_stats) comb[half * 128 + ch] = make_float2(s1, s2);
+      named_bar_sync(1, kEpiThreads);  // tile staged, offsets and partial sums written
+      if (has_stats && et < p.Cout) {
+        const float2 a0 = comb[et], a1 = comb[128 + et];
+        reinterpret_cast<float2*>(p.stats)[(int64_t(b) * p.stats_T + p.stats_t0 + t256) * p.Cout + et] =
+            make_float2(a0.x + a1.x, a0.y + a1.y);
+      }
+      // coalesced copy-out: consecutive threads take consecutive 16-byte pieces of consecutive positions
+      for (int piece = et; piece < kSwapPix * ppr; piece += kEpiThreads) {
+        const int r = piece / ppr, part = piece - r * ppr;
+        const long long off = rowoff[r];
+        if (off >= 0)
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + part * 8) =
+              *reinterpret_cast<const uint4*>(S + r * pitch + part * 16);
+      }
+      named_bar_sync(1, kEpiThreads);  // the staging buffers are rewritten by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, 512);
+  }
+}
+
+// =============================================================================================
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                      const WgradParams p, const int stages, const uint32_t tmem_cols, const int NA) {
@@ -920,6 +1140,25 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
       L->p.MT = 128;
     }
   }
+  // transposed persistent kernel for layers with at most 128 output channels (bf16 output, one channel block)
+  L->swap = 0;
+  {
+    const char* env = getenv("SGGAN_CONV_SWAP");
+    const bool allow = !(env && env[0] == '0');
+    const int T256 = (p.M + 255) / 256;
+    if (allow && !L->pair && p.CoutPad <= 128 && p.Cout <= 128 && (p.Cout & 7) == 0 && p.shift_kw == 0 && !p.out_f32 &&
+        (p.omap.C & 7) == 0 && p.wt_taps * p.CoutPad >= 128 && int64_t(T256) * p.B >= 32) {
+      L->swap = 1;
+      L->T256 = T256;
+      L->stat_tiles = T256;
+      const int stage_rest = 226 * 1024 - 1024 - kSwapWStages * kSwapWStage - (256 * (p.Cout * 2 + 16) + 256 * 8 + 2048);
+      L->swap_pstages = stage_rest / kSwapPStage;
+      if (L->swap_pstages > 4) L->swap_pstages = 4;
+      if (L->swap_pstages < 2) L->swap = 0;
+      L->swap_smem = size_t(L->swap_pstages) * kSwapPStage + kSwapWStages * kSwapWStage +
+                     (256 * (p.Cout * 2 + 16) + 256 * 8 + 2048) + 1024;
+    }
+  }
   const uint64_t rs = uint64_t(p.a_row_stride) * 2, fs = uint64_t(p.a_frame_pix) * p.a_row_stride * 2;
   int r = make_tmap_bf16_3d(&L->tmA, p.A, p.Cin, p.a_frame_pix, p.B, rs, fs, 64, 128);
   if (r) return -1000 - r;
@@ -927,7 +1166,7 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
   if (r) return -1500 - r;
   r = make_tmap_bf16_2d(&L->tmB, p.Wt, p.Cin, uint64_t(p.wt_taps) * p.CoutPad, uint64_t(p.Cin) * 2, 64, p.BN);
   if (r) return -2000 - r;
-  if (L->pair) {
+  if (L->pair || L->swap) {
     r = make_tmap_bf16_2d(&L->tmBh, p.Wt, p.Cin, uint64_t(p.wt_taps) * p.CoutPad, uint64_t(p.Cin) * 2, 64, 128);
     if (r) return -2500 - r;
   }
@@ -938,6 +1177,8 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
     if (e != cudaSuccess) return -3000 - int(e);
     e = cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
     if (e != cudaSuccess) return -3100 - int(e);
+    e = cudaFuncSetAttribute(conv_gemm_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return -3200 - int(e);
     attr_set = true;
   }
   return 0;
@@ -950,6 +1191,13 @@ int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
                                                                               L.npairs);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -4100 - int(e);
+  }
+  if (L.swap) {
+    const int tiles = L.T256 * L.p.B;
+    conv_gemm_swap_kernel<<<dim3(tiles < 148 ? tiles : 148), kConvThreads, L.swap_smem, st>>>(L.tmA, L.tmA8, L.tmBh, L.p,
+                                                                                             L.T256, L.swap_pstages);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -4200 - int(e);
   }
   dim3 grid(L.grid_x, L.grid_y, L.grid_z);
   conv_gemm_tc_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tmA, L.tmA8, L.tmB, L.p, L.sa_stages, L.sb_stages,

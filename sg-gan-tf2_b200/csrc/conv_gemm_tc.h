@@ -18,7 +18,9 @@ struct ConvGemmLaunch {
   size_t smem;
   int stat_tiles;          // 128-row statistics tiles per image this launch writes
   int pair, T128, npairs;  // CTA-pair persistent kernel (256-channel layers): tiles per image, pair tiles in all
-  CUtensorMap tmBh;        // half weight tile (128 of the 256 output channels) for the pair kernel
+  CUtensorMap tmBh;        // 128-row weight tile (pair kernel: half of the channels; swap kernel: the M operand)
+  int swap, T256, swap_pstages;  // transposed persistent kernel (<= 128 output channels): 256-pixel tiles per image
+  size_t swap_smem;
 };
 struct WgradLaunch {
   WgradParams p;

@@ -125,6 +125,7 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
   L.p.stats_T = L.stat_tiles;
   L.p.stats_t0 = 0;
   if (L.pair) printf("CTA-pair persistent kernel: %d tiles/image, %d pair tiles\n", L.T128, L.npairs);
+  if (L.swap) printf("transposed persistent kernel: %d tiles/image, %d pixel stages, smem %zu\n", L.T256, L.swap_pstages, L.swap_smem);
   printf("grid %d x %d x %d, MT %d, runs %d, stages A %d B %d, smem %zu, tmem cols %u\n", L.grid_x, L.grid_y, L.grid_z,
          L.p.MT, L.p.nruns, L.sa_stages, L.sb_stages, L.smem, L.tmem_cols);
   r = run_conv_gemm(L, 0);
@@ -210,7 +211,8 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
     if (ndiff || sd != 0.0) ++bad;
   }
   if (iters > 0) {
-    if (L.pair) {  // stamps of the persistent CTA-pair kernel
+    if (L.swap) {
+    } else if (L.pair) {  // stamps of the persistent CTA-pair kernel
       const int nct = 148;
       long long* dDbg;
       CK(cudaMalloc(&dDbg, size_t(nct) * 16 * sizeof(long long)));
@@ -669,6 +671,15 @@ int main(int argc, char** argv) {
   } else if (!strcmp(t, "conv_pair_odd")) {  // odd tile count: the last pair has a dummy peer
     ConvCase c = {3, 51, 126, 64, 256, 256, 256, 3, SG_ACT_NONE, 0, 1};
     rc = run_conv_case(c, 0, true);
+  } else if (!strcmp(t, "conv_swap128")) {  // Cout 128: transposed kernel, full check incl. statistics
+    ConvCase c = {2, 40, 126, 64, 128, 128, 128, 3, SG_ACT_LRELU, 0, 1};
+    rc = run_conv_case(c, 0, true);
+  } else if (!strcmp(t, "conv_swap64")) {
+    ConvCase c = {3, 37, 90, 128, 64, 64, 64, 3, SG_ACT_RELU, 0, 1};
+    rc = run_conv_case(c, 0, true);
+  } else if (!strcmp(t, "conv_swap_big")) {  // the 128x256-resolution 3x3 layers of the generator
+    ConvCase c = {8, 128, 256, 64, 128, 128, 128, 3, SG_ACT_NONE, 0, 1};
+    rc = run_conv_case(c, 20, false);
   } else if (!strcmp(t, "conv_res128")) {
     ConvCase c = {8, 64, 128, 256, 256, 256, 128, 3, SG_ACT_NONE, 0, 1};
     rc = run_conv_case(c, 20, false);
