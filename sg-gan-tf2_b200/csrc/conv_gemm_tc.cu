@@ -730,23 +730,24 @@ constexpr int kSwapWStages = 4;
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA8,
                       const __grid_constant__ CUtensorMap tmW, const ConvGemmParams p, const int T256,
-                      const int p_stages) {
+                      const int p_stages, const int nblk) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t p_full[4], p_empty[4], w_full[kSwapWStages], w_empty[kSwapWStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_sh;
-  __shared__ float sbias[128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smP = smem;
   uint8_t* smW = smem + p_stages * kSwapPStage;
   uint8_t* S = smW + kSwapWStages * kSwapWStage;          // staged bf16 tile [256 pixels][pitch]
-  const int pitch = p.Cout * 2 + 16;                        // Cout is a multiple of 8
+  const int cw = p.Cout < 128 ? p.Cout : 128;              // channels per tile (multiple of 8)
+  const int pitch = cw * 2 + 16;
   long long* rowoff = reinterpret_cast<long long*>(S + kSwapPix * pitch);  // [256] output element offsets
   float2* comb = reinterpret_cast<float2*>(rowoff + kSwapPix);             // [2][128] partial statistics
   const int cchunks = p.Cin / kChunkK;
-  const int total_tiles = p.B * T256;
+  const int total_tiles = p.B * T256 * nblk;  // tile t: channel block t % nblk (fastest, so the blocks of one pixel
+                                              // tile run side by side and share it in L2), pixel tile t / nblk
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p_stages; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
@@ -758,7 +759,6 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1) tmem_alloc(&tmem_base_sh, 512);
-  if (threadIdx.x < 128) sbias[threadIdx.x] = (p.bias != nullptr && int(threadIdx.x) < p.Cout) ? __ldg(p.bias + threadIdx.x) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -769,7 +769,8 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       int g = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int b = t / T256, m0 = (t - b * T256) * kSwapPix;
+        const int pt = t / nblk;
+        const int b = pt / T256, m0 = (pt - b * T256) * kSwapPix;
         for (int r = 0; r < p.nruns; ++r)
           for (int cc = 0; cc < cchunks; ++cc, ++g) {
             const int s = g % p_stages;
@@ -787,15 +788,18 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     // ------------------------------------------------------------ weight-tile producer: one tile per (tap, chunk)
     if (lane == 0) {
       int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x)
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n0 = (t % nblk) * 128;
         for (int r = 0, t0 = 0; r < p.nruns; t0 += p.run_len[r], ++r)
           for (int cc = 0; cc < cchunks; ++cc)
             for (int q = 0; q < p.run_len[r]; ++q, ++it) {
               const int s = it % kSwapWStages;
               mbar_wait(&w_empty[s], ((it / kSwapWStages) & 1) ^ 1, 4);
               mbar_arrive_expect_tx(&w_full[s], kSwapWStage);
-              tma_load_2d(&tmW, &w_full[s], smW + s * kSwapWStage, cc * kChunkK, int(p.run_w[t0 + q]) * p.CoutPad);
+              tma_load_2d(&tmW, &w_full[s], smW + s * kSwapWStage, cc * kChunkK,
+                          int(p.run_w[t0 + q]) * p.CoutPad + n0);
             }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
@@ -841,15 +845,17 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const bool has_stats = p.stats != nullptr;
     const int act = p.act;
     const float alpha = p.act_alpha;
-    const float bch = sbias[ch];
-    const int ppr = p.Cout >> 3;  // 16-byte pieces per output position
+    const int ppr = cw >> 3;  // 16-byte pieces per output position and channel block
     __nv_bfloat16* Sh = reinterpret_cast<__nv_bfloat16*>(S);
     const int pitch_h = pitch >> 1;
     int k = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
       const int buf = k & 1;
-      const int b = t / T256, t256 = t - b * T256;
+      const int pt = t / nblk, n0 = (t - pt * nblk) * 128;
+      const int b = pt / T256, t256 = pt - b * T256;
       const int m0 = t256 * kSwapPix;
+      const bool ch_ok = n0 + ch < p.Cout;
+      const float bch = (p.bias != nullptr && ch_ok) ? __ldg(p.bias + n0 + ch) : 0.f;
       mbar_wait(&acc_full[buf], (k >> 1) & 1, 3);
       tc_fence_after();
       float s1 = 0.f, s2 = 0.f;
@@ -861,7 +867,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const bool valid = (m < p.M) && (i < p.Hv) && (j < p.Wv) && (oi < p.omap.H) && (oj < p.omap.W);
         const uint32_t mask = __ballot_sync(0xffffffffu, valid);
         if (q == 0)
-          rowoff[c0 + lane] = valid ? (int64_t(b) * p.omap.frame_pix + frame_pixel(p.omap, oi, oj)) * p.omap.C : -1;
+          rowoff[c0 + lane] = valid ? (int64_t(b) * p.omap.frame_pix + frame_pixel(p.omap, oi, oj)) * p.omap.C + n0 : -1;
         float v[32];
         tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(buf * kSwapPix + c0), v);
 #pragma unroll
@@ -877,7 +883,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int e = 0; e < 32; ++e) v[e] = tanhf(v[e]);
         }
         __nv_bfloat16* sp = Sh + c0 * pitch_h + ch;
-        if (ch < p.Cout) {
+        if (ch_ok) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const __nv_bfloat16 h = __float2bfloat16_rn(v[e]);
@@ -904,9 +910,9 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       if (has_stats) comb[half * 128 + ch] = make_float2(s1, s2);
       named_bar_sync(1, kEpiThreads);  // tile staged, offsets and partial sums written
-      if (has_stats && et < p.Cout) {
+      if (has_stats && et < 128 && n0 + et < p.Cout) {
         const float2 a0 = comb[et], a1 = comb[128 + et];
-        reinterpret_cast<float2*>(p.stats)[(int64_t(b) * p.stats_T + p.stats_t0 + t256) * p.Cout + et] =
+        reinterpret_cast<float2*>(p.stats)[(int64_t(b) * p.stats_T + p.stats_t0 + t256) * p.Cout + n0 + et] =
             make_float2(a0.x + a1.x, a0.y + a1.y);
       }
       // coalesced copy-out: consecutive threads take consecutive 16-byte pieces of consecutive positions
@@ -1146,17 +1152,21 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
     const char* env = getenv("SGGAN_CONV_SWAP");
     const bool allow = !(env && env[0] == '0');
     const int T256 = (p.M + 255) / 256;
-    if (allow && !L->pair && p.CoutPad <= 128 && p.Cout <= 128 && (p.Cout & 7) == 0 && p.shift_kw == 0 && !p.out_f32 &&
-        (p.omap.C & 7) == 0 && p.wt_taps * p.CoutPad >= 128 && int64_t(T256) * p.B >= 32) {
+    const char* env256 = getenv("SGGAN_CONV_SWAP256");
+    const bool wide_ok = (env256 && env256[0] == '1') && p.Cout % 128 == 0 && p.CoutPad == p.Cout;  // several channel blocks
+    if (allow && !L->pair && ((p.CoutPad <= 128 && p.Cout <= 128) || wide_ok) && (p.Cout & 7) == 0 && p.shift_kw == 0 && !p.out_f32 &&
+        (p.omap.C & 7) == 0 && p.wt_taps * p.CoutPad >= 128 && int64_t(T256) * p.B * ((p.Cout + 127) / 128) >= 32) {
       L->swap = 1;
       L->T256 = T256;
       L->stat_tiles = T256;
-      const int stage_rest = 226 * 1024 - 1024 - kSwapWStages * kSwapWStage - (256 * (p.Cout * 2 + 16) + 256 * 8 + 2048);
+      const int cw = p.Cout < 128 ? p.Cout : 128;
+      L->swap_nblk = (p.Cout + 127) / 128;
+      const int stage_rest = 226 * 1024 - 1024 - kSwapWStages * kSwapWStage - (256 * (cw * 2 + 16) + 256 * 8 + 2048);
       L->swap_pstages = stage_rest / kSwapPStage;
       if (L->swap_pstages > 4) L->swap_pstages = 4;
       if (L->swap_pstages < 2) L->swap = 0;
       L->swap_smem = size_t(L->swap_pstages) * kSwapPStage + kSwapWStages * kSwapWStage +
-                     (256 * (p.Cout * 2 + 16) + 256 * 8 + 2048) + 1024;
+                     (256 * (cw * 2 + 16) + 256 * 8 + 2048) + 1024;
     }
   }
   const uint64_t rs = uint64_t(p.a_row_stride) * 2, fs = uint64_t(p.a_frame_pix) * p.a_row_stride * 2;
@@ -1193,9 +1203,9 @@ int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
     return e == cudaSuccess ? 0 : -4100 - int(e);
   }
   if (L.swap) {
-    const int tiles = L.T256 * L.p.B;
-    conv_gemm_swap_kernel<<<dim3(tiles < 148 ? tiles : 148), kConvThreads, L.swap_smem, st>>>(L.tmA, L.tmA8, L.tmBh, L.p,
-                                                                                             L.T256, L.swap_pstages);
+    const int tiles = L.T256 * L.p.B * L.swap_nblk;
+    conv_gemm_swap_kernel<<<dim3(tiles < 148 ? tiles : 148), kConvThreads, L.swap_smem, st>>>(
+        L.tmA, L.tmA8, L.tmBh, L.p, L.T256, L.swap_pstages, L.swap_nblk);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -4200 - int(e);
   }
