@@ -238,7 +238,11 @@ def main():
         "losses_last_step": losses,
         "step_tflops": (gf * B / ms_step) if gf else None,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
+                     "frac": (achieved / peak_tf) if achieved else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one such launch at 256x512 batch 8 from the
+                     # ncu --set full capture summarised in profiles/r01_ncu_conv_res_summary.txt (the 33.6 MB
+                     # output mostly stays in the 126 MB L2); only valid for that workload
+                     "traffic": 37.8e6 if (H, W, B) == (256, 512, 8) else None, "traffic_unit": "bytes/launch",
                      "kernel": "conv_gemm_tc_kernel, residual-block 3x3 256->256 forward (%d launches timed with CUDA events "
                                "inside the steps; algorithmic %.2f GFLOP per launch)" % (conv_n, conv_flops / 1e9),
                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback"},
