@@ -746,6 +746,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   long long* rowoff = reinterpret_cast<long long*>(S + kSwapPix * pitch);  // [256] output element offsets
   float2* comb = reinterpret_cast<float2*>(rowoff + kSwapPix);             // [2][128] partial statistics
   const int cchunks = p.Cin / kChunkK;
+  const int tstep = p.shift_kw > 0 ? kSwapPix - (p.shift_kw - 1) : kSwapPix;  // shift-sum tiles overlap by kw - 1 pixels
   const int total_tiles = p.B * T256 * nblk;  // tile t: channel block t % nblk (fastest, so the blocks of one pixel
                                               // tile run side by side and share it in L2), pixel tile t / nblk
 
@@ -770,7 +771,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int g = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int pt = t / nblk;
-        const int b = pt / T256, m0 = (pt - b * T256) * kSwapPix;
+        const int b = pt / T256, m0 = (pt - b * T256) * tstep;
         for (int r = 0; r < p.nruns; ++r)
           for (int cc = 0; cc < cchunks; ++cc, ++g) {
             const int s = g % p_stages;
@@ -853,11 +854,46 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int buf = k & 1;
       const int pt = t / nblk, n0 = (t - pt * nblk) * 128;
       const int b = pt / T256, t256 = pt - b * T256;
-      const int m0 = t256 * kSwapPix;
+      const int m0 = t256 * tstep;
       const bool ch_ok = n0 + ch < p.Cout;
       const float bch = (p.bias != nullptr && ch_ok) ? __ldg(p.bias + n0 + ch) : 0.f;
       mbar_wait(&acc_full[buf], (k >> 1) & 1, 3);
       tc_fence_after();
+      if (p.shift_kw > 0) {
+        // ---- shift-sum (7x7 output convolution): lane = kw * 4 + co holds that tap's partial product for
+        // every pixel column; out[pixel][co] = sum_kw D[kw*4+co][pixel + kw].  Stage the 32 lanes as fp32
+        // rows (pitch 257: conflict-free both ways), then one thread per pixel adds across kw.
+        float* T = reinterpret_cast<float*>(S);
+        if (q == 0) {
+          for (int c0 = half * 32; c0 < kSwapPix; c0 += 64) {
+            float v[32];
+            tmem_ld32(tmem_acc + uint32_t(buf * kSwapPix + c0), v);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) T[lane * 257 + c0 + e] = v[e];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        named_bar_sync(1, kEpiThreads);
+        const int r = et;
+        if (r < tstep) {
+          const int m = m0 + r;
+          const int i = m / p.P, j = m - i * p.P;
+          if (m < p.M && i < p.Hv && j < p.Wv) {
+            const int64_t ob = (int64_t(b) * p.omap.frame_pix + frame_pixel(p.omap, i, j)) * p.omap.C;
+            for (int co = 0; co < p.Cout; ++co) {
+              float x = p.bias != nullptr ? __ldg(p.bias + co) : 0.f;
+              for (int kw = 0; kw < p.shift_kw; ++kw) x += T[(kw * 4 + co) * 257 + r + kw];
+              x = apply_act(x, act, alpha);
+              if (p.out_f32) reinterpret_cast<float*>(p.out)[ob + co] = x;
+              else reinterpret_cast<__nv_bfloat16*>(p.out)[ob + co] = __float2bfloat16_rn(x);
+            }
+          }
+        }
+        named_bar_sync(1, kEpiThreads);  // T is rewritten by the next tile
+        continue;
+      }
       float s1 = 0.f, s2 = 0.f;
       for (int c0 = half * 32; c0 < kSwapPix; c0 += 64) {
         // validity of the 32 pixels of this chunk (the same for every channel lane)
@@ -1151,22 +1187,26 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
   {
     const char* env = getenv("SGGAN_CONV_SWAP");
     const bool allow = !(env && env[0] == '0');
-    const int T256 = (p.M + 255) / 256;
     const char* env256 = getenv("SGGAN_CONV_SWAP256");
     const bool wide_ok = (env256 && env256[0] == '1') && p.Cout % 128 == 0 && p.CoutPad == p.Cout;  // several channel blocks
-    if (allow && !L->pair && ((p.CoutPad <= 128 && p.Cout <= 128) || wide_ok) && (p.Cout & 7) == 0 && p.shift_kw == 0 && !p.out_f32 &&
-        (p.omap.C & 7) == 0 && p.wt_taps * p.CoutPad >= 128 && int64_t(T256) * p.B * ((p.Cout + 127) / 128) >= 32) {
+    const bool plain_ok = ((p.CoutPad <= 128 && p.Cout <= 128) || wide_ok) && (p.Cout & 7) == 0 && p.shift_kw == 0 &&
+                          !p.out_f32 && (p.omap.C & 7) == 0;
+    const bool shift_ok = p.shift_kw > 0 && p.BN == 32 && p.shift_kw * 4 <= 32 && p.Cout <= 4 && p.stats == nullptr;
+    const int tstep = p.shift_kw > 0 ? 256 - (p.shift_kw - 1) : 256;
+    const int T = (p.M + tstep - 1) / tstep;
+    if (allow && !L->pair && (plain_ok || shift_ok) && p.wt_taps * p.CoutPad >= 128 &&
+        int64_t(T) * p.B * ((p.Cout + 127) / 128) >= 32) {
       L->swap = 1;
-      L->T256 = T256;
-      L->stat_tiles = T256;
+      L->T256 = T;
+      L->stat_tiles = T;
       const int cw = p.Cout < 128 ? p.Cout : 128;
       L->swap_nblk = (p.Cout + 127) / 128;
-      const int stage_rest = 226 * 1024 - 1024 - kSwapWStages * kSwapWStage - (256 * (cw * 2 + 16) + 256 * 8 + 2048);
+      const int epi = shift_ok ? 32 * 257 * 4 + 1024 : 256 * (cw * 2 + 16) + 256 * 8 + 2048;
+      const int stage_rest = 226 * 1024 - 1024 - kSwapWStages * kSwapWStage - epi;
       L->swap_pstages = stage_rest / kSwapPStage;
       if (L->swap_pstages > 4) L->swap_pstages = 4;
       if (L->swap_pstages < 2) L->swap = 0;
-      L->swap_smem = size_t(L->swap_pstages) * kSwapPStage + kSwapWStages * kSwapWStage +
-                     (256 * (cw * 2 + 16) + 256 * 8 + 2048) + 1024;
+      L->swap_smem = size_t(L->swap_pstages) * kSwapPStage + kSwapWStages * kSwapWStage + epi + 1024;
     }
   }
   const uint64_t rs = uint64_t(p.a_row_stride) * 2, fs = uint64_t(p.a_frame_pix) * p.a_row_stride * 2;

@@ -48,16 +48,17 @@ struct ConvCase {
   int B, H, W, Cin, Cout, CoutPad, BN, k;  // k x k taps, frame padded by k/2, pitch W + k - 1
   int act, out_f32, use_stats;
   int MT;  // 0 = let prepare_conv_gemm choose
+  int shift;  // 1: shift-sum form of a k x k convolution with Cout <= 4 (one tap per filter row, N = kw*4 + co)
 };
 
 static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
   const int pad = c.k / 2, P = c.W + 2 * pad, rows = c.H + 2 * pad;
   const int64_t frame_pix = int64_t(rows) * P + 8;
-  const int ntaps = c.k * c.k;
+  const int ntaps = c.shift ? c.k : c.k * c.k;
   std::vector<uint16_t> hA(size_t(c.B) * frame_pix * c.Cin), hW(size_t(ntaps) * c.CoutPad * c.Cin, 0);
   for (auto& v : hA) v = f2bf(frand());
   for (int t = 0; t < ntaps; ++t)
-    for (int n = 0; n < c.Cout; ++n)
+    for (int n = 0; n < (c.shift ? c.CoutPad : c.Cout); ++n)
       for (int ci = 0; ci < c.Cin; ++ci) hW[(size_t(t) * c.CoutPad + n) * c.Cin + ci] = f2bf(frand() * 0.1f);
   std::vector<float> hbias(c.Cout);
   for (auto& v : hbias) v = frand();
@@ -93,6 +94,10 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
   p.CoutPad = c.CoutPad;
   p.Cout = c.Cout;
   p.BN = c.BN;
+  if (c.shift) {
+    p.shift_kw = c.k;
+    for (int kh = 0; kh < c.k; ++kh) { p.tap_off[kh] = kh * P; p.tap_w[kh] = uint8_t(kh); }
+  } else
   for (int kh = 0; kh < c.k; ++kh)
     for (int kw = 0; kw < c.k; ++kw) {
       p.tap_off[kh * c.k + kw] = kh * P + kw;
@@ -158,10 +163,11 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
     const int b = int(pos / (c.H * c.W)), i = int((pos / c.W) % c.H), j = int(pos % c.W);
     for (int n = 0; n < c.Cout; ++n) {
       double acc = hbias[n];
-      for (int t = 0; t < ntaps; ++t) {
-        const int64_t pix = int64_t(i) * P + j + p.tap_off[t];
+      for (int t = 0; t < c.k * c.k; ++t) {
+        const int kh = t / c.k, kw = t % c.k;
+        const int64_t pix = int64_t(i) * P + j + kh * P + kw;
         const uint16_t* a = &hA[(size_t(b) * frame_pix + pix) * c.Cin];
-        const uint16_t* w = &hW[(size_t(t) * c.CoutPad + n) * c.Cin];
+        const uint16_t* w = c.shift ? &hW[(size_t(kh) * c.CoutPad + kw * 4 + n) * c.Cin] : &hW[(size_t(t) * c.CoutPad + n) * c.Cin];
         for (int ci = 0; ci < c.Cin; ++ci) acc += double(bf2f(a[ci])) * double(bf2f(w[ci]));
       }
       float ref = float(acc);
@@ -691,6 +697,15 @@ int main(int argc, char** argv) {
     rc = run_conv_case(c, 20, false);
   } else if (!strcmp(t, "conv_out7_big")) {
     ConvCase c = {8, 256, 512, 64, 3, 32, 32, 7, SG_ACT_TANH, 1, 0, 0};
+    rc = run_conv_case(c, 10, false);
+  } else if (!strcmp(t, "conv_out7_mid")) {  // shift-sum epilogue of the transposed persistent kernel, full check
+    ConvCase c = {2, 40, 200, 64, 3, 32, 32, 7, SG_ACT_TANH, 1, 0, 0, 1};
+    rc = run_conv_case(c, 0, true);
+  } else if (!strcmp(t, "conv_out7_shift_small")) {  // shift-sum epilogue of the single-CTA kernel (few tiles)
+    ConvCase c = {1, 8, 40, 64, 3, 32, 32, 7, SG_ACT_TANH, 1, 0, 0, 1};
+    rc = run_conv_case(c, 0, true);
+  } else if (!strcmp(t, "conv_out7_shift_big")) {
+    ConvCase c = {8, 256, 512, 64, 3, 32, 32, 7, SG_ACT_TANH, 1, 0, 0, 1};
     rc = run_conv_case(c, 10, false);
   } else if (!strcmp(t, "conv_out7")) {
     ConvCase c = {1, 8, 40, 64, 3, 32, 32, 7, SG_ACT_TANH, 1, 0};

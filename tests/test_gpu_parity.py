@@ -14,12 +14,14 @@ Tolerances (stated per north_star: bf16 rel 1e-2 for losses; integer work bit-ex
 import argparse
 import ctypes as C
 import importlib
+import os
 
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def rel(a, b):
@@ -431,3 +433,33 @@ def test_model_api(L, O, tmp_path):
     d = m.discriminator([seg_A, mask])
     assert tuple(d.shape) == (1, 1, 5, 1)
     assert abs(float(m.disc_loss_p2p(d, -d)) - float(O.disc_loss_p2p(d.cpu(), -d.cpu()))) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- kernel probe
+PROBE_CASES = ["conv_small", "conv_small64", "conv_small256", "conv_swap128", "conv_swap64", "conv_pair_check",
+               "conv_out7", "conv_out7_mid", "conv_out7_shift_small", "wgrad_small", "shift"]
+
+
+@pytest.mark.parametrize("case", PROBE_CASES)
+def test_tc_probe_kernels(case):
+    """tests/gpu/tc_probe.cu drives the tcgen05 kernels directly (no engine): every output position and the
+    per-(image, channel) statistics against a double-precision CPU loop, plus bit-reproducibility of a
+    second launch.  Covers the single-CTA staged epilogue, the transposed persistent kernel (Cout 64 / 128),
+    the shift-sum 7x7 output convolution and the split-K weight-gradient kernel."""
+    import subprocess
+    exe = os.path.join(ROOT, "build", "tc_probe")
+    if not os.path.exists(exe):
+        pytest.fail("build/tc_probe missing: run __graft_entry__.build()")
+    out = subprocess.run([exe, case], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and ("RESULT %s PASS" % case) in out.stdout, out.stdout[-2000:] + out.stderr[-500:]
+
+
+def test_tc_probe_pair_kernel():
+    """The opt-in CTA-pair (cta_group::2) kernel, including an odd tile count (dummy peer tile)."""
+    import subprocess
+    exe = os.path.join(ROOT, "build", "tc_probe")
+    env = dict(os.environ, SGGAN_CONV_PAIR="1")
+    for case in ("conv_pair_check", "conv_pair_odd"):
+        out = subprocess.run([exe, case], capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0 and "CTA-pair persistent kernel" in out.stdout and ("RESULT %s PASS" % case) in out.stdout, \
+            out.stdout[-2000:]
