@@ -725,22 +725,22 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // instead of once per tile (these layers have short K loops: set-up + epilogue used to be half their time).
 constexpr int kSwapPix = 256;
 constexpr int kSwapPStage = (kSwapPix + kHaloRows) * 128, kSwapWStage = 128 * 128;
-constexpr int kSwapWStages = 4;
+constexpr int kSwapMaxWStages = 6;
 
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA8,
                       const __grid_constant__ CUtensorMap tmW, const ConvGemmParams p, const int T256,
-                      const int p_stages, const int nblk) {
+                      const int p_stages, const int w_stages, const int nblk) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  __shared__ uint64_t p_full[4], p_empty[4], w_full[kSwapWStages], w_empty[kSwapWStages];
+  __shared__ uint64_t p_full[4], p_empty[4], w_full[kSwapMaxWStages], w_empty[kSwapMaxWStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_sh;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* smP = smem;
   uint8_t* smW = smem + p_stages * kSwapPStage;
-  uint8_t* S = smW + kSwapWStages * kSwapWStage;          // staged bf16 tile [256 pixels][pitch]
+  uint8_t* S = smW + w_stages * kSwapWStage;          // staged bf16 tile [256 pixels][pitch]
   const int cw = p.Cout < 128 ? p.Cout : 128;              // channels per tile (multiple of 8)
   const int pitch = cw * 2 + 16;
   long long* rowoff = reinterpret_cast<long long*>(S + kSwapPix * pitch);  // [256] output element offsets
@@ -752,7 +752,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p_stages; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], 1); }
-    for (int s = 0; s < kSwapWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < w_stages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], kEpiWarps); }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -794,8 +794,8 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int r = 0, t0 = 0; r < p.nruns; t0 += p.run_len[r], ++r)
           for (int cc = 0; cc < cchunks; ++cc)
             for (int q = 0; q < p.run_len[r]; ++q, ++it) {
-              const int s = it % kSwapWStages;
-              mbar_wait(&w_empty[s], ((it / kSwapWStages) & 1) ^ 1, 4);
+              const int s = it % w_stages;
+              mbar_wait(&w_empty[s], ((it / w_stages) & 1) ^ 1, 4);
               mbar_arrive_expect_tx(&w_full[s], kSwapWStage);
               tma_load_2d(&tmW, &w_full[s], smW + s * kSwapWStage, cc * kChunkK,
                           int(p.run_w[t0 + q]) * p.CoutPad + n0);
@@ -820,8 +820,8 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tc_fence_after();
             const uint32_t p_base = smem_u32(smP + sp_i * kSwapPStage);
             for (int q = 0; q < p.run_len[r]; ++q, ++it) {
-              const int sw_i = it % kSwapWStages;
-              mbar_wait(&w_full[sw_i], (it / kSwapWStages) & 1, 5);
+              const int sw_i = it % w_stages;
+              mbar_wait(&w_full[sw_i], (it / w_stages) & 1, 5);
               tc_fence_after();
               const uint64_t wdesc = desc_kmajor_sw128(smem_u32(smW + sw_i * kSwapWStage));
               const uint64_t pdesc = desc_kmajor_sw128(p_base + uint32_t(q) * 128u);  // tap q: q pixel rows in
@@ -1202,11 +1202,19 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
       const int cw = p.Cout < 128 ? p.Cout : 128;
       L->swap_nblk = (p.Cout + 127) / 128;
       const int epi = shift_ok ? 32 * 257 * 4 + 1024 : 256 * (cw * 2 + 16) + 256 * 8 + 2048;
-      const int stage_rest = 226 * 1024 - 1024 - kSwapWStages * kSwapWStage - epi;
-      L->swap_pstages = stage_rest / kSwapPStage;
-      if (L->swap_pstages > 4) L->swap_pstages = 4;
-      if (L->swap_pstages < 2) L->swap = 0;
-      L->swap_smem = size_t(L->swap_pstages) * kSwapPStage + kSwapWStages * kSwapWStage + epi + 1024;
+      // split the pipeline memory: 3 pixel stages (33 KB each; one serves run_len x 4 MMAs) when at least 3 weight
+      // stages (16 KB each; one serves 4 MMAs) still fit, else 2
+      const int pipe = 226 * 1024 - 1024 - epi;
+      const char* ews = getenv("SGGAN_SWAP_WSTAGES");
+      int ps = 3, ws = (pipe - ps * kSwapPStage) / kSwapWStage;
+      if (ews) { ws = atoi(ews); ps = (pipe - ws * kSwapWStage) / kSwapPStage; }
+      if (ws < 3) { ps = 2; ws = (pipe - ps * kSwapPStage) / kSwapWStage; }
+      if (ws > kSwapMaxWStages) ws = kSwapMaxWStages;
+      if (ps > 4) ps = 4;
+      if (ps < 2 || ws < 2) L->swap = 0;
+      L->swap_pstages = ps;
+      L->swap_wstages = ws;
+      L->swap_smem = size_t(ps) * kSwapPStage + size_t(ws) * kSwapWStage + epi + 1024;
     }
   }
   const uint64_t rs = uint64_t(p.a_row_stride) * 2, fs = uint64_t(p.a_frame_pix) * p.a_row_stride * 2;
@@ -1245,7 +1253,7 @@ int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
   if (L.swap) {
     const int tiles = L.T256 * L.p.B * L.swap_nblk;
     conv_gemm_swap_kernel<<<dim3(tiles < 148 ? tiles : 148), kConvThreads, L.swap_smem, st>>>(
-        L.tmA, L.tmA8, L.tmBh, L.p, L.T256, L.swap_pstages, L.swap_nblk);
+        L.tmA, L.tmA8, L.tmBh, L.p, L.T256, L.swap_pstages, L.swap_wstages, L.swap_nblk);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : -4200 - int(e);
   }

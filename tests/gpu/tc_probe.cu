@@ -130,7 +130,7 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
   L.p.stats_T = L.stat_tiles;
   L.p.stats_t0 = 0;
   if (L.pair) printf("CTA-pair persistent kernel: %d tiles/image, %d pair tiles\n", L.T128, L.npairs);
-  if (L.swap) printf("transposed persistent kernel: %d tiles/image, %d pixel stages, smem %zu\n", L.T256, L.swap_pstages, L.swap_smem);
+  if (L.swap) printf("transposed persistent kernel: %d tiles/image, %d pixel + %d weight stages, smem %zu\n", L.T256, L.swap_pstages, L.swap_wstages, L.swap_smem);
   printf("grid %d x %d x %d, MT %d, runs %d, stages A %d B %d, smem %zu, tmem cols %u\n", L.grid_x, L.grid_y, L.grid_z,
          L.p.MT, L.p.nruns, L.sa_stages, L.sb_stages, L.smem, L.tmem_cols);
   r = run_conv_gemm(L, 0);
