@@ -113,7 +113,7 @@ def run_reference(args):
     w = min(args.warmup, 1)
     k = max(1, min(args.steps, 5))
     cb, sec, n = cpu_baseline(args.height, args.width, args.classes, k, w, max_seconds=120.0)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+    line = {"impl": "reference", "metric": METRIC if (H, W) == (256, 512) else "G+D train img/s at %dx%d" % (H, W), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n,
             "warmup": w, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "SG-GAN train_step %dx%d C=%d, CPU restatement of the reference (TF2 unavailable), "
@@ -227,7 +227,7 @@ def main():
     value = B * world * args.steps / (ms * 1e-3)
     gf = GFLOP_PER_IMG.get((H, W, C))
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC if (H, W) == (256, 512) else "G+D train img/s at %dx%d" % (H, W), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "SG-GAN full G+D train step (generator_resnet 9 blocks + semantic-aware D, fwd+bwd+Adam), "
