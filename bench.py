@@ -113,6 +113,7 @@ def run_reference(args):
     w = min(args.warmup, 1)
     k = max(1, min(args.steps, 5))
     cb, sec, n = cpu_baseline(args.height, args.width, args.classes, k, w, max_seconds=120.0)
+    H, W = args.height, args.width
     line = {"impl": "reference", "metric": METRIC if (H, W) == (256, 512) else "G+D train img/s at %dx%d" % (H, W), "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n,
             "warmup": w, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
