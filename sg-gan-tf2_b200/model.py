@@ -62,6 +62,7 @@ class sggan(object):
         self.runtime = None
         self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._pinned = {}
+        self._h2d_done = {}
 
     # ---- plan -----------------------------------------------------------------------------------------
     def _ensure_runtime(self, B, H, W, mask_hw):
@@ -88,13 +89,23 @@ class sggan(object):
         """numpy batch -> device through a persistent pinned staging buffer (H2D inside the step)."""
         if isinstance(x, torch.Tensor) and x.is_cuda:
             return x.float().contiguous()
-        x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+        if isinstance(x, torch.Tensor) and x.dtype == torch.float32 and x.is_contiguous() and x.is_pinned():
+            return x.to("cuda", non_blocking=True)  # already page-locked: one asynchronous H2D copy, no staging
+        x = torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float32))) if not isinstance(x, torch.Tensor) \
+            else x.float().contiguous()
         buf = self._pinned.get(name)
         if buf is None or buf.shape != x.shape:
-            buf = torch.empty(x.shape, dtype=torch.float32).pin_memory()
+            buf = torch.empty(tuple(x.shape), dtype=torch.float32).pin_memory()
             self._pinned[name] = buf
-        buf.numpy()[...] = x
-        return buf.to("cuda", non_blocking=True)
+        ev = self._h2d_done.get(name)
+        if ev is not None:
+            ev.synchronize()  # the previous step's asynchronous copy out of this staging buffer has finished
+        buf.copy_(x)  # multi-threaded host copy into the page-locked staging buffer
+        dev = buf.to("cuda", non_blocking=True)
+        ev = ev or torch.cuda.Event()
+        ev.record()
+        self._h2d_done[name] = ev
+        return dev
 
     # ---- the hot path ---------------------------------------------------------------------------------
     def train_step(self, args=None):
