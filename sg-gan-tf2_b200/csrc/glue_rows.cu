@@ -78,78 +78,61 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
   for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(f[2 * k], f[2 * k + 1]);
   return u;
 }
-// mirror images of index i inside a reflect border of width p (excluding i itself)
-__device__ __forceinline__ int mirrors(int i, int n, int p, int* out) {
+// mirror images of index i inside a reflect border of width p (excluding i itself): returns how many (0..2)
+__device__ __forceinline__ int mirrors(int i, int n, int p, int& m0, int& m1) {
   int k = 0;
+  m0 = m1 = 0;
   if (p > 0) {
-    if (i >= 1 && i <= p) out[k++] = -i;
-    if (i >= n - 1 - p && i <= n - 2) out[k++] = 2 * (n - 1) - i;
+    if (i >= 1 && i <= p) { m0 = -i; k = 1; }
+    if (i >= n - 1 - p && i <= n - 2) {
+      if (k == 0) m0 = 2 * (n - 1) - i; else m1 = 2 * (n - 1) - i;
+      ++k;
+    }
   }
   return k;
 }
 
-// ---- destination row of a frame -----------------------------------------------------------------------
-struct DstRow {
-  sg_bf16* base[3];  // kind 0: row i and its reflected copies, at logical column 0; kind 1: [0] even, [1] odd columns
-  int n;
+// ---- per-chunk bookkeeping, resolved ONCE by the producer thread and handed to the consumers through shared
+// memory next to the data (the consumers used to redo it per thread: reflected rows, plane bases, 64-bit
+// multiplies, local-memory arrays -- about as many instructions as the arithmetic itself) -----------------------
+struct __align__(16) ChunkDesc {
+  int i, j0, cw, lo;   // image row, first column, width; pixels [lo, hi) need no border bookkeeping
+  int hi, dn, n1, n2;  // rows the result goes to (1 + reflected copies); rows of the two folded gradient sources
+  long long dbase[3];  // element offsets (without the channel) of the destination rows at logical column 0;
+                       // phase-split frames: [0] even-column plane, [1] odd-column plane
+  long long s1[3];     // element offsets of the gradient-source rows (primary first, then its mirrored rows)
+  long long s2[3];
+  long long pad;
 };
-__device__ __forceinline__ void dst_row_init(DstRow& r, sg_bf16* dst, const FrameMap& m, int b, int i, int c0) {
-  sg_bf16* img = dst + int64_t(b) * m.frame_pix * m.C + c0;
+static_assert(sizeof(ChunkDesc) == 112 || sizeof(ChunkDesc) == 128, "ChunkDesc layout");
+
+__device__ __forceinline__ void dst_store8(const ChunkDesc* cd, const FrameMap& m, sg_bf16* dst_c0, int j, const uint4& w) {
   if (m.kind == 0) {
-    int mr[2];
-    const int nm = mirrors(i, m.H, m.reflect, mr);
-    r.n = 1 + nm;
-    r.base[0] = img + (int64_t(i + m.pt) * m.P + m.pl) * m.C;
-    for (int k = 0; k < nm; ++k) r.base[1 + k] = img + (int64_t(mr[k] + m.pt) * m.P + m.pl) * m.C;
-  } else {
-    r.n = 1;
-    const int64_t row = int64_t((i >> 1) + m.pt) * m.P + m.pl;
-    r.base[0] = img + (int64_t((i & 1) * 2) * m.plane_pix + row) * m.C;
-    r.base[1] = img + (int64_t((i & 1) * 2 + 1) * m.plane_pix + row) * m.C;
-  }
-}
-__device__ __forceinline__ void dst_store8(const DstRow& r, const FrameMap& m, int j, const uint4& w) {
-  if (m.kind == 0) {
-    for (int k = 0; k < r.n; ++k) *reinterpret_cast<uint4*>(r.base[k] + int64_t(j) * m.C) = w;
+    const int dn = cd->dn;
+    for (int k = 0; k < dn; ++k) *reinterpret_cast<uint4*>(dst_c0 + cd->dbase[k] + int64_t(j) * m.C) = w;
     if (m.reflect > 0 && (j <= m.reflect || j >= m.W - 1 - m.reflect)) {
-      int mc[2];
-      const int nc = mirrors(j, m.W, m.reflect, mc);
+      int c0, c1;
+      const int nc = mirrors(j, m.W, m.reflect, c0, c1);
       for (int q = 0; q < nc; ++q)
-        for (int k = 0; k < r.n; ++k) *reinterpret_cast<uint4*>(r.base[k] + int64_t(mc[q]) * m.C) = w;
+        for (int k = 0; k < dn; ++k) *reinterpret_cast<uint4*>(dst_c0 + cd->dbase[k] + int64_t(q ? c1 : c0) * m.C) = w;
     }
   } else {
-    *reinterpret_cast<uint4*>(r.base[j & 1] + int64_t(j >> 1) * m.C) = w;
+    *reinterpret_cast<uint4*>(dst_c0 + cd->dbase[j & 1] + int64_t(j >> 1) * m.C) = w;
   }
 }
-
-// ---- folded-border extras of a gradient source (everything except the primary read) ---------------------------
-struct SrcRow {
-  const sg_bf16* base[3];
-  int n;
-};
-__device__ __forceinline__ void src_row_init(SrcRow& r, const GradSrc& g, int b, int i, int H, int C, int c0) {
-  if (g.ptr == nullptr) {
-    r.n = 0;
-    return;
-  }
-  const sg_bf16* img = reinterpret_cast<const sg_bf16*>(g.ptr) + int64_t(b) * g.Hs * g.Ws * C + c0;
-  int mr[2];
-  const int nm = mirrors(i, H, g.fold, mr);
-  r.n = 1 + nm;
-  r.base[0] = img + (int64_t(i + g.oy) * g.Ws + g.ox) * C;
-  for (int k = 0; k < nm; ++k) r.base[1 + k] = img + (int64_t(mr[k] + g.oy) * g.Ws + g.ox) * C;
+// folded-border extras of a gradient source: everything except the primary read (row 0, column j)
+__device__ __forceinline__ bool src_has_extra(int n, const GradSrc& g, int j, int W) {
+  return n > 1 || (g.fold > 0 && n > 0 && (j <= g.fold || j >= W - 1 - g.fold));
 }
-__device__ __forceinline__ bool src_has_extra(const SrcRow& r, const GradSrc& g, int j, int W) {
-  return r.n > 1 || (g.fold > 0 && r.n > 0 && (j <= g.fold || j >= W - 1 - g.fold));
-}
-__device__ __forceinline__ void src_extra8(const SrcRow& r, const GradSrc& g, int j, int W, int C, float* acc) {
-  int mc[2];
-  const int nc = (g.fold > 0 && (j <= g.fold || j >= W - 1 - g.fold)) ? mirrors(j, W, g.fold, mc) : 0;
-  for (int k = 0; k < r.n; ++k)
+__device__ __forceinline__ void src_extra8(const long long* rows, int n, const GradSrc& g, int j, int W, int C, int c0, float* acc) {
+  int m0 = 0, m1 = 0;
+  const int nc = (g.fold > 0 && (j <= g.fold || j >= W - 1 - g.fold)) ? mirrors(j, W, g.fold, m0, m1) : 0;
+  const sg_bf16* src_c0 = reinterpret_cast<const sg_bf16*>(g.ptr) + c0;
+  for (int k = 0; k < n; ++k)
     for (int q = (k == 0 ? 1 : 0); q <= nc; ++q) {
-      const int col = q == 0 ? j : mc[q - 1];
+      const int col = q == 0 ? j : (q == 1 ? m0 : m1);
       float t[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(r.base[k] + int64_t(col) * C)), t);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(src_c0 + rows[k] + int64_t(col) * C)), t);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += t[e];
     }
@@ -161,16 +144,17 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // pointer arithmetic keeps the shared address space
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+  __shared__ ChunkDesc descs[kStages];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int ba = b < p.nb_act ? b : b - p.act_wrap;
   const int cpr = (p.W + p.CW - 1) / p.CW;  // chunks per row
   const int nchunks = p.H * cpr;
-  // each block owns a contiguous range of chunks, so consecutive chunks mostly share their image row and the
-  // per-row bookkeeping (border rows, base pointers) is amortised
+  // each block owns a contiguous range of chunks, so consecutive chunks mostly share their image row
   const int cper = (nchunks + gridDim.x - 1) / gridDim.x;
   const int cbeg = blockIdx.x * cper, cend = min(nchunks, cbeg + cper);
+  const int dkind = (MODE == RS_GATHER) ? 0 : p.dmap.kind;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -182,17 +166,70 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   __syncthreads();
 
   if (warp == kConsumers / 32) {
-    // ------------------------------------------------------------ producer: bulk copies, kStages chunks ahead
+    // ------------------------------------------------------------ producer: bookkeeping + bulk copies, kStages ahead
     if (lane == 0) {
+      const int src_band = (MODE == RS_APPLY) ? 0 : max(p.g[0].ptr ? p.g[0].fold : 0, p.g[1].ptr ? p.g[1].fold : 0);
+      const int dst_band = ((MODE == RS_APPLY || MODE == RS_BWD_APPLY) && dkind == 0) ? p.dmap.reflect : 0;
+      const int band = max(src_band, dst_band);
+      ChunkDesc row;  // row-level part, recomputed when the image row changes
+      int cur_i = -1;
       int k = 0;
       int i = cbeg / cpr, jc = cbeg - i * cpr;
       for (int c = cbeg; c < cend; ++c, ++k) {
         const int s = k % kStages;
+        if (i != cur_i) {
+          cur_i = i;
+          row.dn = 1; row.n1 = row.n2 = 0;
+          int m0, m1;
+          if (MODE == RS_GATHER) {
+            row.dbase[0] = (int64_t(b) * p.H + i) * p.W * p.C;
+          } else if (MODE == RS_APPLY || MODE == RS_BWD_APPLY) {
+            const FrameMap& m = p.dmap;
+            const int64_t img = int64_t(b) * m.frame_pix * m.C;
+            if (m.kind == 0) {
+              const int nm = mirrors(i, m.H, m.reflect, m0, m1);
+              row.dn = 1 + nm;
+              row.dbase[0] = img + (int64_t(i + m.pt) * m.P + m.pl) * m.C;
+              if (nm > 0) row.dbase[1] = img + (int64_t(m0 + m.pt) * m.P + m.pl) * m.C;
+              if (nm > 1) row.dbase[2] = img + (int64_t(m1 + m.pt) * m.P + m.pl) * m.C;
+            } else {
+              const int64_t r = int64_t((i >> 1) + m.pt) * m.P + m.pl;
+              row.dbase[0] = img + (int64_t((i & 1) * 2) * m.plane_pix + r) * m.C;
+              row.dbase[1] = img + (int64_t((i & 1) * 2 + 1) * m.plane_pix + r) * m.C;
+            }
+          }
+          if (MODE != RS_APPLY) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const GradSrc& g = p.g[q];
+              long long* rows = q ? row.s2 : row.s1;
+              int n = 0;
+              if (g.ptr != nullptr) {
+                const int64_t img = int64_t(b) * g.Hs * g.Ws * p.C;
+                const int nm = mirrors(i, p.H, g.fold, m0, m1);
+                n = 1 + nm;
+                rows[0] = img + (int64_t(i + g.oy) * g.Ws + g.ox) * p.C;
+                if (nm > 0) rows[1] = img + (int64_t(m0 + g.oy) * g.Ws + g.ox) * p.C;
+                if (nm > 1) rows[2] = img + (int64_t(m1 + g.oy) * g.Ws + g.ox) * p.C;
+              }
+              if (q) row.n2 = n; else row.n1 = n;
+            }
+          }
+        }
         mbar_wait(&empty_bar[s], ((k / kStages) & 1) ^ 1, 41);
         const int j0 = jc * p.CW;
         const int cw = min(p.CW, p.W - j0);
+        int lo = 0, hi = cw;
+        if (row.dn > 1 || row.n1 > 1 || row.n2 > 1) {
+          hi = 0;
+        } else if (band > 0) {
+          lo = min(cw, max(0, band + 1 - j0));
+          hi = max(lo, min(cw, p.W - 1 - band - j0));
+        }
+        row.i = i; row.j0 = j0; row.cw = cw; row.lo = lo; row.hi = hi;
+        descs[s] = row;
         const uint32_t bytes = uint32_t(cw) * p.C * 2;
-        mbar_arrive_expect_tx(&full_bar[s], bytes * NS);
+        mbar_arrive_expect_tx(&full_bar[s], bytes * NS);  // release: the descriptor is visible with the data
         for (int q = 0; q < NS; ++q) {
           const StreamDesc& d = p.s[q];
           const sg_bf16* src = d.base + int64_t(d.act_index ? ba : b) * d.img_stride + int64_t(i + d.oy) * d.row_stride +
@@ -239,18 +276,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     }
   }
   const uint32_t chunk_bytes = p.chunk_bytes, stage_bytes = NS * p.chunk_bytes;
-  const int W = p.W, C = p.C, CW = p.CW;
-  const int src_band = (MODE == RS_APPLY) ? 0 : max(p.g[0].ptr ? p.g[0].fold : 0, p.g[1].ptr ? p.g[1].fold : 0);
-  const int dst_band = ((MODE == RS_APPLY || MODE == RS_BWD_APPLY) && p.dmap.kind == 0) ? p.dmap.reflect : 0;
-  const int band = max(src_band, dst_band);
+  const int W = p.W, C = p.C;
   const int dC = (MODE == RS_GATHER) ? C : p.dmap.C;
-  const int dkind = (MODE == RS_GATHER) ? 0 : p.dmap.kind;
   const int pshift = 31 - __clz(pstep);  // pstep = 512 / C8 is a power of two
   const uint32_t sbase = smem_u32(smem) + threadIdx.x * 16;
-  DstRow dr;
-  SrcRow e1, e2;
-  e1.n = e2.n = 0;
-  dr.n = 1;
+  sg_bf16* const dst_c0 = p.dst + c0;
+  const ChunkDesc* cd = nullptr;
 
   // one pixel (8 channels) of this thread: `sa` = its vector in stream 0 of the stage, `dptr` = where the lean
   // (no border bookkeeping) result goes, `j` = image column
@@ -261,22 +292,26 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     float y[8], d[8];
     if (MODE == RS_APPLY) {
       unpack8(r0, y);
-      unpack8(r1, d);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float z = fmaf(y[e] - mean[e], scale[e], beta[e]);
-        y[e] = (z > 0.f ? z : z * gneg) + d[e];
+        y[e] = z > 0.f ? z : z * gneg;
+      }
+      if (NS > 1) {
+        unpack8(r1, d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] += d[e];
       }
       if (lean) *reinterpret_cast<uint4*>(dptr) = pack8(y);
-      else dst_store8(dr, p.dmap, j, pack8(y));
+      else dst_store8(cd, p.dmap, dst_c0, j, pack8(y));
     } else if (MODE == RS_GATHER) {
       unpack8(r0, d);
       unpack8(r1, y);
 #pragma unroll
       for (int e = 0; e < 8; ++e) d[e] += y[e];
       if (!lean) {
-        if (src_has_extra(e1, p.g[0], j, W)) src_extra8(e1, p.g[0], j, W, C, d);
-        if (src_has_extra(e2, p.g[1], j, W)) src_extra8(e2, p.g[1], j, W, C, d);
+        if (src_has_extra(cd->n1, p.g[0], j, W)) src_extra8(cd->s1, cd->n1, p.g[0], j, W, C, c0, d);
+        if (src_has_extra(cd->n2, p.g[1], j, W)) src_extra8(cd->s2, cd->n2, p.g[1], j, W, C, c0, d);
       }
       *reinterpret_cast<uint4*>(dptr) = pack8(d);
     } else {
@@ -289,8 +324,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
         for (int e = 0; e < 8; ++e) d[e] += t[e];
       }
       if (!lean) {
-        if (src_has_extra(e1, p.g[0], j, W)) src_extra8(e1, p.g[0], j, W, C, d);
-        if (src_has_extra(e2, p.g[1], j, W)) src_extra8(e2, p.g[1], j, W, C, d);
+        if (src_has_extra(cd->n1, p.g[0], j, W)) src_extra8(cd->s1, cd->n1, p.g[0], j, W, C, c0, d);
+        if (src_has_extra(cd->n2, p.g[1], j, W)) src_extra8(cd->s2, cd->n2, p.g[1], j, W, C, c0, d);
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -308,54 +343,35 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       }
       if (MODE == RS_BWD_APPLY) {
         if (lean) *reinterpret_cast<uint4*>(dptr) = pack8(d);
-        else dst_store8(dr, p.dmap, j, pack8(d));
+        else dst_store8(cd, p.dmap, dst_c0, j, pack8(d));
       }
     }
   };
 
   int k = 0;
-  int cur_i = -1;
-  int i = cbeg / cpr, jc = cbeg - i * cpr;
-  for (int c = cbeg; c < cend; ++c, ++k, jc = (jc + 1 == cpr ? 0 : jc + 1), i += (jc == 0)) {
+  for (int c = cbeg; c < cend; ++c, ++k) {
     const int s = k % kStages;
-    const int j0 = jc * CW;
-    const int cw = min(CW, W - j0);
-    if (i != cur_i) {  // new image row: resolve border rows and base pointers once
-      cur_i = i;
-      if (MODE == RS_APPLY || MODE == RS_BWD_APPLY) dst_row_init(dr, p.dst, p.dmap, b, i, c0);
-      if (MODE != RS_APPLY) {
-        src_row_init(e1, p.g[0], b, i, p.H, C, c0);
-        src_row_init(e2, p.g[1], b, i, p.H, C, c0);
-      }
-    }
-    // pixels [lo, hi) of this chunk need no border bookkeeping
-    int lo = 0, hi = cw;
-    if (dr.n > 1 || e1.n > 1 || e2.n > 1) {
-      hi = 0;
-    } else if (band > 0) {
-      lo = min(cw, max(0, band + 1 - j0));
-      hi = max(lo, min(cw, W - 1 - band - j0));
-    }
+    cd = &descs[s];
+    mbar_wait(&full_bar[s], (k / kStages) & 1, 42);
+    const int4 h0 = *reinterpret_cast<const int4*>(cd);      // i, j0, cw, lo
+    const int hi = cd->hi;
+    const int j0 = h0.y, cw = h0.z, lo = h0.w;
     // this thread visits pixels px0 + t * pstep, t in [0, nt); t in [tlo, thi) are lean
     const int nt = cw > px0 ? ((cw - px0 + pstep - 1) >> pshift) : 0;
     const int tlo = min(nt, lo > px0 ? ((lo - px0 + pstep - 1) >> pshift) : 0);
     const int thi = max(tlo, min(nt, hi > px0 ? ((hi - px0 + pstep - 1) >> pshift) : 0));
     // incremental destination pointer of this thread (element units)
+    int j = j0 + px0;
     sg_bf16* dptr;
     int dstep;
-    if (MODE == RS_GATHER) {
-      dptr = p.dst + ((int64_t(b) * p.H + i) * W + j0 + px0) * C + c0;
-      dstep = pstep * C;
-    } else if (dkind == 0) {
-      dptr = dr.base[0] + (j0 + px0) * dC;
+    if (MODE == RS_GATHER || dkind == 0) {
+      dptr = dst_c0 + cd->dbase[0] + int64_t(j) * dC;
       dstep = pstep * dC;
     } else {  // phase planes: the column parity of this thread is fixed because pstep is even
-      dptr = dr.base[(j0 + px0) & 1] + ((j0 + px0) >> 1) * dC;
+      dptr = dst_c0 + cd->dbase[j & 1] + int64_t(j >> 1) * dC;
       dstep = (pstep >> 1) * dC;
     }
-    mbar_wait(&full_bar[s], (k / kStages) & 1, 42);
     uint32_t sa = sbase + s * stage_bytes;
-    int j = j0 + px0;
     int t = 0;
     for (; t < tlo; ++t, sa += kConsumers * 16, dptr += dstep, j += pstep) pixel(false, sa, dptr, j);
 #pragma unroll 2
