@@ -648,6 +648,100 @@ static int run_mma_rate() {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Experiment: L2 -> SM delivery rate of TMA tiles when the CTAs of a cluster all need the SAME tile
+// (unicast: every CTA loads it; multicast: each CTA loads 1/csz of it for everybody).
+__global__ void __launch_bounds__(64, 1) tma_share_kernel(const __grid_constant__ CUtensorMap tm, int iters, int mode,
+                                                          int ntiles, long long* cycles_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t full[4], empty[4];
+  uint32_t csz, rank, cid;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csz));
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+  constexpr int kRows = 256, kTileBytes = kRows * 128;  // 32 KB tile of 256 rows x 64 bf16
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], mode ? csz : 1); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  cluster_sync_all();
+  const long long t0 = clock64();
+  if (threadIdx.x == 0) {  // producer
+    for (int it = 0; it < iters; ++it) {
+      const int s = it & 3;
+      mbar_wait(&empty[s], ((it >> 2) & 1) ^ 1, 71);
+      const int tile = int((uint64_t(cid) * 977u + uint64_t(it)) % uint64_t(ntiles));
+      mbar_arrive_expect_tx(&full[s], kTileBytes);
+      if (mode == 0) {
+        tma_load_2d(&tm, &full[s], smem + s * kTileBytes, 0, tile * kRows);
+        tma_load_2d(&tm, &full[s], smem + s * kTileBytes + kTileBytes / 2, 0, tile * kRows + kRows / 2);
+      } else {
+        const int rows = kRows / int(csz);  // this CTA's slice, delivered to every CTA of the cluster
+        // box height is fixed at 128 rows by the tensor map: csz == 2 -> one box each
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(smem_u32(smem + s * kTileBytes + int(rank) * rows * 128)), "l"(reinterpret_cast<uint64_t>(&tm)),
+              "r"(smem_u32(&full[s])), "r"(0), "r"(tile * kRows + int(rank) * rows), "h"(uint16_t((1u << csz) - 1))
+            : "memory");
+      }
+    }
+  } else if (threadIdx.x == 32) {  // consumer: nothing to compute, just recycle the stage
+    for (int it = 0; it < iters; ++it) {
+      const int s = it & 3;
+      mbar_wait(&full[s], (it >> 2) & 1, 72);
+      if (mode == 0) mbar_arrive(&empty[s]);
+      else
+        for (uint32_t r = 0; r < csz; ++r) mbar_arrive_cluster(mapa_u32(smem_u32(&empty[s]), r));
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x == 0) cycles_out[blockIdx.x] = clock64() - t0;
+}
+
+static int run_tma_share() {
+  const size_t rows = size_t(1) << 19;  // 64 MB of 128-byte rows: L2 resident
+  uint16_t* d;
+  CK(cudaMalloc(&d, rows * 128));
+  CK(cudaMemset(d, 0, rows * 128));
+  CUtensorMap tm;
+  int r = make_tmap_bf16_2d(&tm, d, 64, rows, 128, 64, 128);
+  if (r) { printf("tmap failed %d\n", r); return 1; }
+  long long* dc;
+  CK(cudaMalloc(&dc, 148 * sizeof(long long)));
+  CK(cudaFuncSetAttribute(tma_share_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768 + 1024));
+  const int iters = 2000, ntiles = int(rows / 256);
+  for (int csz : {1, 2}) {
+    for (int mode : {0, 1}) {
+      if (csz == 1 && mode == 1) continue;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(148);
+      cfg.blockDim = dim3(64);
+      cfg.dynamicSmemBytes = 4 * 32768 + 1024;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      for (int rep = 0; rep < 2; ++rep) {
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tma_share_kernel, tm, iters, mode, ntiles, dc);
+        if (e != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); return 1; }
+        e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("sync failed: %s (watchdog %d)\n", cudaGetErrorString(e), read_tc_watchdog()); return 1; }
+      }
+      std::vector<long long> h(148);
+      CK(cudaMemcpy(h.data(), dc, 148 * sizeof(long long), cudaMemcpyDeviceToHost));
+      double avg = 0;
+      for (auto v : h) avg += double(v);
+      avg /= 148;
+      printf("TMA_SHARE cluster %d %s: %.1f B/clk delivered per SM (%.0f cycles per 32 KB tile), chip %.0f B/clk\n", csz,
+             mode ? "multicast" : "unicast  ", iters * 32768.0 / avg, avg / iters, 148 * iters * 32768.0 / avg);
+    }
+  }
+  return 0;
+}
+
 static int run_tmap_overlap() {
   // Overlapping-window map: rows of 64 bf16 that start every 8 elements (16 B).  Used for the
   // Cin=3 (padded to 8) 7x7 convolution if the driver accepts it.
@@ -714,6 +808,8 @@ int main(int argc, char** argv) {
     rc = run_wgrad_case(2, 6, 20, 128, 64, 64, 3, 3, 0, true);
   } else if (!strcmp(t, "wgrad_res")) {
     rc = run_wgrad_case(8, 64, 128, 256, 256, 256, 3, 8, 10, false);
+  } else if (!strcmp(t, "tma_share")) {
+    rc = run_tma_share();
   } else if (!strcmp(t, "mma_rate_pair")) {
     rc = run_mma_rate_pair();
   } else if (!strcmp(t, "mma_rate")) {
