@@ -220,7 +220,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int a = 0; a + 1 < NA; ++a) {
         named_bar_sync(2 + a, kEpiThreads + kStatThreads);
         const uint8_t* S = smem + a * kTileM * pitch;
-#ifndef SG_EXP_NOSTORE
         {
           const long long off = rowoff[a * kTileM + t];
           if (off >= 0) {
@@ -228,14 +227,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             bulk_commit_group();
           }
         }
-#endif
-#ifndef SG_EXP_NOSTATS
         if (p.stats != nullptr) {
           const int tile = p.stats_t0 + blockIdx.x * NA + a;
           staged_stats(S, pitch, BN, kStatThreads, t, comb0, 4,
                        reinterpret_cast<float2*>(p.stats) + (int64_t(b) * p.stats_T + tile) * p.Cout + n0);
         }
-#endif
       }
       bulk_wait_group_read0();  // shared memory must outlive the reads of the copies
       if (dbg && t == 0) dbg[7] = clock64();
@@ -337,7 +333,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (dbg && et == 0) dbg[4 + a] = clock64();
       }
       named_bar_sync(1, kEpiThreads);  // the last tile is completely staged
-#ifndef SG_EXP_NOSTORE
       if (half == 0) {
         const long long off = rowoff[(NA - 1) * kTileM + row];
         if (off >= 0) {
@@ -346,15 +341,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           bulk_commit_group();
         }
       }
-#endif
-#ifndef SG_EXP_NOSTATS
       if (has_stats) {
         const int tile = p.stats_t0 + blockIdx.x * NA + (NA - 1);
         staged_stats(smem + (NA - 1) * kTileM * pitch, pitch, BN, kEpiThreads, et,
                      reinterpret_cast<float2*>(aux + 2048), 1,
                      reinterpret_cast<float2*>(p.stats) + (int64_t(b) * p.stats_T + tile) * p.Cout + n0);
       }
-#endif
       bulk_wait_group_read0();
       tc_fence_before();
     } else
@@ -397,17 +389,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             v[2 * e2 + 1] = __uint_as_float(pk[e2] & 0xffff0000u);
           }
         }
-#ifndef SG_EXP_NOSTATS
         if (has_stats) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) tsm[(c0 + e) * 129 + row] = v[e] * msk;
         }
-#endif
-#ifdef SG_EXP_NOSTORE
-        if (valid && pk[0] == 0x12345678u) {
-#else
         if (valid) {
-#endif
           if (vec_ok && nb + 32 <= p.Cout) {
             uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + obase + nb);
 #pragma unroll
@@ -425,7 +411,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
-#ifndef SG_EXP_NOSTATS
       if (has_stats) {
         named_bar_sync(1, kEpiThreads);
         for (int c = et; c < BN; c += kEpiThreads) {
@@ -445,7 +430,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (a + 1 < NA) named_bar_sync(1, kEpiThreads);  // tsm is rewritten by the next accumulator
       }
-#endif
       if (dbg && et == 0) dbg[4 + a] = clock64();
     }
     tc_fence_before();
