@@ -665,6 +665,7 @@ void Engine::in_apply(Net& n, int li, sg_bf16* dst, const FrameMap& dmap, const 
   memset(&p, 0, sizeof(p));
   p.Y = l.Y; p.B = l.nb; p.H = l.Hout; p.W = l.Wout; p.C = l.Cout;
   p.stats = l.stats; p.gamma = n.p + n.T[l.ti_g].offset; p.beta = n.p + n.T[l.ti_be].offset;
+  p.stats_part = l.stats_part; p.stats_T = l.stats_T; p.stats_out = l.stats;  // finalize fused into the apply pass
   p.eps = cfg.in_eps; p.act = l.act; p.act_alpha = l.alpha;
   p.res = res;
   if (rmap) p.rmap = *rmap;
@@ -699,10 +700,10 @@ void Engine::in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb
   p.stats = l.stats; p.gamma = n.p + n.T[l.ti_g].offset; p.beta = n.p + n.T[l.ti_be].offset;
   p.eps = cfg.in_eps; p.act = l.act; p.act_alpha = l.alpha;
   p.g1 = g1; p.g2 = g2; p.sums = l.bsums; p.dst = l.dY; p.dmap = l.dymap;
+  p.dgamma = n.g + n.T[l.ti_g].offset; p.dbeta = n.g + n.T[l.ti_be].offset; p.nb_param = nb_param;
   launch_in_bwd_reduce(p, st);
-  launch_in_bwd_apply(p, st);
-  launch_in_param_grad(l.bsums, nb_param, l.Cout, n.g + n.T[l.ti_g].offset, n.g + n.T[l.ti_be].offset, st);
-  nlaunch += 3;
+  launch_in_bwd_apply(p, st);  // also writes dgamma / dbeta
+  nlaunch += 2;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -720,7 +721,6 @@ int Engine::gen_forward(const float* real_A, float* fake_out) {
     if ((r = run_conv_list(l.fwd))) return r;
     if (timed) cudaEventRecord(prof_ev[prof_used++], st);
     if (!l.has_norm) continue;
-    launch_stats_finalize(l.stats_part, l.nb, l.stats_T, l.Cout, l.stats, st); ++nlaunch;
     Layer& nx = G.L[li + 1];
     const bool block_b = in_block && ((li - 3) & 1) == 1;
     if (block_b) in_apply(G, li, nx.X, nx.xmap, G.L[li - 1].X, &G.L[li - 1].xmap);  // y + x (module.py:217)
@@ -743,7 +743,6 @@ int Engine::disc_forward_2b(const float* first, const float* second, int nimg_ea
     Layer& l = D.L[li];
     if ((r = run_conv_list(l.fwd))) return r;
     if (l.has_norm) {
-      launch_stats_finalize(l.stats_part, l.nb, l.stats_T, l.Cout, l.stats, st); ++nlaunch;
       in_apply(D, li, D.L[li + 1].X, D.L[li + 1].xmap, nullptr, nullptr);
     }
   }

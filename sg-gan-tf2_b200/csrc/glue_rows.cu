@@ -55,6 +55,12 @@ struct RowStreamParams {
   int act;
   float alpha;
   float* sums;   // in_bwd: [B][C][2]
+  const float* stats_part;  // in_apply: per-tile partials to finalize in the kernel (or null), see InApplyParams
+  int stats_T;
+  float* stats_out;
+  float* dgamma;  // in_bwd apply: affine-parameter gradients written by block (0, 0) (or null)
+  float* dbeta;
+  int nb_param;
   GradSrc g[2];  // fold information of the gradient streams (extras are read directly from global)
   sg_bf16* dst;  // frame (apply modes) or plain [B][H][W][C] (gather)
   FrameMap dmap;
@@ -250,6 +256,48 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   const int c0 = cg * 8;
   const int px0 = threadIdx.x / C8, pstep = kConsumers / C8;  // pstep is even (C8 <= 64)
   const float n = float(p.H * p.W);
+  // fused statistics finalize: the per-tile partials of the producing convolution are added in a fixed order by
+  // all consumers of the block (slices of the tile range per channel, then the slices) while the producer's first
+  // chunks are in flight; block 0 of the image also publishes the result for the backward pass
+  const float2* fin = nullptr;
+  if (MODE == RS_APPLY && p.stats_part != nullptr) {
+    float2* st_part = reinterpret_cast<float2*>(smem + kPipeBytes);  // [slices][C]
+    float2* st_fin = st_part + kConsumers;                           // [C]
+    const int Cc = p.C, slices = kConsumers / Cc, sl = threadIdx.x / Cc, c = threadIdx.x - sl * Cc;
+    const int T = p.stats_T, per = (T + slices - 1) / slices, t0 = sl * per, t1 = min(T, t0 + per);
+    const float2* part = reinterpret_cast<const float2*>(p.stats_part) + int64_t(ba) * T * Cc + c;
+    float s1 = 0.f, s2 = 0.f;
+    for (int t = t0; t < t1; ++t) {
+      const float2 v = __ldg(part + int64_t(t) * Cc);
+      s1 += v.x;
+      s2 += v.y;
+    }
+    st_part[sl * Cc + c] = make_float2(s1, s2);
+    named_bar_sync(3, kConsumers);
+    if (int(threadIdx.x) < Cc) {
+      float2 acc = st_part[threadIdx.x];
+      for (int q = 1; q < slices; ++q) {
+        const float2 o = st_part[q * Cc + threadIdx.x];
+        acc.x += o.x; acc.y += o.y;
+      }
+      st_fin[threadIdx.x] = acc;
+      if (blockIdx.x == 0) reinterpret_cast<float2*>(p.stats_out)[int64_t(ba) * Cc + threadIdx.x] = acc;
+    }
+    named_bar_sync(3, kConsumers);
+    fin = st_fin;
+  }
+  if (MODE == RS_BWD_APPLY && p.dgamma != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
+    for (int c = threadIdx.x; c < p.C; c += kConsumers) {
+      float g = 0.f, be = 0.f;
+      for (int bb = 0; bb < p.nb_param; ++bb) {
+        const float2 q = reinterpret_cast<const float2*>(p.sums)[int64_t(bb) * p.C + c];
+        be += q.x;
+        g += q.y;
+      }
+      p.dgamma[c] = g;
+      p.dbeta[c] = be;
+    }
+  }
   // activation as a slope for the non-positive side: relu 0, leaky alpha, identity 1 (tanh never reaches the glue)
   const float gneg = p.act == SG_ACT_RELU ? 0.f : (p.act == SG_ACT_LRELU ? p.alpha : 1.f);
   float mean[8], rstd[8], scale[8], beta[8], a1[8], a2[8];
@@ -258,8 +306,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     for (int e = 0; e < 8; ++e) {
       const int c = c0 + e;
       float mu = 0.f, rs = 1.f;
-      if (p.stats != nullptr) {
-        const float2 st = reinterpret_cast<const float2*>(p.stats)[int64_t(ba) * p.C + c];
+      if (fin != nullptr || p.stats != nullptr) {
+        const float2 st = fin != nullptr ? fin[c] : reinterpret_cast<const float2*>(p.stats)[int64_t(ba) * p.C + c];
         mu = st.x / n;
         rs = rsqrtf(fmaxf(st.y / n - mu * mu, 0.f) + p.eps);
       }
@@ -420,7 +468,7 @@ static void launch_row_stream(RowStreamParams& p, cudaStream_t st) {
   p.CW = kPipeBytes / (kStages * p.ns) / (p.C * 2);
   if (p.CW > p.W) p.CW = p.W;
   p.chunk_bytes = p.CW * p.C * 2;
-  const size_t smem = size_t(kPipeBytes) + 128;
+  const size_t smem = size_t(kPipeBytes) + 128 + 2 * kConsumers * sizeof(float2);  // + staged statistics
   // one persistent block per SM; blocks never span images (per-image statistics)
   int gx = 148 / p.B;
   if (gx < 1) gx = 1;
@@ -460,6 +508,7 @@ void launch_in_apply(const InApplyParams& a, cudaStream_t st) {
   }
   p.s[2] = null_stream();
   p.stats = a.stats; p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.act = a.act; p.alpha = a.act_alpha;
+  p.stats_part = a.stats_part; p.stats_T = a.stats_T; p.stats_out = a.stats_out;
   p.dst = a.dst; p.dmap = a.dmap;
   launch_row_stream<RS_APPLY>(p, st);
 }
@@ -472,6 +521,7 @@ static void bwd_params(const InBwdParams& a, RowStreamParams& p) {
   p.g[0] = a.g1; p.g[1] = a.g2;
   p.stats = a.stats; p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.act = a.act; p.alpha = a.act_alpha;
   p.sums = a.sums; p.dst = a.dst; p.dmap = a.dmap;
+  p.dgamma = a.dgamma; p.dbeta = a.dbeta; p.nb_param = a.nb_param;
 }
 void launch_in_bwd_reduce(const InBwdParams& a, cudaStream_t st) {
   RowStreamParams p = {};

@@ -153,6 +153,11 @@ struct InApplyParams {
   const sg_bf16* Y;  // [B][H][W][C] raw conv output
   int B, H, W, C;
   const float* stats;  // [B][C][2]
+  // optional: per-tile partial statistics [B][stats_T][C][2] of the producing convolution; the kernel adds them in
+  // a fixed order itself (and writes the result to `stats_out` for the backward pass) instead of a separate launch
+  const float* stats_part;
+  int stats_T;
+  float* stats_out;
   const float* gamma;
   const float* beta;
   float eps;
@@ -183,4 +188,8 @@ struct InBwdParams {
   float* sums;  // [B][C][2]
   sg_bf16* dst;
   FrameMap dmap;
+  // optional (apply pass): dgamma[c] = sum_b sums[b][c].y, dbeta[c] = sum_b sums[b][c].x over the first nb_param images
+  float* dgamma;
+  float* dbeta;
+  int nb_param;
 };
