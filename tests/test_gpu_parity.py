@@ -463,3 +463,15 @@ def test_tc_probe_pair_kernel():
         out = subprocess.run([exe, case], capture_output=True, text=True, timeout=300, env=env)
         assert out.returncode == 0 and "CTA-pair persistent kernel" in out.stdout and ("RESULT %s PASS" % case) in out.stdout, \
             out.stdout[-2000:]
+
+
+def test_config_sweep():
+    """Batch sizes, resolutions (incl. non powers of two) and class counts around the kernel-selection thresholds:
+    losses within 1e-2, generator output within 3e-2, gradient direction (cosine) > 0.9 against the oracle;
+    a resolution too small for the discriminator stack is rejected with an error."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu", "config_sweep.py")], capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0 and "DEVIATES" not in out.stdout and "rejected loudly" in out.stdout, \
+        out.stdout[-3000:] + out.stderr[-1000:]
