@@ -72,7 +72,15 @@ int sggan_create(const sggan_config* cfg, void* workspace, size_t workspace_byte
   return 0;
 }
 
-void sggan_destroy(sggan_handle* h) { delete h; }
+void sggan_destroy(sggan_handle* h) {
+  if (h == nullptr) return;
+  Engine& e = h->e;
+  if (e.st2) cudaStreamDestroy(e.st2);
+  if (e.ev_fork) cudaEventDestroy(e.ev_fork);
+  if (e.ev_join) cudaEventDestroy(e.ev_join);
+  for (auto ev : e.prof_ev) cudaEventDestroy(ev);
+  delete h;
+}
 
 
 int sggan_num_tensors(const sggan_handle* h, int net) { return int(net_of(h, net).T.size()); }

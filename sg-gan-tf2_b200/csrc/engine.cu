@@ -9,6 +9,8 @@
 //     borders), so zero borders / pitch slack stay zero for the life of the handle.
 #include "engine.h"
 
+#include <cstdlib>
+
 #include <math.h>
 #include <string.h>
 
@@ -543,6 +545,17 @@ int Engine::prepare_layer(Net& n, int li) {
 
 int Engine::build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t stream, bool dry_run, size_t* need) {
   cfg = c; st = stream; dry = dry_run; step = 0; nlaunch = 0; weights_ready = false;
+  if (!dry_run && st2 == nullptr) {
+    const char* env = getenv("SGGAN_SIDE_STREAM");
+    if (!(env && env[0] == '0')) {
+      if (cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        err = "side stream creation failed";
+        return SGGAN_E_CUDA;
+      }
+    }
+  }
   if (c.gf_dim != 64 || c.df_dim != 64) { err = "gf_dim and df_dim must be 64 (module.py:221,274)"; return SGGAN_E_INVALID; }
   if (c.batch < 1 || c.image_height % 4 || c.image_width % 4 || c.n_blocks < 1 || c.segment_class < 1 ||
       c.segment_class > 64) { err = "unsupported batch / image size / class count"; return SGGAN_E_INVALID; }
@@ -646,17 +659,31 @@ int Engine::run_conv_list(const std::vector<ConvGemmLaunch>& v) {
 }
 
 int Engine::run_wgrad(Layer& l, Net& n) {
+  cudaStream_t ws = st;
+  if (st2 != nullptr) {  // fork: everything the weight gradient reads has been enqueued on `st` by now
+    cudaEventRecord(ev_fork, st);
+    cudaStreamWaitEvent(st2, ev_fork, 0);
+    ws = st2;
+    side_used = true;
+  }
   for (const auto& L : l.wgrad) {
-    int r = run_wgrad_gemm(L, st);
+    int r = run_wgrad_gemm(L, ws);
     ++nlaunch;
     if (r) { err = "wgrad launch failed " + std::to_string(r); return SGGAN_E_CUDA; }
-    if (L.p.part != nullptr) { launch_wgrad_reduce(L, int64_t(L.p.ntaps) * L.p.dw_tap_stride, st); ++nlaunch; }
+    if (L.p.part != nullptr) { launch_wgrad_reduce(L, int64_t(L.p.ntaps) * L.p.dw_tap_stride, ws); ++nlaunch; }
   }
   if (l.unpack_mode >= 0) {
-    launch_unpack_wgrad(l.wscratch, n.g + n.T[l.ti_w].offset, l.unpack_mode, l.k, l.k, l.Cin, l.Cout, 64, st);
+    launch_unpack_wgrad(l.wscratch, n.g + n.T[l.ti_w].offset, l.unpack_mode, l.k, l.k, l.Cin, l.Cout, 64, ws);
     ++nlaunch;
   }
   return 0;
+}
+
+void Engine::join_side() {
+  if (!side_used) return;
+  cudaEventRecord(ev_join, st2);
+  cudaStreamWaitEvent(st, ev_join, 0);
+  side_used = false;
 }
 
 void Engine::in_apply(Net& n, int li, sg_bf16* dst, const FrameMap& dmap, const sg_bf16* res, const FrameMap* rmap) {
@@ -800,6 +827,7 @@ int Engine::step_fwd_bwd_d(const float* real_A, const float* seg_A, const float*
     if ((r = run_wgrad(l, D))) return r;
     if ((r = run_conv_list(l.dgrad))) return r;
   }
+  join_side();
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
 
@@ -853,6 +881,7 @@ int Engine::step_bwd_g() {
       cur ^= 1;
     }
   }
+  join_side();
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
 

@@ -74,6 +74,12 @@ struct Arena {
 struct Engine {
   sggan_config cfg;
   cudaStream_t st;
+  // weight-gradient GEMMs run on a side stream: they only need the layer's input frame and dY, so they fill the SMs
+  // that the dgrad / norm-backward chain on `st` leaves idle at its wave tails; joined at the end of each phase
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool side_used = false;
+  void join_side();
   bool dry;
   Net G, D;
   int Hd, Wd, Ho, Wo;  // D logit grid and broadcast output grid
