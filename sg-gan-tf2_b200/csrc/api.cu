@@ -139,9 +139,11 @@ int sggan_step_adam(sggan_handle* h, int net) {
 }
 int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask, float* losses_out) {
   FWD_ERR(h->e.step_fwd_bwd_d(real_A, seg_A, mask, losses_out));
+  // D's gradients are final: its Adam + weight re-pack (HBM-bound) run on the side stream underneath the
+  // generator backward (tensor-bound), which joins the side stream when it ends
+  FWD_ERR(h->e.step_adam(SGGAN_NET_D, true));
   FWD_ERR(h->e.step_bwd_g());
   FWD_ERR(h->e.step_adam(SGGAN_NET_G));
-  FWD_ERR(h->e.step_adam(SGGAN_NET_D));
   h->e.step += 1;
   return 0;
 }

@@ -611,9 +611,9 @@ int Engine::build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t
 }
 
 // ---------------------------------------------------------------------------------------------
-int Engine::pack_weights(int net) {
+int Engine::pack_weights(int net, cudaStream_t s) {
   // one launch per net: the job table (one PackParams per weight slab) was uploaded by build()
-  launch_pack_weights_batch(pack_jobs[net], pack_starts[net], pack_njobs[net], pack_blocks[net], st);
+  launch_pack_weights_batch(pack_jobs[net], pack_starts[net], pack_njobs[net], pack_blocks[net], s ? s : st);
   ++nlaunch;
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
@@ -885,15 +885,22 @@ int Engine::step_bwd_g() {
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
 
-int Engine::step_adam(int net) {
+int Engine::step_adam(int net, bool on_side_stream) {
   Net& n = net == SGGAN_NET_G ? G : D;
+  cudaStream_t s = st;
+  if (on_side_stream && st2 != nullptr) {  // the caller guarantees this net's gradients are final on `st`
+    cudaEventRecord(ev_fork, st);
+    cudaStreamWaitEvent(st2, ev_fork, 0);
+    s = st2;
+    side_used = true;
+  }
   const int64_t t = step + 1;
   const float alpha_t = float(double(cfg.lr) * sqrt(1.0 - pow(double(cfg.beta2), double(t))) /
                               (1.0 - pow(double(cfg.beta1), double(t))));
   launch_adam(n.p, n.g, n.m, n.v, n.nparams, alpha_t, cfg.beta1, cfg.beta2, cfg.adam_eps,
-              1.f / float(cfg.world_size > 0 ? cfg.world_size : 1), st);
+              1.f / float(cfg.world_size > 0 ? cfg.world_size : 1), s);
   ++nlaunch;
-  return pack_weights(net);
+  return pack_weights(net, s);
 }
 
 }  // namespace sggan

@@ -103,14 +103,14 @@ struct Engine {
   bool prof_on = false;
 
   int build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t stream, bool dry_run, size_t* need);
-  int pack_weights(int net);
+  int pack_weights(int net, cudaStream_t s = nullptr);
   int upload_pack_jobs(int net);
   int gen_forward(const float* real_A, float* fake_out);
   int disc_forward_2b(const float* real_img, const float* fake_img, int nimg_each);
   int disc_forward_user(const float* x, const float* mask, float* logits_out);
   int step_fwd_bwd_d(const float* real_A, const float* seg_A, const float* mask, float* losses_out);
   int step_bwd_g();
-  int step_adam(int net);
+  int step_adam(int net, bool on_side_stream = false);
 
  private:
   int build_net_g();
