@@ -718,7 +718,8 @@ static GradSrc no_src() {
 }
 
 // instance-norm backward of layer li: gradient sources g1 (+ g2) w.r.t. its post-activation output
-void Engine::in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb_act, int act_wrap, int nb_param) {
+void Engine::in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb_act, int act_wrap, int nb_param,
+                    sg_bf16* gather_dst, int gH, int gW) {
   Layer& l = n.L[li];
   InBwdParams p;
   memset(&p, 0, sizeof(p));
@@ -728,7 +729,12 @@ void Engine::in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb
   p.eps = cfg.in_eps; p.act = l.act; p.act_alpha = l.alpha;
   p.g1 = g1; p.g2 = g2; p.sums = l.bsums; p.dst = l.dY; p.dmap = l.dymap;
   p.dgamma = n.g + n.T[l.ti_g].offset; p.dbeta = n.g + n.T[l.ti_be].offset; p.nb_param = nb_param;
+  p.gather_dst = gather_dst;  // reduce pass also materialises g1 + g2 (the residual-stream gradient) ...
   launch_in_bwd_reduce(p, st);
+  if (gather_dst != nullptr) {  // ... which is then the single source of the apply pass
+    p.g1.ptr = gather_dst; p.g1.f32 = 0; p.g1.Hs = gH; p.g1.Ws = gW; p.g1.oy = 0; p.g1.ox = 0; p.g1.fold = 0;
+    memset(&p.g2, 0, sizeof(p.g2));
+  }
   launch_in_bwd_apply(p, st);  // also writes dgamma / dbeta
   nlaunch += 2;
 }
@@ -836,6 +842,7 @@ int Engine::step_bwd_g() {
   int r;
   const int nl = int(G.L.size());
   Layer& lo = G.L[nl - 1];
+  static const bool fuse_gather = []() { const char* e = getenv("SGGAN_FUSE_GATHER"); return !(e && e[0] == '0'); }();
   FakeGradParams fg;
   memset(&fg, 0, sizeof(fg));
   fg.fake = fake; fg.dD = dD; fg.B = B; fg.H = H; fg.W = W; fg.loss = loss; fg.dst = lo.dY; fg.dmap = lo.dymap;
@@ -862,23 +869,36 @@ int Engine::step_bwd_g() {
   int cur = 0;  // resG ping-pong index holding the gradient w.r.t. the current block output
   const Layer& rb = G.L[first_blk];
   GradSrc gres = no_src();
+  GradSrc add = no_src();  // pending G_{k-1} = G_k + fold(dX of conv_a): materialised by the NEXT norm-backward reduce
   for (int li = nl - 2; li >= 0; --li) {
     Layer& l = G.L[li];
     Layer& up = G.L[li + 1];
     const bool in_blocks = li >= first_blk && li <= last_b;
     const bool is_b = in_blocks && ((li - first_blk) & 1) == 1;
     if (li == last_b) gres = dx_src(up);                                // grad w.r.t. r_n = dX of the first deconv
-    if (is_b) in_bwd(G, li, gres, no_src(), l.nb, 0, l.nb);            // IN after conv_b: no activation, dz = G_k
-    else if (li == first_blk - 1) in_bwd(G, li, gres, no_src(), l.nb, 0, l.nb);  // c3: dz = G_0
-    else in_bwd(G, li, dx_src(up), no_src(), l.nb, 0, l.nb);
+    if (is_b || li == first_blk - 1) {  // IN after conv_b (no activation, dz = G_k) / c3 (dz = G_0)
+      if (add.ptr != nullptr) {
+        in_bwd(G, li, gres, add, l.nb, 0, l.nb, resG[cur], rb.Hin, rb.Win);
+        gres = plain_src(resG[cur], rb.Hin, rb.Win);
+        cur ^= 1;
+        add = no_src();
+      } else {
+        in_bwd(G, li, gres, no_src(), l.nb, 0, l.nb);
+      }
+    } else {
+      in_bwd(G, li, dx_src(up), no_src(), l.nb, 0, l.nb);
+    }
     if ((r = run_wgrad(l, G))) return r;
     if (li == 0) break;
     if ((r = run_conv_list(l.dgrad))) return r;
     if (in_blocks && !is_b) {
-      // G_{k-1} = G_k + fold(dX of conv_a)
-      launch_grad_gather(gres, dx_src(l), B, rb.Hin, rb.Win, rb.Cin, resG[cur], st); ++nlaunch;
-      gres = plain_src(resG[cur], rb.Hin, rb.Win);
-      cur ^= 1;
+      if (fuse_gather) {
+        add = dx_src(l);
+      } else {  // separate gather launch: G_{k-1} = G_k + fold(dX of conv_a)
+        launch_grad_gather(gres, dx_src(l), B, rb.Hin, rb.Win, rb.Cin, resG[cur], st); ++nlaunch;
+        gres = plain_src(resG[cur], rb.Hin, rb.Win);
+        cur ^= 1;
+      }
     }
   }
   join_side();

@@ -120,7 +120,8 @@ struct Engine {
   int run_conv_list(const std::vector<ConvGemmLaunch>& v);
   int run_wgrad(Layer& l, Net& n);
   void in_apply(Net& n, int li, sg_bf16* dst, const FrameMap& dmap, const sg_bf16* res, const FrameMap* rmap);
-  void in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb_act, int act_wrap, int nb_param);
+  void in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb_act, int act_wrap, int nb_param,
+              sg_bf16* gather_dst = nullptr, int gH = 0, int gW = 0);
   GradSrc dx_src(const Layer& l) const;
   const float *real_A_, *seg_A_, *mask_;
   float* losses_out_;

@@ -58,6 +58,7 @@ struct RowStreamParams {
   const float* stats_part;  // in_apply: per-tile partials to finalize in the kernel (or null), see InApplyParams
   int stats_T;
   float* stats_out;
+  sg_bf16* gather_dst;  // in_bwd reduce: also store g1 + g2 (folded) as plain [B][H][W][C] (or null)
   float* dgamma;  // in_bwd apply: affine-parameter gradients written by block (0, 0) (or null)
   float* dbeta;
   int nb_param;
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   // each block owns a contiguous range of chunks, so consecutive chunks mostly share their image row
   const int cper = (nchunks + gridDim.x - 1) / gridDim.x;
   const int cbeg = blockIdx.x * cper, cend = min(nchunks, cbeg + cper);
-  const int dkind = (MODE == RS_GATHER) ? 0 : p.dmap.kind;
+  const int dkind = (MODE == RS_GATHER || MODE == RS_BWD_REDUCE) ? 0 : p.dmap.kind;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
           cur_i = i;
           row.dn = 1; row.n1 = row.n2 = 0;
           int m0, m1;
-          if (MODE == RS_GATHER) {
+          if (MODE == RS_GATHER || (MODE == RS_BWD_REDUCE && p.gather_dst != nullptr)) {
             row.dbase[0] = (int64_t(b) * p.H + i) * p.W * p.C;
           } else if (MODE == RS_APPLY || MODE == RS_BWD_APPLY) {
             const FrameMap& m = p.dmap;
@@ -325,10 +326,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   }
   const uint32_t chunk_bytes = p.chunk_bytes, stage_bytes = NS * p.chunk_bytes;
   const int W = p.W, C = p.C;
-  const int dC = (MODE == RS_GATHER) ? C : p.dmap.C;
+  const int dC = (MODE == RS_GATHER || MODE == RS_BWD_REDUCE) ? C : p.dmap.C;
   const int pshift = 31 - __clz(pstep);  // pstep = 512 / C8 is a power of two
   const uint32_t sbase = smem_u32(smem) + threadIdx.x * 16;
-  sg_bf16* const dst_c0 = p.dst + c0;
+  const bool gather = MODE == RS_BWD_REDUCE && p.gather_dst != nullptr;
+  sg_bf16* const dst_c0 = (gather ? p.gather_dst : p.dst) + c0;
   const ChunkDesc* cd = nullptr;
 
   // one pixel (8 channels) of this thread: `sa` = its vector in stream 0 of the stage, `dptr` = where the lean
@@ -375,6 +377,13 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
         if (src_has_extra(cd->n1, p.g[0], j, W)) src_extra8(cd->s1, cd->n1, p.g[0], j, W, C, c0, d);
         if (src_has_extra(cd->n2, p.g[1], j, W)) src_extra8(cd->s2, cd->n2, p.g[1], j, W, C, c0, d);
       }
+      if (MODE == RS_BWD_REDUCE && gather) {
+        // fused residual-gradient gather: store the sum, and take the statistics over the value AS STORED so that
+        // the apply pass (which reads it back) stays exactly consistent with these sums
+        const uint4 w = pack8(d);
+        *reinterpret_cast<uint4*>(dptr) = w;
+        unpack8(w, d);
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         // zpre = (y - mean)*scale + beta;  xhat = (y - mean)*rstd.  The apply form keeps a single-pixel norm
@@ -412,7 +421,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     int j = j0 + px0;
     sg_bf16* dptr;
     int dstep;
-    if (MODE == RS_GATHER || dkind == 0) {
+    if (MODE == RS_GATHER || MODE == RS_BWD_REDUCE || dkind == 0) {
       dptr = dst_c0 + cd->dbase[0] + int64_t(j) * dC;
       dstep = pstep * dC;
     } else {  // phase planes: the column parity of this thread is fixed because pstep is even
@@ -522,6 +531,7 @@ static void bwd_params(const InBwdParams& a, RowStreamParams& p) {
   p.stats = a.stats; p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.act = a.act; p.alpha = a.act_alpha;
   p.sums = a.sums; p.dst = a.dst; p.dmap = a.dmap;
   p.dgamma = a.dgamma; p.dbeta = a.dbeta; p.nb_param = a.nb_param;
+  p.gather_dst = a.gather_dst;
 }
 void launch_in_bwd_reduce(const InBwdParams& a, cudaStream_t st) {
   RowStreamParams p = {};

@@ -188,6 +188,9 @@ struct InBwdParams {
   float* sums;  // [B][C][2]
   sg_bf16* dst;
   FrameMap dmap;
+  // optional (reduce pass): also store the summed, border-folded gradient g1 + g2 as plain [B][H][W][C] bf16 -- the
+  // residual-stream gradient gather of the generator blocks, fused with the statistics of the layer that reads it
+  sg_bf16* gather_dst;
   // optional (apply pass): dgamma[c] = sum_b sums[b][c].y, dbeta[c] = sum_b sums[b][c].x over the first nb_param images
   float* dgamma;
   float* dbeta;
