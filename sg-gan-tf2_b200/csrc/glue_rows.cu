@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       a1[e] = a2[e] = 0.f;
       if (MODE == RS_BWD_APPLY) {
         const float2 q = reinterpret_cast<const float2*>(p.sums)[int64_t(b) * p.C + c];
-        a1[e] = q.x / n;  // mean of dzh
-        a2[e] = q.y / n;  // mean of dzh * xhat
+        a1[e] = q.x / n;        // mean of dzh
+        a2[e] = q.y / n * rs;   // mean of dzh * xhat, times rstd (applied to y - mean directly)
       }
     }
   }
@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   const int pshift = 31 - __clz(pstep);  // pstep = 512 / C8 is a power of two
   const uint32_t sbase = smem_u32(smem) + threadIdx.x * 16;
   const bool gather = MODE == RS_BWD_REDUCE && p.gather_dst != nullptr;
+  const bool has_act = gneg != 1.f;
   sg_bf16* const dst_c0 = (gather ? p.gather_dst : p.dst) + c0;
   const ChunkDesc* cd = nullptr;
 
@@ -384,18 +385,33 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
         *reinterpret_cast<uint4*>(dptr) = w;
         unpack8(w, d);
       }
+      // zpre = (y - mean)*scale + beta;  xhat = (y - mean)*rstd.  rstd is folded into the channel constants: the
+      // reduce pass accumulates sum(dzh * (y - mean)) and scales it once at the end, the apply pass gets
+      // a2 = mean(dzh * xhat) * rstd.  The apply form keeps a single-pixel norm (y == mean, dzh == a1)
+      // back-propagating exactly zero, as the reference does at 128x128 (Appendix B).  Layers without an
+      // activation (gneg == 1: the second norm of every residual block) skip the mask altogether.
+      if (has_act) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        // zpre = (y - mean)*scale + beta;  xhat = (y - mean)*rstd.  The apply form keeps a single-pixel norm
-        // (xhat == 0, dzh == m1) back-propagating exactly zero, as the reference does at 128x128 (Appendix B).
-        const float yc = y[e] - mean[e];
-        const float dz = fmaf(yc, scale[e], beta[e]) > 0.f ? d[e] : d[e] * gneg;
-        const float xh = yc * rstd[e];
-        if (MODE == RS_BWD_APPLY) {
-          d[e] = scale[e] * ((dz - a1[e]) - xh * a2[e]);
-        } else {
-          a1[e] += dz;
-          a2[e] = fmaf(dz, xh, a2[e]);
+        for (int e = 0; e < 8; ++e) {
+          const float yc = y[e] - mean[e];
+          const float dz = fmaf(yc, scale[e], beta[e]) > 0.f ? d[e] : d[e] * gneg;
+          if (MODE == RS_BWD_APPLY) {
+            d[e] = scale[e] * ((dz - a1[e]) - yc * a2[e]);
+          } else {
+            a1[e] += dz;
+            a2[e] = fmaf(dz, yc, a2[e]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float yc = y[e] - mean[e];
+          if (MODE == RS_BWD_APPLY) {
+            d[e] = scale[e] * ((d[e] - a1[e]) - yc * a2[e]);
+          } else {
+            a1[e] += d[e];
+            a2[e] = fmaf(d[e], yc, a2[e]);
+          }
         }
       }
       if (MODE == RS_BWD_APPLY) {
@@ -446,7 +462,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       red[((px0 * 8 + e) * 2 + 0) * C8 + cg] = a1[e];
-      red[((px0 * 8 + e) * 2 + 1) * C8 + cg] = a2[e];
+      red[((px0 * 8 + e) * 2 + 1) * C8 + cg] = a2[e] * rstd[e];  // sum(dzh * (y - mean)) -> sum(dzh * xhat)
     }
     named_bar_sync(2, kConsumers);
     for (int t = threadIdx.x; t < 2 * C; t += kConsumers) {
