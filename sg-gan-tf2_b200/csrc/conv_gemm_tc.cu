@@ -137,6 +137,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) tmem_alloc(&tmem_base_sh, tmem_cols);
+  pdl_launch_dependents();
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only below
   for (int t = threadIdx.x; t < 256; t += kConvThreads)
     sbias[t] = (p.bias != nullptr && t < BN && n0 + t < p.Cout) ? __ldg(p.bias + n0 + t) : 0.f;
   tc_fence_before();
@@ -744,6 +746,8 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmW);
   }
   if (warp == 1) tmem_alloc(&tmem_base_sh, 512);
+  pdl_launch_dependents();
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -993,6 +997,8 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     tma_prefetch_desc(&tmY);
   }
   if (warp == 1) tmem_alloc(&tmem_base_sh, tmem_cols);
+  pdl_launch_dependents();
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1236,15 +1242,14 @@ int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
   }
   if (L.swap) {
     const int tiles = L.T256 * L.p.B * L.swap_nblk;
-    conv_gemm_swap_kernel<<<dim3(tiles < 148 ? tiles : 148), kConvThreads, L.swap_smem, st>>>(
-        L.tmA, L.tmA8, L.tmBh, L.p, L.T256, L.swap_pstages, L.swap_wstages, L.swap_nblk);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_kernel_pdl(conv_gemm_swap_kernel, dim3(tiles < 148 ? tiles : 148), dim3(kConvThreads), L.swap_smem,
+                                      st, pdl_enabled(), L.tmA, L.tmA8, L.tmBh, L.p, L.T256, L.swap_pstages,
+                                      L.swap_wstages, L.swap_nblk);
     return e == cudaSuccess ? 0 : -4200 - int(e);
   }
   dim3 grid(L.grid_x, L.grid_y, L.grid_z);
-  conv_gemm_tc_kernel<<<grid, kConvThreads, L.smem, st>>>(L.tmA, L.tmA8, L.tmB, L.p, L.sa_stages, L.sb_stages,
-                                                          L.tmem_cols);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_kernel_pdl(conv_gemm_tc_kernel, grid, dim3(kConvThreads), L.smem, st, pdl_enabled(), L.tmA, L.tmA8,
+                                    L.tmB, L.p, L.sa_stages, L.sb_stages, L.tmem_cols);
   return e == cudaSuccess ? 0 : -4000 - int(e);
 }
 
@@ -1286,13 +1291,15 @@ int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L) {
 
 int run_wgrad_gemm(const WgradLaunch& L, cudaStream_t st) {
   dim3 grid(L.grid_x, L.grid_y, L.grid_z);
-  wgrad_gemm_tc_kernel<<<grid, kWgradThreads, L.smem, st>>>(L.tmX, L.tmY, L.p, L.stages, L.tmem_cols, L.na);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_kernel_pdl(wgrad_gemm_tc_kernel, grid, dim3(kWgradThreads), L.smem, st, pdl_enabled(), L.tmX, L.tmY,
+                                    L.p, L.stages, L.tmem_cols, L.na);
   return e == cudaSuccess ? 0 : -4000 - int(e);
 }
 
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int64_t stride,
                                                            int64_t n, float* dW) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t n4 = n >> 2;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
     float4 acc = reinterpret_cast<float4*>(dW)[i];
@@ -1313,7 +1320,8 @@ void launch_wgrad_reduce(const WgradLaunch& L, int64_t numel, cudaStream_t st) {
   int blocks = int((numel / 4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(L.p.part, L.p.ksplit, L.p.part_stride, numel, L.p.dW);
+  launch_kernel_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, pdl_enabled(), (const float*)L.p.part, L.p.ksplit,
+                    L.p.part_stride, numel, L.p.dW);
 }
 
 int read_tc_watchdog() {

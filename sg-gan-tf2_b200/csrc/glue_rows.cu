@@ -170,6 +170,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     }
     fence_barrier_init();
   }
+  pdl_launch_dependents();
+  pdl_wait();  // barrier set-up overlapped the previous kernel's tail; global memory is touched only below
   __syncthreads();
 
   if (warp == kConsumers / 32) {
@@ -482,7 +484,7 @@ static void launch_row_stream_ns(const RowStreamParams& p, dim3 grid, size_t sme
     cudaFuncSetAttribute(row_stream_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     attr_set = true;
   }
-  row_stream_kernel<MODE, NS><<<grid, kStreamThreads, smem, st>>>(p);
+  launch_kernel_pdl(row_stream_kernel<MODE, NS>, grid, dim3(kStreamThreads), smem, st, pdl_enabled(), p);
 }
 
 template <int MODE>

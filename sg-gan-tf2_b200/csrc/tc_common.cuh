@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace sggan {
 
@@ -174,6 +175,14 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its stream
+// predecessor is still draining: everything before pdl_wait() (barrier init, TMEM allocation, descriptor
+// prefetch -- nothing that touches global memory) overlaps the predecessor's tail; pdl_wait() returns once the
+// predecessor grid has completed and its writes are visible.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- CTA pair (cluster of 2, cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -238,6 +247,27 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
           smem_u32(bar)),
       "h"(uint16_t(3))
       : "memory");
+}
+
+// Host: launch with (or without) the programmatic-serialization attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+inline bool pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("SGGAN_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 }  // namespace sggan
