@@ -87,6 +87,11 @@ int sggan_step_forward_backward_d(sggan_handle* h, const float* real_A, const fl
                                   float* losses_out);
 int sggan_step_backward_g(sggan_handle* h);
 int sggan_step_adam(sggan_handle* h, int net);
+/* Same update, issued on the handle's internal side stream so that it overlaps whatever the caller enqueues next
+ * (the data-parallel trainer updates D this way while G's all-reduce is in flight).  The next sggan_step_adam /
+ * sggan_step_* / sggan_train_step call on this handle joins it.  The step counter advances once both nets of a
+ * step have been updated, in either order. */
+int sggan_step_adam_async(sggan_handle* h, int net);
 int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask,
                      float* losses_out);
 int64_t sggan_step_count(const sggan_handle* h);

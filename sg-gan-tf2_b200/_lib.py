@@ -56,6 +56,7 @@ SYMBOLS = {
     "sggan_step_forward_backward_d": (_I, [_P, _P, _P, _P, _P]),
     "sggan_step_backward_g": (_I, [_P]),
     "sggan_step_adam": (_I, [_P, _I]),
+    "sggan_step_adam_async": (_I, [_P, _I]),
     "sggan_train_step": (_I, [_P, _P, _P, _P, _P]),
     "sggan_step_count": (_I64, [_P]),
     "sggan_kernel_launches": (_I, [_P]),
@@ -239,8 +240,10 @@ class Engine:
     def step_backward_g(self):
         check(lib().sggan_step_backward_g(self.h))
 
-    def step_adam(self, net):
-        check(lib().sggan_step_adam(self.h, net))
+    def step_adam(self, net, overlapped=False):
+        """Adam + weight re-pack of one net; overlapped=True issues it on the engine's side stream (joined by the next
+        engine call), so that it runs underneath whatever is enqueued next."""
+        check((lib().sggan_step_adam_async if overlapped else lib().sggan_step_adam)(self.h, net))
 
     def train_step(self, real_A, seg_A, mask):
         """One full G+D step; returns the device tensor [gen_loss, disc_loss] (no host sync)."""

@@ -132,9 +132,20 @@ int sggan_step_backward_g(sggan_handle* h) {
   FWD_ERR(h->e.step_bwd_g());
   return 0;
 }
+// both optimizers of a step use the same Adam time step; the counter advances when the second one has run
+static void adam_mark(Engine& e, int net) {
+  e.adam_mask |= 1 << (net == SGGAN_NET_G ? 0 : 1);
+  if (e.adam_mask == 3) { e.step += 1; e.adam_mask = 0; }
+}
 int sggan_step_adam(sggan_handle* h, int net) {
   FWD_ERR(h->e.step_adam(net));
-  if (net == SGGAN_NET_D) h->e.step += 1;  // D is updated last (model.py:199-200)
+  h->e.join_side();  // an update issued with sggan_step_adam_async is complete (in stream order) after this call
+  adam_mark(h->e, net);
+  return 0;
+}
+int sggan_step_adam_async(sggan_handle* h, int net) {
+  FWD_ERR(h->e.step_adam(net, true));
+  adam_mark(h->e, net);
   return 0;
 }
 int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask, float* losses_out) {

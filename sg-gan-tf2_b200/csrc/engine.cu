@@ -741,6 +741,7 @@ void Engine::in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb
 
 // ---------------------------------------------------------------------------------------------
 int Engine::gen_forward(const float* real_A, float* fake_out) {
+  join_side();  // an optimizer update issued on the side stream (sggan_step_adam_async) must have landed
   if (!weights_ready) { err = "weights not set (call sggan_weights_changed)"; return SGGAN_E_STATE; }
   const int B = cfg.batch, H = cfg.image_height, W = cfg.image_width;
   int r;
@@ -766,6 +767,7 @@ int Engine::gen_forward(const float* real_A, float* fake_out) {
 
 // D forward over [first | second] (each nimg_each = B images)
 int Engine::disc_forward_2b(const float* first, const float* second, int nimg_each) {
+  join_side();  // an optimizer update issued on the side stream (sggan_step_adam_async) must have landed
   const int H = cfg.image_height, W = cfg.image_width;
   int r;
   launch_prep_image3(first, nimg_each, H, W, D.L[0].X, D.L[0].xmap, 0, st);
@@ -792,6 +794,7 @@ int Engine::disc_forward_user(const float* x, const float* mask, float* logits_o
 }
 
 int Engine::step_fwd_bwd_d(const float* real_A, const float* seg_A, const float* mask, float* losses_out) {
+  join_side();  // an optimizer update issued on the side stream (sggan_step_adam_async) must have landed
   if (!weights_ready) { err = "weights not set"; return SGGAN_E_STATE; }
   nlaunch = 0;
   real_A_ = real_A; seg_A_ = seg_A; mask_ = mask; losses_out_ = losses_out;

@@ -94,6 +94,7 @@ struct Engine {
   size_t wg_part_elems;
   uint8_t *zero_begin, *zero_end;
   int64_t step;
+  int adam_mask = 0;  // which nets have been updated in the current step (bit 0 G, bit 1 D)
   int nlaunch;
   bool weights_ready;
   std::string err;

@@ -126,10 +126,10 @@ class sggan(object):
             hd = dist.all_reduce(eng.flat(L.NET_D, 1), async_op=True)
             eng.step_backward_g()
             hg = dist.all_reduce(eng.flat(L.NET_G, 1), async_op=True)
+            hd.wait()                                  # long finished: it ran underneath the generator backward
+            eng.step_adam(L.NET_D, overlapped=True)    # side stream: runs while G's all-reduce is in flight
             hg.wait()
-            eng.step_adam(L.NET_G)
-            hd.wait()
-            eng.step_adam(L.NET_D)
+            eng.step_adam(L.NET_G)                     # joins the side stream
         self.fake_A = eng.last_fake()
         self.gen_loss, self.disc_loss = eng.losses[0], eng.losses[1]  # device scalars; float() syncs
         return self.gen_loss, self.disc_loss
