@@ -1,16 +1,22 @@
-// conv_gemm_tc.cu -- the two tensor-core kernels of the SG-GAN step, hand-written for sm_100a:
+// conv_gemm_tc.cu -- the tensor-core kernels of the SG-GAN step, hand-written for sm_100a:
 //
-//   conv_gemm_tc_kernel   implicit-GEMM convolution (forward conv, dgrad, deconv phases) over
-//                         pitch-linearised frames: TMA boxes -> smem (SWIZZLE_128B) ->
-//                         tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> epilogue (bias, act,
-//                         per-(image,channel) sum / sum^2 for instance norm, bf16 store).
-//   wgrad_gemm_tc_kernel  weight gradient: MN-major operands (pixels are K), split-K over
-//                         images x pixel chunks, fp32 red.global accumulation.
+//   conv_gemm_tc_kernel    implicit-GEMM convolution (forward conv, dgrad, deconv phases) over
+//                          pitch-linearised frames: TMA boxes -> smem (SWIZZLE_128B) ->
+//                          tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> staged epilogue (bias, act,
+//                          bf16 tile in smem, bulk async stores, per-(image,channel) sum / sum^2
+//                          partials for instance norm).  Used for Cout >= 256 and fp32 outputs.
+//   conv_gemm_swap_kernel  the same operation with the operand roles exchanged (weights = M, 256 pixels
+//                          = N), persistent with two TMEM accumulators: layers with Cout <= 128 and
+//                          the 7x7 output convolution in shift-sum form.
+//   conv_gemm_pair_kernel  CTA-pair (cta_group::2) persistent variant for 256-channel layers; opt-in.
+//   wgrad_gemm_tc_kernel   weight gradient: MN-major operands (pixels are K), split-K over
+//                          images x pixel chunks into fp32 partial tiles, added in a fixed order by
+//                          wgrad_reduce_kernel.
 //
 // Replaces the cuDNN/Eigen calls behind tf.keras.layers.Conv2D / Conv2DTranspose and their
 // gradients on the reference path (module.py:211-216,232-265,284-311; model.py:196-197).
 //
-// The convolution is L2-bandwidth bound unless operand re-use is organised on chip (measured:
+// The convolution is operand-bandwidth bound unless re-use is organised on chip (measured:
 // 392 TFLOP/s with one TMA box per tap).  Two forms of re-use are built in:
 //   * the CTA tile is MT = 256 output positions x BN channels held as two 128-row accumulators in
 //     TMEM, so each weight tile (B) loaded into smem feeds two MMAs;
@@ -21,8 +27,11 @@
 //     swizzled data -- verified on hardware by tests/gpu/tc_probe.cu `shift`.
 // A and B therefore travel in separate mbarrier rings fed by two producer warps.
 //
-// Warp roles (352 threads): warp 0 = A producer, warp 1 = TMEM allocator + MMA issuer, warp 2 = B
-// producer, warps 3..10 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31; two warps per quarter).
+// Warp roles of conv_gemm_tc_kernel (480 threads): warp 0 = A producer, warp 1 = TMEM allocator + MMA
+// issuer, warp 2 = B producer, warps 3..10 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31; two warps
+// per quarter), warps 11..14 = statistics + store warps of the staged epilogue.  All kernels here are
+// launched with programmatic stream serialization: their set-up overlaps the predecessor's tail and
+// pdl_wait() precedes the first global access.
 #include "conv_gemm_tc.h"
 #include "tc_common.cuh"
 #include "tmap.h"

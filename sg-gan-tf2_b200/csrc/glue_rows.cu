@@ -11,7 +11,10 @@
 // complete_tx), so ~190 KB per SM are in flight independent of register pressure, and 16 consumer warps
 // compute out of shared memory (conflict-free 128-bit accesses, 8 channels per thread) and store 128-bit
 // results straight into the destination frame.  Row bookkeeping (reflected border rows/columns, 2x2 phase
-// planes, folded gradient borders) is resolved once per chunk into base pointers.
+// planes, folded gradient borders) is resolved once per chunk by the producer thread and handed over as a
+// descriptor in shared memory.  Fused into these passes: the fixed-order finalize of the convolution's per-tile
+// statistics (apply prologue), dgamma / dbeta (backward apply), and the residual-stream gradient gather
+// (backward reduce of the layer that reads it).
 #include <cuda_bf16.h>
 
 #include "glue.h"
