@@ -83,7 +83,7 @@ struct ConvGemmParams {
   int o_scale, o_a, o_b;
   const float* bias;  // [Cout] or null
   float* stats;       // per-tile partial (sum, sum of squares) of the stored result, [B][stats_T][Cout][2], or null;
-                      // launch_stats_finalize adds the tiles in a fixed order (deterministic forward)
+                      // the norm-apply pass adds the tiles in a fixed order (deterministic forward)
   int stats_T;        // tiles per image over all launches of the layer
   int stats_t0;       // first tile index of this launch
   int act;
