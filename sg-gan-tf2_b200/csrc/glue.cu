@@ -174,39 +174,6 @@ void launch_lrelu(const float* x, float* y, int64_t n, float leak, cudaStream_t 
 }
 
 // ------------------------------------------------------------------------------------------ IN fwd
-// Fixed-order reduction of the per-tile partials: 16 slices of the tile range are summed sequentially by
-// 16 threads per channel, then combined in a fixed tree -> bitwise reproducible statistics.
-__global__ void __launch_bounds__(1024) stats_finalize_kernel(const float2* __restrict__ part, int T, int C,
-                                                              float2* stats) {
-  __shared__ float2 sh[16][64];
-  const int b = blockIdx.y, cl = threadIdx.x & 63, sl = threadIdx.x >> 6;
-  const int c = blockIdx.x * 64 + cl;
-  const int per = (T + 15) / 16, t0 = sl * per, t1 = min(T, t0 + per);
-  float s1 = 0.f, s2 = 0.f;
-  if (c < C) {
-    const float2* p = part + int64_t(b) * T * C + c;
-    for (int t = t0; t < t1; ++t) {
-      const float2 v = __ldg(p + int64_t(t) * C);
-      s1 += v.x;
-      s2 += v.y;
-    }
-  }
-  sh[sl][cl] = make_float2(s1, s2);
-  __syncthreads();
-  for (int w = 8; w > 0; w >>= 1) {
-    if (sl < w) {
-      sh[sl][cl].x += sh[sl + w][cl].x;
-      sh[sl][cl].y += sh[sl + w][cl].y;
-    }
-    __syncthreads();
-  }
-  if (sl == 0 && c < C) stats[int64_t(b) * C + c] = sh[0][cl];
-}
-void launch_stats_finalize(const float* part, int B, int T, int C, float* stats, cudaStream_t st) {
-  dim3 grid((C + 63) / 64, B);
-  stats_finalize_kernel<<<grid, 1024, 0, st>>>(reinterpret_cast<const float2*>(part), T, C, reinterpret_cast<float2*>(stats));
-}
-
 __global__ void __launch_bounds__(kGlueThreads) in_stats_kernel(const sg_bf16* __restrict__ y, int HW, int C,
                                                                 float* stats, int ppb) {
   extern __shared__ float sred[];

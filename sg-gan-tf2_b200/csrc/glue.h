@@ -13,8 +13,7 @@ namespace sggan {
 void launch_prep_image3(const float* src, int B, int H, int W, sg_bf16* dst, const FrameMap& dmap, int dst_b0,
                         cudaStream_t st);
 
-// stats[b][c] = sum over tiles t (in order) of part[b][t][c]   (both (sum, sum^2) pairs)
-void launch_stats_finalize(const float* part, int B, int T, int C, float* stats, cudaStream_t st);
+// instance-norm passes as row streams (glue_rows.cu)
 void launch_in_apply(const InApplyParams& p, cudaStream_t st);
 void launch_in_bwd_reduce(const InBwdParams& p, cudaStream_t st);
 void launch_in_bwd_apply(const InBwdParams& p, cudaStream_t st);
