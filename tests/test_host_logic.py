@@ -102,3 +102,22 @@ def test_keras_variable_order():
     ns = argparse.Namespace(batch_size=1, image_width=512, image_height=256, use_resnet=False)
     with pytest.raises(Exception, match="use_resnet"):
         model.sggan(ns)
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) prints ONE JSON line with the contract's
+    keys; it must work without a GPU and without /root/reference."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--height", "128", "--width", "256"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "img/s"
