@@ -47,6 +47,7 @@ struct StreamDesc {
 struct RowStreamParams {
   int B, H, W, C, CW;  // CW = pixels per chunk
   int ns;              // active streams (a prefix of s[])
+  int evict_first;     // load the streams with an L2 evict-first hint
   int chunk_bytes;     // bytes per stream and stage: the pipeline memory is split over kStages x ns chunks
   int nb_act, act_wrap;
   StreamDesc s[kMaxStreams];
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       const int src_band = (MODE == RS_APPLY) ? 0 : max(p.g[0].ptr ? p.g[0].fold : 0, p.g[1].ptr ? p.g[1].fold : 0);
       const int dst_band = ((MODE == RS_APPLY || MODE == RS_BWD_APPLY) && dkind == 0) ? p.dmap.reflect : 0;
       const int band = max(src_band, dst_band);
+      const uint64_t pol = l2_policy_evict_first();  // the streams are read once per pass
       ChunkDesc row;  // row-level part, recomputed when the image row changes
       int cur_i = -1;
       int k = 0;
@@ -246,7 +248,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
           const StreamDesc& d = p.s[q];
           const sg_bf16* src = d.base + int64_t(d.act_index ? ba : b) * d.img_stride + int64_t(i + d.oy) * d.row_stride +
                                int64_t(j0 + d.ox) * p.C;
-          bulk_load_1d(smem + (s * NS + q) * p.chunk_bytes, src, bytes, &full_bar[s]);
+          if (p.evict_first) bulk_load_1d_hint(smem + (s * NS + q) * p.chunk_bytes, src, bytes, &full_bar[s], pol);
+          else bulk_load_1d(smem + (s * NS + q) * p.chunk_bytes, src, bytes, &full_bar[s]);
         }
         if (++jc == cpr) { jc = 0; ++i; }
       }
@@ -495,6 +498,10 @@ static void launch_row_stream(RowStreamParams& p, cudaStream_t st) {
   p.ns = 0;
   while (p.ns < kMaxStreams && p.s[p.ns].base != nullptr) ++p.ns;  // active streams are a prefix
   if (p.ns == 0) return;
+  {
+    static const int ef = []() { const char* e = getenv("SGGAN_ROWS_EVICT_FIRST"); return (e && e[0] == '0') ? 0 : 1; }();
+    p.evict_first = ef;
+  }
   p.CW = kPipeBytes / (kStages * p.ns) / (p.C * 2);
   if (p.CW > p.W) p.CW = p.W;
   p.chunk_bytes = p.CW * p.C * 2;

@@ -652,7 +652,7 @@ static int run_mma_rate() {
 // Experiment: L2 -> SM delivery rate of TMA tiles when the CTAs of a cluster all need the SAME tile
 // (unicast: every CTA loads it; multicast: each CTA loads 1/csz of it for everybody).
 __global__ void __launch_bounds__(64, 1) tma_share_kernel(const __grid_constant__ CUtensorMap tm, int iters, int mode,
-                                                          int ntiles, long long* cycles_out) {
+                                                          int ntiles, long long* cycles_out, const uint8_t* raw) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ uint64_t full[4], empty[4];
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(64, 1) tma_share_kernel(const __grid_constant_
   asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
   constexpr int kRows = 256, kTileBytes = kRows * 128;  // 32 KB tile of 256 rows x 64 bf16
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], mode ? csz : 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], mode == 1 ? csz : 1); }
     fence_barrier_init();
   }
   __syncthreads();
@@ -677,6 +677,12 @@ __global__ void __launch_bounds__(64, 1) tma_share_kernel(const __grid_constant_
       if (mode == 0) {
         tma_load_2d(&tm, &full[s], smem + s * kTileBytes, 0, tile * kRows);
         tma_load_2d(&tm, &full[s], smem + s * kTileBytes + kTileBytes / 2, 0, tile * kRows + kRows / 2);
+      } else if (mode == 2) {  // the same bytes as ONE 1-D bulk copy (what the row-stream kernels issue)
+        bulk_load_1d(smem + s * kTileBytes, raw + size_t(tile) * kTileBytes, kTileBytes, &full[s]);
+      } else if (mode == 3) {  // ... or as two 16 KB 1-D bulk copies
+        bulk_load_1d(smem + s * kTileBytes, raw + size_t(tile) * kTileBytes, kTileBytes / 2, &full[s]);
+        bulk_load_1d(smem + s * kTileBytes + kTileBytes / 2, raw + size_t(tile) * kTileBytes + kTileBytes / 2, kTileBytes / 2,
+                     &full[s]);
       } else {
         const int rows = kRows / int(csz);  // this CTA's slice, delivered to every CTA of the cluster
         // box height is fixed at 128 rows by the tensor map: csz == 2 -> one box each
@@ -691,7 +697,7 @@ __global__ void __launch_bounds__(64, 1) tma_share_kernel(const __grid_constant_
     for (int it = 0; it < iters; ++it) {
       const int s = it & 3;
       mbar_wait(&full[s], (it >> 2) & 1, 72);
-      if (mode == 0) mbar_arrive(&empty[s]);
+      if (mode != 1) mbar_arrive(&empty[s]);
       else
         for (uint32_t r = 0; r < csz; ++r) mbar_arrive_cluster(mapa_u32(smem_u32(&empty[s]), r));
     }
@@ -714,8 +720,9 @@ static int run_tma_share() {
   CK(cudaFuncSetAttribute(tma_share_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768 + 1024));
   const int iters = 2000, ntiles = int(rows / 256);
   for (int csz : {1, 2}) {
-    for (int mode : {0, 1}) {
+    for (int mode : {0, 1, 2, 3}) {
       if (csz == 1 && mode == 1) continue;
+      if (csz == 2 && mode >= 2) continue;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(148);
       cfg.blockDim = dim3(64);
@@ -725,7 +732,7 @@ static int run_tma_share() {
       at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       for (int rep = 0; rep < 2; ++rep) {
-        cudaError_t e = cudaLaunchKernelEx(&cfg, tma_share_kernel, tm, iters, mode, ntiles, dc);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tma_share_kernel, tm, iters, mode, ntiles, dc, (const uint8_t*)d);
         if (e != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); return 1; }
         e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("sync failed: %s (watchdog %d)\n", cudaGetErrorString(e), read_tc_watchdog()); return 1; }
@@ -736,7 +743,7 @@ static int run_tma_share() {
       for (auto v : h) avg += double(v);
       avg /= 148;
       printf("TMA_SHARE cluster %d %s: %.1f B/clk delivered per SM (%.0f cycles per 32 KB tile), chip %.0f B/clk\n", csz,
-             mode ? "multicast" : "unicast  ", iters * 32768.0 / avg, avg / iters, 148 * iters * 32768.0 / avg);
+             mode == 1 ? "multicast" : (mode == 0 ? "unicast 2-D boxes" : (mode == 2 ? "1-D bulk 32 KB" : "1-D bulk 2x16 KB")), iters * 32768.0 / avg, avg / iters, 148 * iters * 32768.0 / avg);
     }
   }
   return 0;
