@@ -1305,6 +1305,7 @@ int run_wgrad_gemm(const WgradLaunch& L, cudaStream_t st) {
   return e == cudaSuccess ? 0 : -4000 - int(e);
 }
 
+template <bool STREAM>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, int nsplit, int64_t stride,
                                                            int64_t n, float* dW) {
   pdl_launch_dependents();
@@ -1313,7 +1314,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
     float4 acc = reinterpret_cast<float4*>(dW)[i];
     for (int z = 0; z < nsplit; ++z) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(part + z * stride) + i);
+      const float4 v = STREAM ? __ldcs(reinterpret_cast<const float4*>(part + z * stride) + i)  // read once: evict first
+                              : __ldg(reinterpret_cast<const float4*>(part + z * stride) + i);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     reinterpret_cast<float4*>(dW)[i] = acc;
@@ -1329,8 +1331,13 @@ void launch_wgrad_reduce(const WgradLaunch& L, int64_t numel, cudaStream_t st) {
   int blocks = int((numel / 4 + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  launch_kernel_pdl(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, pdl_enabled(), (const float*)L.p.part, L.p.ksplit,
-                    L.p.part_stride, numel, L.p.dW);
+  static const bool stream = []() { const char* e = getenv("SGGAN_REDUCE_STREAM"); return !(e && e[0] == '0'); }();
+  if (stream)
+    launch_kernel_pdl(wgrad_reduce_kernel<true>, dim3(blocks), dim3(256), 0, st, pdl_enabled(), (const float*)L.p.part,
+                      L.p.ksplit, L.p.part_stride, numel, L.p.dW);
+  else
+    launch_kernel_pdl(wgrad_reduce_kernel<false>, dim3(blocks), dim3(256), 0, st, pdl_enabled(), (const float*)L.p.part,
+                      L.p.ksplit, L.p.part_stride, numel, L.p.dW);
 }
 
 int read_tc_watchdog() {
