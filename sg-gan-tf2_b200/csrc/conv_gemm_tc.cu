@@ -159,7 +159,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------ A producer: one tile per (run, chunk)
     if (lane == 0) {
-      const uint64_t pol = l2_policy_evict_first();
       for (int g = 0; g < agroups; ++g) {
         const int s = g % sa_stages;
         const uint32_t ph = (g / sa_stages) & 1;
@@ -168,14 +167,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* sa = smA + s * a_stage_bytes;
         const int row0 = m0 + p.run_off[r];
         mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
-        if (p.a_evict_first) {
-          for (int a = 0; a < NA; ++a)
-            tma_load_3d_hint(&tmA, &a_full[s], sa + a * kABytes, cc * kChunkK, row0 + a * kTileM, b, pol);
-          tma_load_3d_hint(&tmA8, &a_full[s], sa + NA * kABytes, cc * kChunkK, row0 + MT, b, pol);
-        } else {
         for (int a = 0; a < NA; ++a) tma_load_3d(&tmA, &a_full[s], sa + a * kABytes, cc * kChunkK, row0 + a * kTileM, b);
         tma_load_3d(&tmA8, &a_full[s], sa + NA * kABytes, cc * kChunkK, row0 + MT, b);
-        }
       }
     }
   } else if (warp == 2) {
@@ -1134,10 +1127,6 @@ static void build_runs(ConvGemmParams& p) {
     i += len;
   }
   for (int k = 0; k < p.ntaps; ++k) p.run_w[k] = uint8_t(t[k].second);
-  {
-    const char* e = getenv("SGGAN_CONV_A_HINT");
-    p.a_evict_first = (e && e[0] == '0') ? 0 : 1;
-  }
 }
 
 int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {

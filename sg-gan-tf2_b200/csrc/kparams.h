@@ -94,8 +94,6 @@ struct ConvGemmParams {
   // 7x fewer tensor-core instructions than one tap per (kh, kw) at N = 32 (tcgen05.mma has a ~156-cycle
   // floor per instruction regardless of N).
   int shift_kw;
-  int a_evict_first;  // load the activation tiles with an L2 evict-first hint (the frame is not needed again until
-                      // the backward pass; measured +0.5 % per step).  SGGAN_CONV_A_HINT=0 disables.
   long long* dbg;  // optional per-CTA clock64 stamps [grid][8] (tests/gpu/tc_probe.cu); null in production
 };
 
