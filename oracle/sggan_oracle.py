@@ -103,6 +103,54 @@ def lrelu(x, leak=0.3):
 
 
 # --------------------------------------------------------------------------------------------
+# bf16 storage emulation (test infrastructure for the CUDA path's numerics, not part of the reference)
+#
+# The CUDA engine stores activations, activation gradients and GEMM weights as bf16 and accumulates in
+# fp32.  `BF16Emu` restates exactly WHERE it rounds, as straight-through autograd functions, so that
+# tests can separate "the kernels compute something else" from "bf16 storage moved a ReLU / sign()":
+#   fq(x)  forward: round to bf16, backward: identity        (a stored activation, a packed weight)
+#   gq(x)  forward: identity,      backward: round to bf16   (a stored gradient)
+#   q(x)   both                                              (raw conv output Y <-> its gradient frame dY)
+# Rounding points of the engine (csrc/engine.cu): network inputs; every conv weight; every raw conv
+# output Y in front of a norm (both directions); every post-norm activation X (forward) and the
+# gradient w.r.t. every PADDED conv input (dgrad output, backward); the residual-stream sum (forward)
+# and its gradient sum (backward); the gradients seeded into the two output convolutions.
+
+
+class _FQ(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _GQ(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class BF16Emu:
+    fq = staticmethod(_FQ.apply)
+    gq = staticmethod(_GQ.apply)
+
+    @staticmethod
+    def q(x):
+        return _GQ.apply(_FQ.apply(x))
+
+
+class _NoEmu:
+    fq = gq = q = staticmethod(lambda x: x)
+
+
+# --------------------------------------------------------------------------------------------
 # weights in Keras creation order
 
 
@@ -158,23 +206,26 @@ def init_weights(spec, seed, dtype=torch.float32, randomize_affine=False):
 # networks
 
 
-def residule_block(x, w, ks=3, s=1):
-    """module.py:208-217.  w = [k1,b1,g1,be1,k2,b2,g2,be2]."""
+def residule_block(x, w, ks=3, s=1, emu=None):
+    """module.py:208-217.  w = [k1,b1,g1,be1,k2,b2,g2,be2].  `emu`: see BF16Emu (None = exact restatement)."""
+    E = emu or _NoEmu
     p = int((ks - 1) / 2)
-    y = reflect_pad(x, p)
-    y = conv2d(y, w[0], w[1], stride=s, padding="VALID")
+    y = E.gq(reflect_pad(x, p))
+    y = E.q(conv2d(y, E.fq(w[0]), w[1], stride=s, padding="VALID"))
     y = instance_norm(y, w[2], w[3])
-    y = torch.relu(y)
-    y = reflect_pad(y, p)
-    y = conv2d(y, w[4], w[5], stride=s, padding="VALID")
+    y = E.fq(torch.relu(y))
+    y = E.gq(reflect_pad(y, p))
+    y = E.q(conv2d(y, E.fq(w[4]), w[5], stride=s, padding="VALID"))
     y = instance_norm(y, w[6], w[7])
-    return y + x
+    return E.q(y + x)
 
 
-def generator_resnet(x, w, n_blocks=None, taps=None):
+def generator_resnet(x, w, n_blocks=None, taps=None, emu=None):
     """module.py:219-269.  `w` is the flat Keras-order list (94 tensors for 9 blocks; the block count
     is inferred from the list length when not given).
-    taps, if a dict, receives named intermediates (used by layer-level parity tests)."""
+    taps, if a dict, receives named intermediates (used by layer-level parity tests).
+    `emu`: see BF16Emu (None = exact restatement)."""
+    E = emu or _NoEmu
     if n_blocks is None:
         n_blocks = (len(w) - 22) // 8
     idx = [0]
@@ -189,29 +240,31 @@ def generator_resnet(x, w, n_blocks=None, taps=None):
             taps[name] = v
         return v
 
-    c0 = reflect_pad(x, 3)
+    c0 = reflect_pad(E.fq(x), 3)
     k, b, g, be = take(4)
-    c1 = tap("c1", torch.relu(instance_norm(conv2d(c0, k, b, 1, "VALID"), g, be)))
+    c1 = tap("c1", E.q(torch.relu(instance_norm(E.q(conv2d(c0, E.fq(k), b, 1, "VALID")), g, be))))
     k, b, g, be = take(4)
-    c2 = tap("c2", torch.relu(instance_norm(conv2d(c1, k, b, 2, "SAME"), g, be)))
+    c2 = tap("c2", E.q(torch.relu(instance_norm(E.q(conv2d(c1, E.fq(k), b, 2, "SAME")), g, be))))
     k, b, g, be = take(4)
-    c3 = tap("c3", torch.relu(instance_norm(conv2d(c2, k, b, 2, "SAME"), g, be)))
+    c3 = tap("c3", E.q(torch.relu(instance_norm(E.q(conv2d(c2, E.fq(k), b, 2, "SAME")), g, be))))
     r = c3
     for i in range(n_blocks):
-        r = tap("r%d" % (i + 1), residule_block(r, take(8)))
+        r = tap("r%d" % (i + 1), residule_block(r, take(8), emu=emu))
     k, b, g, be = take(4)
-    d1 = tap("d1", torch.relu(instance_norm(conv2d_transpose(r, k, b, 2), g, be)))
+    d1 = tap("d1", E.q(torch.relu(instance_norm(E.q(conv2d_transpose(r, E.fq(k), b, 2)), g, be))))
     k, b, g, be = take(4)
-    d2 = tap("d2", torch.relu(instance_norm(conv2d_transpose(d1, k, b, 2), g, be)))
-    d2 = reflect_pad(d2, 3)
+    d2 = tap("d2", E.fq(torch.relu(instance_norm(E.q(conv2d_transpose(d1, E.fq(k), b, 2)), g, be))))
+    d2 = E.gq(reflect_pad(d2, 3))
     k, b = take(2)
-    pred = torch.tanh(conv2d(d2, k, b, 1, "VALID"))
+    pred = torch.tanh(E.gq(conv2d(d2, E.fq(k), b, 1, "VALID")))
     assert idx[0] == len(w)
     return pred
 
 
-def discriminator(x, mask, w, taps=None):
-    """module.py:272-318.  w = flat Keras-order list (28 tensors).  Returns (B,Hd,Wd,1)."""
+def discriminator(x, mask, w, taps=None, emu=None):
+    """module.py:272-318.  w = flat Keras-order list (28 tensors).  Returns (B,Hd,Wd,1).
+    `emu`: see BF16Emu (None = exact restatement)."""
+    E = emu or _NoEmu
     idx = [0]
 
     def take(n):
@@ -225,13 +278,13 @@ def discriminator(x, mask, w, taps=None):
         return v
 
     k, b = take(2)
-    h = tap("h0", lrelu(conv2d(x, k, b, 2, "SAME")))
+    h = tap("h0", E.q(lrelu(E.gq(conv2d(E.fq(x), E.fq(k), b, 2, "SAME")))))
     for name, stride, pad in (("h1", 2, "SAME"), ("h2", 2, "SAME"), ("h3", 1, "SAME"), ("h31", 2, "VALID"),
                               ("h32", 2, "VALID"), ("h33", 1, "VALID")):
         k, b, g, be = take(4)
-        h = tap(name, lrelu(instance_norm(conv2d(h, k, b, stride, pad), g, be)))
+        h = tap(name, E.q(lrelu(instance_norm(E.q(conv2d(h, E.fq(k), b, stride, pad)), g, be))))
     k, b = take(2)
-    h4 = tap("h4", conv2d(h, k, b, 1, "SAME"))
+    h4 = tap("h4", E.gq(conv2d(h, E.fq(k), b, 1, "SAME")))
     h4 = h4 * mask  # tf.keras.layers.multiply: numpy broadcasting (A.9)
     assert idx[0] == len(w)
     return h4.sum(dim=-1, keepdim=True)
@@ -373,17 +426,19 @@ class StepState:
         self.lr, self.beta1 = lr, beta1
 
 
-def step_grads(g_w, d_w, real_A, seg_A, mask_A, loss_mode="p2p", L1_lambda=10.0, Lg_lambda=5.0, use_lsgan=True):
+def step_grads(g_w, d_w, real_A, seg_A, mask_A, loss_mode="p2p", L1_lambda=10.0, Lg_lambda=5.0, use_lsgan=True,
+               p2p_lambda=100, emu=None):
     """Forward + both gradients of model.py:169-197 ("fresh" fake_A branch).
-    Returns dict(gen_loss, disc_loss, fake_A, da_real, da_fake, g_grads, d_grads)."""
+    Returns dict(gen_loss, disc_loss, fake_A, da_real, da_fake, g_grads, d_grads).
+    `emu=BF16Emu` adds the CUDA engine's bf16 storage rounding (see BF16Emu); p2p_lambda is LAMBDA of model.py:151."""
     g_w = [w.detach().clone().requires_grad_(True) for w in g_w]
     d_w = [w.detach().clone().requires_grad_(True) for w in d_w]
-    fake_A = generator_resnet(real_A, g_w)
-    da_real = discriminator(seg_A, mask_A, d_w)
-    da_fake = discriminator(fake_A, mask_A, d_w)
+    fake_A = generator_resnet(real_A, g_w, emu=emu)
+    da_real = discriminator(seg_A, mask_A, d_w, emu=emu)
+    da_fake = discriminator(fake_A, mask_A, d_w, emu=emu)
     da_fake_sample = da_fake  # bit-identical duplicate forward in the reference (model.py:188)
     if loss_mode == "p2p":
-        gen_loss = gen_loss_p2p(da_fake, fake_A, seg_A)
+        gen_loss = gen_loss_p2p(da_fake, fake_A, seg_A, LAMBDA=p2p_lambda)
         disc_loss = disc_loss_p2p(da_real, da_fake_sample)
     elif loss_mode == "sggan":
         gen_loss, _ = generator_loss(da_fake, real_A, fake_A, seg_A, L1_lambda, use_lsgan, Lg_lambda)

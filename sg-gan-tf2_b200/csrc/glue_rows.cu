@@ -36,6 +36,18 @@ constexpr int kMaxStreams = 3;
 
 enum { RS_APPLY = 0, RS_BWD_REDUCE = 1, RS_BWD_APPLY = 2, RS_GATHER = 3 };
 
+#ifdef SG_ROWS_DEBUG
+// tests/gpu/rows_probe.cu: per-block clock64 stamps [block][8]: 0 start, 1 after the dependency wait, 2 consumer
+// coefficients ready, 3 first chunk arrived, 4 last chunk consumed, 5 end, 6 last load issued (producer)
+__device__ long long* g_rows_dbg = nullptr;
+#define RS_STAMP(slot, cond)                                                                          \
+  do {                                                                                                \
+    if (g_rows_dbg != nullptr && (cond)) g_rows_dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = clock64(); \
+  } while (0)
+#else
+#define RS_STAMP(slot, cond) do { } while (0)
+#endif
+
 struct StreamDesc {
   const sg_bf16* base;  // null = absent (reads as zeros)
   int64_t img_stride;   // elements between images
@@ -167,6 +179,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   const int cbeg = blockIdx.x * cper, cend = min(nchunks, cbeg + cper);
   const int dkind = (MODE == RS_GATHER || MODE == RS_BWD_REDUCE) ? 0 : p.dmap.kind;
 
+  RS_STAMP(0, threadIdx.x == 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -177,6 +190,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   pdl_launch_dependents();
   pdl_wait();  // barrier set-up overlapped the previous kernel's tail; global memory is touched only below
   __syncthreads();
+  RS_STAMP(1, threadIdx.x == 0);
 
   if (warp == kConsumers / 32) {
     // ------------------------------------------------------------ producer: bookkeeping + bulk copies, kStages ahead
@@ -253,6 +267,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
         }
         if (++jc == cpr) { jc = 0; ++i; }
       }
+      RS_STAMP(6, true);
     }
     return;
   }
@@ -332,6 +347,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       }
     }
   }
+  RS_STAMP(2, threadIdx.x == 0);
   const uint32_t chunk_bytes = p.chunk_bytes, stage_bytes = NS * p.chunk_bytes;
   const int W = p.W, C = p.C;
   const int dC = (MODE == RS_GATHER || MODE == RS_BWD_REDUCE) ? C : p.dmap.C;
@@ -434,6 +450,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     const int s = k % kStages;
     cd = &descs[s];
     mbar_wait(&full_bar[s], (k / kStages) & 1, 42);
+    RS_STAMP(3, threadIdx.x == 0 && k == 0);
     const int4 h0 = *reinterpret_cast<const int4*>(cd);      // i, j0, cw, lo
     const int hi = cd->hi;
     const int j0 = h0.y, cw = h0.z, lo = h0.w;
@@ -461,6 +478,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
   }
+  RS_STAMP(4, threadIdx.x == 0);
   if (MODE == RS_BWD_REDUCE) {
     // threads that share a channel group differ in px0 (kConsumers / C8 of them): stage their partials in the
     // (now idle) pipeline buffers as [px0][e][k][cg] (consecutive lanes -> consecutive words) and add them
@@ -481,6 +499,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       atomicAdd(p.sums + int64_t(b) * C * 2 + t, acc);
     }
   }
+  RS_STAMP(5, threadIdx.x == 0);
 }
 
 template <int MODE, int NS>

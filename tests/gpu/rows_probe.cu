@@ -1,0 +1,138 @@
+// rows_probe.cu -- standalone timing probe for the row-stream (instance-norm / gather) passes at the
+// residual-block shape of BASELINE config 3 (B=8, 64x128x256) and the 128x256x128 / 256x512x64 layers.
+// Usage: rows_probe [B H W C]   -- prints CUDA-event time per launch over rotating buffer sets (cold L2)
+// and per-block phase stamps.  Timing only; correctness is covered by tests/test_gpu_parity.py.
+#define SG_ROWS_DEBUG 1
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../sg-gan-tf2_b200/csrc/glue_rows.cu"
+
+using namespace sggan;
+
+#define CK(x)                                                                       \
+  do {                                                                              \
+    cudaError_t e_ = (x);                                                           \
+    if (e_ != cudaSuccess) {                                                        \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                      \
+    }                                                                               \
+  } while (0)
+
+struct Set {
+  sg_bf16 *Y, *X, *R, *dX, *dY, *gat;
+  float *part, *stats, *sums, *gamma, *beta, *dg, *db;
+};
+
+int main(int argc, char** argv) {
+  int B = 8, H = 64, W = 128, C = 256;
+  if (argc >= 5) { B = atoi(argv[1]); H = atoi(argv[2]); W = atoi(argv[3]); C = atoi(argv[4]); }
+  const int NSETS = 4, ITERS = 24;
+  const int P = W + 2, T = (H * P + 127) / 128 + 1;
+  FrameMap xm;
+  memset(&xm, 0, sizeof(xm));
+  xm.frame_pix = int64_t(H + 2) * P; xm.C = C; xm.H = H; xm.W = W; xm.kind = 0; xm.P = P; xm.pt = 1; xm.pl = 1; xm.reflect = 1;
+  FrameMap dym;
+  memset(&dym, 0, sizeof(dym));
+  dym.frame_pix = int64_t(H + 4) * P; dym.C = C; dym.H = H; dym.W = W; dym.kind = 0; dym.P = P; dym.pt = 2; dym.pl = 0;
+  const size_t nY = size_t(B) * H * W * C, nX = size_t(B) * xm.frame_pix * C, ndX = size_t(B) * (H + 2) * P * C,
+               ndY = size_t(B) * dym.frame_pix * C;
+  std::vector<Set> sets(NSETS);
+  std::vector<uint16_t> h(nX + 4096);
+  for (size_t i = 0; i < h.size(); ++i) h[i] = uint16_t(0x3c00 + (i * 2654435761u >> 22));  // small positive/neg mix is irrelevant for timing
+  for (auto& s : sets) {
+    CK(cudaMalloc(&s.Y, nY * 2)); CK(cudaMalloc(&s.X, nX * 2 + 4096)); CK(cudaMalloc(&s.R, nX * 2 + 4096));
+    CK(cudaMalloc(&s.dX, ndX * 2)); CK(cudaMalloc(&s.dY, ndY * 2 + 4096)); CK(cudaMalloc(&s.gat, nY * 2));
+    CK(cudaMalloc(&s.part, size_t(B) * T * C * 8)); CK(cudaMalloc(&s.stats, size_t(B) * C * 8));
+    CK(cudaMalloc(&s.sums, size_t(B) * C * 8)); CK(cudaMalloc(&s.gamma, C * 4)); CK(cudaMalloc(&s.beta, C * 4));
+    CK(cudaMalloc(&s.dg, C * 4)); CK(cudaMalloc(&s.db, C * 4));
+    CK(cudaMemcpy(s.Y, h.data(), nY * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.R, h.data(), nX * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(s.dX, h.data(), ndX * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemset(s.part, 0, size_t(B) * T * C * 8)); CK(cudaMemset(s.stats, 0, size_t(B) * C * 8));
+    CK(cudaMemset(s.sums, 0, size_t(B) * C * 8)); CK(cudaMemset(s.gamma, 0, C * 4)); CK(cudaMemset(s.beta, 0, C * 4));
+    CK(cudaMemset(s.X, 0, nX * 2)); CK(cudaMemset(s.dY, 0, ndY * 2));
+  }
+  long long* dbg;
+  CK(cudaMalloc(&dbg, 4096 * 8 * 8));
+  cudaStream_t st;
+  CK(cudaStreamCreate(&st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+
+  auto apply = [&](Set& s, bool res, bool part) {
+    InApplyParams p;
+    memset(&p, 0, sizeof(p));
+    p.Y = s.Y; p.B = B; p.H = H; p.W = W; p.C = C; p.stats = s.stats; p.gamma = s.gamma; p.beta = s.beta; p.eps = 1e-3f;
+    p.act = res ? SG_ACT_NONE : SG_ACT_RELU;
+    if (part) { p.stats_part = s.part; p.stats_T = T; p.stats_out = s.stats; }
+    if (res) { p.res = s.R; p.rmap = xm; }
+    p.dst = s.X; p.dmap = xm;
+    launch_in_apply(p, st);
+  };
+  auto bwd = [&](Set& s, int which, bool gather) {
+    InBwdParams p;
+    memset(&p, 0, sizeof(p));
+    p.Y = s.Y; p.B = B; p.H = H; p.W = W; p.C = C; p.nb_act = B; p.act_wrap = 0; p.stats = s.stats; p.gamma = s.gamma;
+    p.beta = s.beta; p.eps = 1e-3f; p.act = SG_ACT_RELU;
+    p.g1.ptr = s.dX; p.g1.f32 = 0; p.g1.Hs = H + 2; p.g1.Ws = P; p.g1.oy = 1; p.g1.ox = 1; p.g1.fold = 1;
+    if (gather) { p.g2 = p.g1; p.g2.ptr = s.R; p.gather_dst = s.gat; }
+    p.sums = s.sums; p.dst = s.dY; p.dmap = dym; p.dgamma = s.dg; p.dbeta = s.db; p.nb_param = B;
+    if (which == 0) launch_in_bwd_reduce(p, st);
+    else { p.gather_dst = nullptr; launch_in_bwd_apply(p, st); }
+  };
+  struct Case { const char* name; int kind; double mb; };
+  const double mY = nY * 2 / 1e6;
+  Case cases[] = {{"apply (stats given)", 0, 2 * mY},       {"apply + finalize", 1, 2 * mY},
+                  {"apply + residual + finalize", 2, 3 * mY}, {"bwd reduce", 3, 2 * mY},
+                  {"bwd reduce + gather", 4, 4 * mY},        {"bwd apply", 5, 3 * mY}};
+  printf("rows_probe B %d H %d W %d C %d  (tensor %.1f MB)  stages %d consumers %d\n", B, H, W, C, mY, kStages, kConsumers);
+  for (auto& c : cases) {
+    auto run = [&](Set& s) {
+      switch (c.kind) {
+        case 0: apply(s, false, false); break;
+        case 1: apply(s, false, true); break;
+        case 2: apply(s, true, true); break;
+        case 3: bwd(s, 0, false); break;
+        case 4: bwd(s, 0, true); break;
+        case 5: bwd(s, 1, false); break;
+      }
+    };
+    for (int i = 0; i < NSETS; ++i) run(sets[i]);
+    CK(cudaStreamSynchronize(st));
+    // (a) back-to-back over rotating sets (PDL chaining as in the step)
+    CK(cudaEventRecord(e0, st));
+    for (int i = 0; i < ITERS; ++i) run(sets[i % NSETS]);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double us = ms * 1e3 / ITERS;
+    // (b) phase stamps of one cold launch
+    CK(cudaMemset(dbg, 0, 4096 * 8 * 8));
+    CK(cudaMemcpyToSymbol(g_rows_dbg, &dbg, sizeof(dbg)));
+    run(sets[0]);
+    CK(cudaStreamSynchronize(st));
+    long long* nullp = nullptr;
+    CK(cudaMemcpyToSymbol(g_rows_dbg, &nullp, sizeof(nullp)));
+    std::vector<long long> hd(4096 * 8);
+    CK(cudaMemcpy(hd.data(), dbg, hd.size() * 8, cudaMemcpyDeviceToHost));
+    double acc[8] = {0};
+    int nblk = 0;
+    for (int bk = 0; bk < 4096; ++bk) {
+      const long long* d = &hd[bk * 8];
+      if (d[0] == 0) continue;
+      for (int k = 1; k < 7; ++k) acc[k] += double(d[k] - d[0]);
+      ++nblk;
+    }
+    printf("%-30s %7.2f us/launch  %6.0f GB/s (algorithmic %.0f MB) | blocks %d, avg cycles from block start: dep-wait %.0f "
+           "coeffs %.0f first-chunk %.0f last-load-issued %.0f last-consumed %.0f end %.0f\n",
+           c.name, us, c.mb / us * 1e3, c.mb, nblk, acc[1] / nblk, acc[2] / nblk, acc[3] / nblk, acc[6] / nblk,
+           acc[4] / nblk, acc[5] / nblk);
+  }
+  return 0;
+}
