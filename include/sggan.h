@@ -95,6 +95,18 @@ int sggan_step_adam_async(sggan_handle* h, int net);
 int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask,
                      float* losses_out);
 int64_t sggan_step_count(const sggan_handle* h);
+/* Resume support: set the number of completed steps (Adam's bias correction uses t = count + 1); the Adam slots
+ * themselves are the flat buffers what = 2 / 3 of sggan_flat_buffer.  model.py:450-503 saves weights only; carrying
+ * the optimizer over is what keeps a re-planned (new batch / image size) or restarted run on the same trajectory. */
+int sggan_set_step_count(sggan_handle* h, int64_t completed_steps);
+/* Re-bind the stream every later call of this handle launches on (the handle's internal side stream follows it
+ * through events).  The caller orders the switch itself (e.g. synchronises the old stream first). */
+int sggan_set_stream(sggan_handle* h, void* stream);
+/* Data parallelism without torch: sum this rank's flat gradient buffer of `net` (SGGAN_NET_G, SGGAN_NET_D, or -1 for
+ * both, D first) over the communicator with ncclAllReduce(ncclFloat32, ncclSum) in place, on `stream`, after the
+ * handle's own stream has produced them (event dependency).  sggan_config.world_size makes Adam apply the 1/N.
+ * `nccl_comm` is an ncclComm_t; libnccl.so.2 is resolved at the first call (no link-time dependency). */
+int sggan_allreduce_grads(sggan_handle* h, int net, void* nccl_comm, void* stream);
 int sggan_kernel_launches(const sggan_handle* h); /* kernels launched by the last train step */
 /* fake_A of the last step / forward (device, [B,H,W,3] fp32). */
 const float* sggan_last_fake(const sggan_handle* h);

@@ -59,6 +59,9 @@ SYMBOLS = {
     "sggan_step_adam_async": (_I, [_P, _I]),
     "sggan_train_step": (_I, [_P, _P, _P, _P, _P]),
     "sggan_step_count": (_I64, [_P]),
+    "sggan_set_step_count": (_I, [_P, _I64]),
+    "sggan_set_stream": (_I, [_P, _P]),
+    "sggan_allreduce_grads": (_I, [_P, _I, _P, _P]),
     "sggan_kernel_launches": (_I, [_P]),
     "sggan_last_fake": (_P, [_P]),
     "sggan_profile_begin": (_I, [_P, _I]),

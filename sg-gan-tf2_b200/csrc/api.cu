@@ -1,4 +1,5 @@
 // api.cu -- the extern "C" surface declared in include/sggan.h.
+#include <dlfcn.h>
 #include <math.h>
 #include <string.h>
 
@@ -78,6 +79,7 @@ void sggan_destroy(sggan_handle* h) {
   if (e.st2) cudaStreamDestroy(e.st2);
   if (e.ev_fork) cudaEventDestroy(e.ev_fork);
   if (e.ev_join) cudaEventDestroy(e.ev_join);
+  if (e.ev_comm) cudaEventDestroy(e.ev_comm);
   for (auto ev : e.prof_ev) cudaEventDestroy(ev);
   delete h;
 }
@@ -159,6 +161,57 @@ int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, c
   return 0;
 }
 int64_t sggan_step_count(const sggan_handle* h) { return h->e.step; }
+int sggan_set_step_count(sggan_handle* h, int64_t completed_steps) {
+  if (completed_steps < 0) { g_err = "negative step count"; return SGGAN_E_INVALID; }
+  h->e.step = completed_steps;
+  h->e.adam_mask = 0;
+  return 0;
+}
+int sggan_set_stream(sggan_handle* h, void* stream) {
+  h->e.join_side();
+  h->e.st = (cudaStream_t)stream;
+  return 0;
+}
+
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+static nccl_allreduce_fn resolve_nccl_allreduce() {
+  static nccl_allreduce_fn fn = nullptr;
+  static bool tried = false;
+  if (tried) return fn;
+  tried = true;
+  void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");  // a host that already loaded NCCL (e.g. torch's bundled copy)
+  if (sym == nullptr) {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (lib == nullptr) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (lib != nullptr) sym = dlsym(lib, "ncclAllReduce");
+  }
+  fn = reinterpret_cast<nccl_allreduce_fn>(sym);
+  return fn;
+}
+int sggan_allreduce_grads(sggan_handle* h, int net, void* nccl_comm, void* stream) {
+  if (nccl_comm == nullptr || net < -1 || net > 1) { g_err = "bad communicator / net"; return SGGAN_E_INVALID; }
+  nccl_allreduce_fn ar = resolve_nccl_allreduce();
+  if (ar == nullptr) { g_err = "libnccl.so.2 (ncclAllReduce) not found"; return SGGAN_E_STATE; }
+  Engine& e = h->e;
+  cudaStream_t cs = (cudaStream_t)stream;
+  e.join_side();  // weight gradients run on the side stream
+  if (cs != e.st) {
+    if (e.ev_comm == nullptr && cudaEventCreateWithFlags(&e.ev_comm, cudaEventDisableTiming) != cudaSuccess) {
+      g_err = "event creation failed"; return SGGAN_E_CUDA;
+    }
+    if (cudaEventRecord(e.ev_comm, e.st) != cudaSuccess || cudaStreamWaitEvent(cs, e.ev_comm, 0) != cudaSuccess) {
+      g_err = "stream dependency failed"; return SGGAN_E_CUDA;
+    }
+  }
+  const int nets[2] = {SGGAN_NET_D, SGGAN_NET_G};
+  for (int k = 0; k < 2; ++k) {
+    if (net != -1 && net != nets[k]) continue;
+    Net& n = net_of(h, nets[k]);
+    const int rc = ar(n.g, n.g, size_t(n.nparams), /*ncclFloat32*/ 7, /*ncclSum*/ 0, nccl_comm, cs);
+    if (rc != 0) { g_err = "ncclAllReduce failed with code " + std::to_string(rc); return SGGAN_E_CUDA; }
+  }
+  return 0;
+}
 int sggan_kernel_launches(const sggan_handle* h) { return h->e.nlaunch; }
 const float* sggan_last_fake(const sggan_handle* h) { return h->e.fake; }
 int sggan_num_layers(const sggan_handle* h, int net) { return int(net_of(h, net).L.size()); }
@@ -346,7 +399,7 @@ static int conv_bwd_run(Layer& l, const float* x, const float* kernel, const flo
   g.ptr = l.dX; g.f32 = 0; g.Hs = l.dxH; g.Ws = l.dxW; g.oy = l.dx_oy; g.ox = l.dx_ox; g.fold = l.dx_fold;
   GradSrc none;
   memset(&none, 0, sizeof(none));
-  launch_grad_gather(g, none, l.nb, l.Hin, l.Win, l.Cin, dxp, st);
+  if (launch_grad_gather(g, none, l.nb, l.Hin, l.Win, l.Cin, dxp, st) < 0) { g_err = "gradient gather launch failed"; return SGGAN_E_CUDA; }
   launch_bf16_to_f32(dxp, dx, int64_t(l.nb) * l.Hin * l.Win * l.Cin, st);
   if (db != nullptr) {
     if (cudaMemsetAsync(db, 0, size_t(l.Cout) * 4, st) != cudaSuccess) return SGGAN_E_CUDA;
@@ -375,9 +428,9 @@ int sggan_instance_norm_bwd(const float* x, const float* gamma, const float* bet
                             float* dgamma, float* dbeta, int B, int H, int W, int C, float eps, int act, float alpha,
                             void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (C % 64) { g_err = "C must be a multiple of 64"; return SGGAN_E_INVALID; }
+  if (C % 64 || C > 512) { g_err = "C must be a multiple of 64, at most 512"; return SGGAN_E_INVALID; }
   const size_t n = size_t(B) * H * W * C;
-  const size_t need = align256(n * 2) * 3 + 2 * align256(size_t(B) * C * 8);
+  const size_t need = align256(n * 2) * 3 + 2 * align256(size_t(B) * C * 8) + align256(in_bwd_partials_bytes(C));
   if (!workspace || workspace_bytes < need) { g_err = "operator workspace too small"; return SGGAN_E_WORKSPACE; }
   uint8_t* base = (uint8_t*)workspace;
   sg_bf16* xb = (sg_bf16*)base;
@@ -385,6 +438,7 @@ int sggan_instance_norm_bwd(const float* x, const float* gamma, const float* bet
   sg_bf16* ob = (sg_bf16*)(base + 2 * align256(n * 2));
   float* stats = (float*)(base + 3 * align256(n * 2));
   float* sums = (float*)(base + 3 * align256(n * 2) + align256(size_t(B) * C * 8));
+  float* part = (float*)(base + 3 * align256(n * 2) + 2 * align256(size_t(B) * C * 8));
   launch_f32_to_bf16(x, xb, n, st);
   launch_f32_to_bf16(dz, gb, n, st);
   if (cudaMemsetAsync(stats, 0, 2 * align256(size_t(B) * C * 8), st) != cudaSuccess) return SGGAN_E_CUDA;
@@ -397,9 +451,11 @@ int sggan_instance_norm_bwd(const float* x, const float* gamma, const float* bet
   p.Y = xb; p.B = B; p.H = H; p.W = W; p.C = C; p.nb_act = B; p.act_wrap = 0; p.stats = stats; p.gamma = gamma; p.beta = beta;
   p.eps = eps; p.act = act; p.act_alpha = alpha;
   p.g1.ptr = gb; p.g1.f32 = 0; p.g1.Hs = H; p.g1.Ws = W;
-  p.sums = sums; p.dst = ob; p.dmap = pm;
-  launch_in_bwd_reduce(p, st);
-  launch_in_bwd_apply(p, st);
+  p.sums = sums; p.sums_part = part; p.dst = ob; p.dmap = pm;
+  const int nblk = launch_in_bwd_reduce(p, st);
+  if (nblk <= 0) { g_err = "instance-norm backward (reduce) launch failed"; return SGGAN_E_CUDA; }
+  p.sums_nblk = nblk;
+  if (launch_in_bwd_apply(p, st) < 0) { g_err = "instance-norm backward (apply) launch failed"; return SGGAN_E_CUDA; }
   launch_in_param_grad(sums, B, C, dgamma, dbeta, st);
   launch_bf16_to_f32(ob, dx, n, st);
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
@@ -409,7 +465,7 @@ int sggan_instance_norm_fwd(const float* x, const float* gamma, const float* bet
                             int B, int H, int W, int C, float eps, int act, float alpha, void* workspace,
                             size_t workspace_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (C % 64) { g_err = "C must be a multiple of 64"; return SGGAN_E_INVALID; }
+  if (C % 64 || C > 512) { g_err = "C must be a multiple of 64, at most 512"; return SGGAN_E_INVALID; }
   const size_t n = size_t(B) * H * W * C;
   const size_t need = align256(n * 2) * 3 + align256(size_t(B) * C * 8);
   if (!workspace || workspace_bytes < need) { g_err = "operator workspace too small"; return SGGAN_E_WORKSPACE; }
@@ -429,7 +485,7 @@ int sggan_instance_norm_fwd(const float* x, const float* gamma, const float* bet
   pm.frame_pix = int64_t(H) * W; pm.C = C; pm.H = H; pm.W = W; pm.P = W;
   p.Y = xb; p.B = B; p.H = H; p.W = W; p.C = C; p.stats = stats; p.gamma = gamma; p.beta = beta; p.eps = eps;
   p.act = act; p.act_alpha = alpha; p.res = residual ? rb : nullptr; p.rmap = pm; p.dst = yb; p.dmap = pm;
-  launch_in_apply(p, st);
+  if (launch_in_apply(p, st) < 0) { g_err = "instance-norm forward launch failed"; return SGGAN_E_CUDA; }
   launch_bf16_to_f32(yb, y, n, st);
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }

@@ -592,6 +592,7 @@ int Engine::build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t
   for (int i = 0; i < 2; ++i) resG[i] = (sg_bf16*)a.take(size_t(B) * rb.Hin * rb.Win * rb.Cin * 2);
   wg_part_elems = size_t(160) * 256 * 256;  // one (2 x 128) x 256 fp32 tile per CTA of a single-wave split-K launch
   wg_part = (float*)a.take(wg_part_elems * 4);
+  in_part = (float*)a.take(in_bwd_partials_bytes(512));  // per-block partial sums of the norm-backward reduce pass
   for (int i = 0; i < 2; ++i) {
     pack_jobs[i] = (PackParams*)a.take(kMaxPackJobs * sizeof(PackParams));
     pack_starts[i] = (int*)a.take((kMaxPackJobs + 1) * sizeof(int));
@@ -666,6 +667,10 @@ int Engine::run_wgrad(Layer& l, Net& n) {
     ws = st2;
     side_used = true;
   }
+  if (l.has_norm) {  // dgamma / dbeta from the sums the norm-backward apply pass of this layer just published
+    launch_in_param_grad(l.bsums, l.nb, l.Cout, n.g + n.T[l.ti_g].offset, n.g + n.T[l.ti_be].offset, ws);
+    ++nlaunch;
+  }
   for (const auto& L : l.wgrad) {
     int r = run_wgrad_gemm(L, ws);
     ++nlaunch;
@@ -697,7 +702,7 @@ void Engine::in_apply(Net& n, int li, sg_bf16* dst, const FrameMap& dmap, const 
   p.res = res;
   if (rmap) p.rmap = *rmap;
   p.dst = dst; p.dmap = dmap;
-  launch_in_apply(p, st);
+  if (launch_in_apply(p, st) < 0 && glue_err == 0) glue_err = 1;
   ++nlaunch;
 }
 
@@ -727,15 +732,18 @@ void Engine::in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb
   p.nb_act = nb_act; p.act_wrap = act_wrap;
   p.stats = l.stats; p.gamma = n.p + n.T[l.ti_g].offset; p.beta = n.p + n.T[l.ti_be].offset;
   p.eps = cfg.in_eps; p.act = l.act; p.act_alpha = l.alpha;
-  p.g1 = g1; p.g2 = g2; p.sums = l.bsums; p.dst = l.dY; p.dmap = l.dymap;
-  p.dgamma = n.g + n.T[l.ti_g].offset; p.dbeta = n.g + n.T[l.ti_be].offset; p.nb_param = nb_param;
+  p.g1 = g1; p.g2 = g2; p.sums = l.bsums; p.sums_part = in_part; p.dst = l.dY; p.dmap = l.dymap;
+  (void)nb_param;  // dgamma / dbeta are taken from l.bsums by run_wgrad (side stream)
   p.gather_dst = gather_dst;  // reduce pass also materialises g1 + g2 (the residual-stream gradient) ...
-  launch_in_bwd_reduce(p, st);
+  const int nblk = launch_in_bwd_reduce(p, st);
+  if (nblk <= 0) { if (glue_err == 0) glue_err = 2; return; }
   if (gather_dst != nullptr) {  // ... which is then the single source of the apply pass
     p.g1.ptr = gather_dst; p.g1.f32 = 0; p.g1.Hs = gH; p.g1.Ws = gW; p.g1.oy = 0; p.g1.ox = 0; p.g1.fold = 0;
     memset(&p.g2, 0, sizeof(p.g2));
   }
-  launch_in_bwd_apply(p, st);  // also writes dgamma / dbeta
+  p.sums_nblk = nblk;
+  p.gather_dst = nullptr;
+  if (launch_in_bwd_apply(p, st) < 0 && glue_err == 0) glue_err = 3;  // also publishes the reduced sums in l.bsums
   nlaunch += 2;
 }
 
@@ -837,6 +845,7 @@ int Engine::step_fwd_bwd_d(const float* real_A, const float* seg_A, const float*
     if ((r = run_conv_list(l.dgrad))) return r;
   }
   join_side();
+  if (glue_err) { err = "row-stream launch failed (code " + std::to_string(glue_err) + ")"; glue_err = 0; return SGGAN_E_CUDA; }
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
 
@@ -898,13 +907,15 @@ int Engine::step_bwd_g() {
       if (fuse_gather) {
         add = dx_src(l);
       } else {  // separate gather launch: G_{k-1} = G_k + fold(dX of conv_a)
-        launch_grad_gather(gres, dx_src(l), B, rb.Hin, rb.Win, rb.Cin, resG[cur], st); ++nlaunch;
+        if (launch_grad_gather(gres, dx_src(l), B, rb.Hin, rb.Win, rb.Cin, resG[cur], st) < 0 && glue_err == 0) glue_err = 4;
+        ++nlaunch;
         gres = plain_src(resG[cur], rb.Hin, rb.Win);
         cur ^= 1;
       }
     }
   }
   join_side();
+  if (glue_err) { err = "row-stream launch failed (code " + std::to_string(glue_err) + ")"; glue_err = 0; return SGGAN_E_CUDA; }
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
 

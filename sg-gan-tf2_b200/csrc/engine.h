@@ -77,7 +77,7 @@ struct Engine {
   // weight-gradient GEMMs run on a side stream: they only need the layer's input frame and dY, so they fill the SMs
   // that the dgrad / norm-backward chain on `st` leaves idle at its wave tails; joined at the end of each phase
   cudaStream_t st2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_comm = nullptr;
   bool side_used = false;
   void join_side();
   bool dry;
@@ -91,6 +91,8 @@ struct Engine {
   int* pack_starts[2];
   int pack_njobs[2], pack_blocks[2];
   float* wg_part;  // split-K partial tiles of the weight-gradient GEMMs (shared by all layers)
+  float* in_part;  // per-block partial sums of the norm-backward reduce pass (consumed by the apply pass that follows)
+  int glue_err = 0;  // first failed row-stream launch of the current phase (reported when the phase ends)
   size_t wg_part_elems;
   uint8_t *zero_begin, *zero_end;
   int64_t step;

@@ -14,13 +14,16 @@ void launch_prep_image3(const float* src, int B, int H, int W, sg_bf16* dst, con
                         cudaStream_t st);
 
 // instance-norm passes as row streams (glue_rows.cu)
-void launch_in_apply(const InApplyParams& p, cudaStream_t st);
-void launch_in_bwd_reduce(const InBwdParams& p, cudaStream_t st);
-void launch_in_bwd_apply(const InBwdParams& p, cudaStream_t st);
+// All return 0 (launch_in_bwd_reduce: the number of partial-sum blocks per image, to be passed to the apply pass as
+// InBwdParams::sums_nblk) or a negative cudaError.
+int launch_in_apply(const InApplyParams& p, cudaStream_t st);
+int launch_in_bwd_reduce(const InBwdParams& p, cudaStream_t st);
+int launch_in_bwd_apply(const InBwdParams& p, cudaStream_t st);
+size_t in_bwd_partials_bytes(int C);  // size of InBwdParams::sums_part
 
 // out[b,i,j,c] (plain bf16 [B][H][W][C]) = g1 + g2 (either may fold a reflected border back).
-void launch_grad_gather(const GradSrc& g1, const GradSrc& g2, int B, int H, int W, int C, sg_bf16* out,
-                        cudaStream_t st);
+int launch_grad_gather(const GradSrc& g1, const GradSrc& g2, int B, int H, int W, int C, sg_bf16* out,
+                       cudaStream_t st);
 
 // Backward of an activation applied in a conv epilogue (discriminator h0: LeakyReLU without norm):
 // dy = dz * act'(z), z read from the frame the epilogue wrote; also accumulates the bias gradient

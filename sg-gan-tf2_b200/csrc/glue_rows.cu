@@ -33,16 +33,32 @@ constexpr int kStreamThreads = kConsumers + 32;  // + 1 producer warp
 constexpr int kStages = SG_STAGES;
 constexpr int kPipeBytes = 196608;  // shared memory of the whole pipeline: kStages x streams x chunk
 constexpr int kMaxStreams = 3;
+constexpr int kMaxC = 512;                                    // channels per pixel the passes support
+constexpr int kCoefBytes = 6 * kMaxC * 4;                     // per-channel coefficients staged in shared memory
+constexpr int kSumBytes = (kConsumers + kMaxC) * 8;           // fixed-order sums: [slices][C] float2 + [C] float2
 
 enum { RS_APPLY = 0, RS_BWD_REDUCE = 1, RS_BWD_APPLY = 2, RS_GATHER = 3 };
 
 #ifdef SG_ROWS_DEBUG
 // tests/gpu/rows_probe.cu: per-block clock64 stamps [block][8]: 0 start, 1 after the dependency wait, 2 consumer
 // coefficients ready, 3 first chunk arrived, 4 last chunk consumed, 5 end, 6 last load issued (producer)
+// slots 8 / 9: %globaltimer (ns, comparable across SMs and launches) at block start / end; launch l of a probe
+// sequence writes to region (l % 8) (the host advances g_rows_dbg_launch)
 __device__ long long* g_rows_dbg = nullptr;
+static int g_rows_dbg_launch = 0;
+__device__ __forceinline__ long long rs_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define RS_STAMP(slot, cond)                                                                          \
   do {                                                                                                \
-    if (g_rows_dbg != nullptr && (cond)) g_rows_dbg[(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = clock64(); \
+    if (g_rows_dbg != nullptr && (cond)) {                                                            \
+      long long* d_ = g_rows_dbg + ((p.dbg_launch & 7) * 256 + blockIdx.y * gridDim.x + blockIdx.x) * 16; \
+      d_[slot] = clock64();                                                                           \
+      if ((slot) == 0) d_[8] = rs_globaltimer();                                                      \
+      if ((slot) == 5) d_[9] = rs_globaltimer();                                                      \
+    }                                                                                                 \
   } while (0)
 #else
 #define RS_STAMP(slot, cond) do { } while (0)
@@ -70,14 +86,17 @@ struct RowStreamParams {
   float eps;
   int act;
   float alpha;
-  float* sums;   // in_bwd: [B][C][2]
+  float* sums;   // in_bwd apply: the reduced (sum dzh, sum dzh * xhat) per (image, channel) are published here, [B][C][2]
+  float* sums_part;  // in_bwd: per-block partial sums [B][gridDim.x][C][2]: written by the reduce pass with plain
+                     // stores, added in a fixed order by the apply pass (no atomics: the backward is bit-reproducible)
   const float* stats_part;  // in_apply: per-tile partials to finalize in the kernel (or null), see InApplyParams
   int stats_T;
   float* stats_out;
   sg_bf16* gather_dst;  // in_bwd reduce: also store g1 + g2 (folded) as plain [B][H][W][C] (or null)
-  float* dgamma;  // in_bwd apply: affine-parameter gradients written by block (0, 0) (or null)
-  float* dbeta;
-  int nb_param;
+  int sums_nblk;  // in_bwd apply: partials per image (= blocks per image of the reduce launch)
+#ifdef SG_ROWS_DEBUG
+  int dbg_launch;
+#endif
   GradSrc g[2];  // fold information of the gradient streams (extras are read directly from global)
   sg_bf16* dst;  // frame (apply modes) or plain [B][H][W][C] (gather)
   FrameMap dmap;
@@ -161,12 +180,92 @@ __device__ __forceinline__ void src_extra8(const long long* rows, int n, const G
     }
 }
 
+// Column sums of src[T][C] (float2 entries) in a fixed order by the kConsumers consumer threads: thread (slice, channel
+// pair) adds rows slice, slice + slices, ... (128-bit loads), then the slices are added in order.  Split in two halves
+// so that the first kPre rows per thread are ISSUED before the producer releases its bulk loads (see `go_bar`): a small
+// load queued behind the ~28 MB the producers of all blocks request at kernel start waits 4-8 us for its turn.
+constexpr int kPre = 12;
+struct SumPre {
+  float4 v[kPre];
+};
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {  // volatile: stays in front of the go_bar arrive
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ld_nc_f2(const float2* p) {
+  float2 r;
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_nc_f1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void fixed_order_sum_issue(const float2* __restrict__ src, int T, int C, int tid, SumPre& pre) {
+  const int CP = C >> 1;
+  const int slices = kConsumers / CP;
+  const int sl = tid / CP, cp = tid - sl * CP;
+  if (sl < slices) {
+    const float4* s4 = reinterpret_cast<const float4*>(src) + cp;
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int t = sl + u * slices;
+      pre.v[u] = t < T ? ld_nc_f4(s4 + int64_t(t) * CP) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+// Second half, step 1: add this thread's rows (the pre-loaded ones, then any further rows in batches of eight
+// independent loads) and park the slice sum in shared memory.  Everything this thread loads has ARRIVED when it returns.
+__device__ __forceinline__ void fixed_order_sum_accumulate(const float2* __restrict__ src, int T, int C, float2* scratch,
+                                                           int tid, const SumPre& pre) {
+  const int CP = C >> 1;
+  const int slices = kConsumers / CP;
+  const int sl = tid / CP, cp = tid - sl * CP;
+  float4* part4 = reinterpret_cast<float4*>(scratch);  // [slices][CP]
+  if (sl < slices) {
+    const float4* s4 = reinterpret_cast<const float4*>(src) + cp;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) { acc.x += pre.v[u].x; acc.y += pre.v[u].y; acc.z += pre.v[u].z; acc.w += pre.v[u].w; }
+    for (int t = sl + kPre * slices; t < T; t += 8 * slices) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = (t + u * slices < T) ? ld_nc_f4(s4 + int64_t(t + u * slices) * CP) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    part4[sl * CP + cp] = acc;
+  }
+}
+// Step 2: add the slices in order.  Result: fin[C] in shared memory (valid after the call for all consumers).
+__device__ __forceinline__ const float2* fixed_order_sum_combine(int C, float2* scratch, int tid) {
+  const int CP = C >> 1;
+  const int slices = kConsumers / CP;
+  float4* part4 = reinterpret_cast<float4*>(scratch);            // [slices][CP]
+  float4* fin4 = reinterpret_cast<float4*>(scratch + kConsumers);  // [CP]
+  named_bar_sync(3, kConsumers);
+  if (tid < CP) {
+    float4 acc = part4[tid];
+    for (int q = 1; q < slices; ++q) {
+      const float4 o = part4[q * CP + tid];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    fin4[tid] = acc;
+  }
+  named_bar_sync(3, kConsumers);
+  return scratch + kConsumers;
+}
+
 // =======================================================================================================
 template <int MODE, int NS>
 __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const RowStreamParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);  // pointer arithmetic keeps the shared address space
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
+  __shared__ uint64_t go_bar;  // consumers -> producer: the prologue's small loads are issued, start the bulk stream
   __shared__ ChunkDesc descs[kStages];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -185,6 +284,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kConsumers / 32);
     }
+    mbar_init(&go_bar, kConsumers / 32);
     fence_barrier_init();
   }
   pdl_launch_dependents();
@@ -199,6 +299,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       const int dst_band = ((MODE == RS_APPLY || MODE == RS_BWD_APPLY) && dkind == 0) ? p.dmap.reflect : 0;
       const int band = max(src_band, dst_band);
       const uint64_t pol = l2_policy_evict_first();  // the streams are read once per pass
+      mbar_wait(&go_bar, 0, 40);
       ChunkDesc row;  // row-level part, recomputed when the image row changes
       int cur_i = -1;
       int k = 0;
@@ -280,47 +381,74 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   const int c0 = cg * 8;
   const int px0 = threadIdx.x / C8, pstep = kConsumers / C8;  // pstep is even (C8 <= 64)
   const float n = float(p.H * p.W);
-  // fused statistics finalize: the per-tile partials of the producing convolution are added in a fixed order by
-  // all consumers of the block (slices of the tile range per channel, then the slices) while the producer's first
-  // chunks are in flight; block 0 of the image also publishes the result for the backward pass
-  const float2* fin = nullptr;
-  if (MODE == RS_APPLY && p.stats_part != nullptr) {
-    float2* st_part = reinterpret_cast<float2*>(smem + kPipeBytes);  // [slices][C]
-    float2* st_fin = st_part + kConsumers;                           // [C]
-    const int Cc = p.C, slices = kConsumers / Cc, sl = threadIdx.x / Cc, c = threadIdx.x - sl * Cc;
-    const int T = p.stats_T, per = (T + slices - 1) / slices, t0 = sl * per, t1 = min(T, t0 + per);
-    const float2* part = reinterpret_cast<const float2*>(p.stats_part) + int64_t(ba) * T * Cc + c;
-    float s1 = 0.f, s2 = 0.f;
-    for (int t = t0; t < t1; ++t) {
-      const float2 v = __ldg(part + int64_t(t) * Cc);
-      s1 += v.x;
-      s2 += v.y;
-    }
-    st_part[sl * Cc + c] = make_float2(s1, s2);
-    named_bar_sync(3, kConsumers);
-    if (int(threadIdx.x) < Cc) {
-      float2 acc = st_part[threadIdx.x];
-      for (int q = 1; q < slices; ++q) {
-        const float2 o = st_part[q * Cc + threadIdx.x];
-        acc.x += o.x; acc.y += o.y;
-      }
-      st_fin[threadIdx.x] = acc;
-      if (blockIdx.x == 0) reinterpret_cast<float2*>(p.stats_out)[int64_t(ba) * Cc + threadIdx.x] = acc;
-    }
-    named_bar_sync(3, kConsumers);
-    fin = st_fin;
+  // Per-channel coefficients, computed cooperatively: one thread per channel does the (independent) global loads and
+  // the arithmetic, the results are staged in shared memory and every thread then picks up its eight channels.  (Each
+  // thread loading its own 8 x 3 values cost ~14k cycles of serialised load latency per launch, a third of the pass.)
+  float* coef = reinterpret_cast<float*>(smem + kPipeBytes);                  // [6][C]: mean, rstd, scale, beta, a1, a2
+  float2* sum_scratch = reinterpret_cast<float2*>(smem + kPipeBytes + kCoefBytes);
+  // ---- round 1: issue the global loads of the prologue
+  const bool do_fin = MODE == RS_APPLY && p.stats_part != nullptr;
+  const float2* sum_src = do_fin ? reinterpret_cast<const float2*>(p.stats_part) + int64_t(ba) * p.stats_T * p.C
+                                 : (MODE == RS_BWD_APPLY ? reinterpret_cast<const float2*>(p.sums_part) + int64_t(b) * p.sums_nblk * p.C
+                                                         : nullptr);
+  const int sum_T = do_fin ? p.stats_T : (MODE == RS_BWD_APPLY ? p.sums_nblk : 0);
+  SumPre pre;
+  if (do_fin || MODE == RS_BWD_APPLY) fixed_order_sum_issue(sum_src, sum_T, p.C, threadIdx.x, pre);
+  float2 st_c = make_float2(0.f, 0.f);
+  float g_c = 1.f, be_c = 0.f;
+  const bool have_st = !do_fin && p.stats != nullptr;
+  if (MODE != RS_GATHER && int(threadIdx.x) < p.C) {  // C <= kMaxC = kConsumers: one channel per thread
+    const int c = threadIdx.x;
+    if (have_st) st_c = ld_nc_f2(reinterpret_cast<const float2*>(p.stats) + int64_t(ba) * p.C + c);
+    if (p.gamma != nullptr) g_c = ld_nc_f1(p.gamma + c);
+    if (p.beta != nullptr) be_c = ld_nc_f1(p.beta + c);
   }
-  if (MODE == RS_BWD_APPLY && p.dgamma != nullptr && blockIdx.x == 0 && blockIdx.y == 0) {
-    for (int c = threadIdx.x; c < p.C; c += kConsumers) {
-      float g = 0.f, be = 0.f;
-      for (int bb = 0; bb < p.nb_param; ++bb) {
-        const float2 q = reinterpret_cast<const float2*>(p.sums)[int64_t(bb) * p.C + c];
-        be += q.x;
-        g += q.y;
+  // ---- round 2: the loads have landed -> release the producer's bulk stream, then the fixed-order sums
+  // (statistics finalize / backward partial sums) and the per-channel coefficients.  The bulk stream starts one or
+  // two L2 round trips late; started first, the ~28 MB that all blocks request at once delay these small loads by
+  // 4-8 us (measured with tests/gpu/rows_probe.cu), a third of the pass.
+  const bool has_sum = do_fin || MODE == RS_BWD_APPLY;
+  if (has_sum) fixed_order_sum_accumulate(sum_src, sum_T, p.C, sum_scratch, threadIdx.x, pre);
+  else if (MODE != RS_GATHER && int(threadIdx.x) < p.C) coef[3 * p.C + threadIdx.x] = be_c + 0.f * (st_c.x + g_c);  // data dependency
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&go_bar);
+  const float2* fin = nullptr;
+  if (do_fin) {
+    // fused statistics finalize: the per-tile partials of the producing convolution are added in a fixed order;
+    // block 0 of the image also publishes the result for the backward pass
+    fin = fixed_order_sum_combine(p.C, sum_scratch, threadIdx.x);
+    if (blockIdx.x == 0)
+      for (int c = threadIdx.x; c < p.C; c += kConsumers) reinterpret_cast<float2*>(p.stats_out)[int64_t(ba) * p.C + c] = fin[c];
+  }
+  const float2* bsum = nullptr;
+  if (MODE == RS_BWD_APPLY) {
+    // the reduce pass left one partial (sum dzh, sum dzh * xhat) per block of this image
+    bsum = fixed_order_sum_combine(p.C, sum_scratch, threadIdx.x);
+    if (blockIdx.x == 0 && p.sums != nullptr)
+      for (int c = threadIdx.x; c < p.C; c += kConsumers) reinterpret_cast<float2*>(p.sums)[int64_t(b) * p.C + c] = bsum[c];
+  }
+  if (MODE != RS_GATHER) {
+    if (int(threadIdx.x) < p.C) {
+      const int c = threadIdx.x;
+      float mu = 0.f, rs = 1.f;
+      if (fin != nullptr || have_st) {
+        const float2 st = fin != nullptr ? fin[c] : st_c;
+        mu = st.x / n;
+        rs = rsqrtf(fmaxf(st.y / n - mu * mu, 0.f) + p.eps);
       }
-      p.dgamma[c] = g;
-      p.dbeta[c] = be;
+      coef[c] = mu;
+      coef[p.C + c] = rs;
+      coef[2 * p.C + c] = g_c * rs;
+      coef[3 * p.C + c] = be_c;  // z = (y - mean)*scale + beta: exactly beta when H*W == 1
+      float q1 = 0.f, q2 = 0.f;
+      if (MODE == RS_BWD_APPLY) {
+        q1 = bsum[c].x / n;        // mean of dzh
+        q2 = bsum[c].y / n * rs;   // mean of dzh * xhat, times rstd (applied to y - mean directly)
+      }
+      coef[4 * p.C + c] = q1;
+      coef[5 * p.C + c] = q2;
     }
+    named_bar_sync(3, kConsumers);
   }
   // activation as a slope for the non-positive side: relu 0, leaky alpha, identity 1 (tanh never reaches the glue)
   const float gneg = p.act == SG_ACT_RELU ? 0.f : (p.act == SG_ACT_LRELU ? p.alpha : 1.f);
@@ -329,22 +457,12 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int c = c0 + e;
-      float mu = 0.f, rs = 1.f;
-      if (fin != nullptr || p.stats != nullptr) {
-        const float2 st = fin != nullptr ? fin[c] : reinterpret_cast<const float2*>(p.stats)[int64_t(ba) * p.C + c];
-        mu = st.x / n;
-        rs = rsqrtf(fmaxf(st.y / n - mu * mu, 0.f) + p.eps);
-      }
-      mean[e] = mu;
-      rstd[e] = rs;
-      scale[e] = (p.gamma ? p.gamma[c] : 1.f) * rs;
-      beta[e] = p.beta ? p.beta[c] : 0.f;  // z = (y - mean)*scale + beta: exactly beta when H*W == 1
-      a1[e] = a2[e] = 0.f;
-      if (MODE == RS_BWD_APPLY) {
-        const float2 q = reinterpret_cast<const float2*>(p.sums)[int64_t(b) * p.C + c];
-        a1[e] = q.x / n;        // mean of dzh
-        a2[e] = q.y / n * rs;   // mean of dzh * xhat, times rstd (applied to y - mean directly)
-      }
+      mean[e] = coef[c];
+      rstd[e] = coef[p.C + c];
+      scale[e] = coef[2 * p.C + c];
+      beta[e] = coef[3 * p.C + c];
+      a1[e] = coef[4 * p.C + c];
+      a2[e] = coef[5 * p.C + c];
     }
   }
   RS_STAMP(2, threadIdx.x == 0);
@@ -496,44 +614,61 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
       const int idx = (((ch & 7) * 2) + kk) * C8 + (ch >> 3);
       float acc = 0.f;
       for (int q = 0; q < pstep; ++q) acc += red[q * 16 * C8 + idx];
-      atomicAdd(p.sums + int64_t(b) * C * 2 + t, acc);
+      p.sums_part[(int64_t(b) * gridDim.x + blockIdx.x) * C * 2 + t] = acc;  // blocks without chunks still write zeros
     }
   }
   RS_STAMP(5, threadIdx.x == 0);
 }
 
+// Returns the blocks per image of the launch (> 0), 0 if there was nothing to do, or -(cudaError) on failure.
 template <int MODE, int NS>
-static void launch_row_stream_ns(const RowStreamParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(row_stream_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    attr_set = true;
+static int launch_row_stream_ns(const RowStreamParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  static bool attr_set[64] = {};  // the attribute is per device
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return -int(e);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    e = cudaFuncSetAttribute(row_stream_kernel<MODE, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return -int(e);
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  launch_kernel_pdl(row_stream_kernel<MODE, NS>, grid, dim3(kStreamThreads), smem, st, pdl_enabled(), p);
+  e = launch_kernel_pdl(row_stream_kernel<MODE, NS>, grid, dim3(kStreamThreads), smem, st, pdl_enabled(), p);
+  return e == cudaSuccess ? int(grid.x) : -int(e);
 }
 
 template <int MODE>
-static void launch_row_stream(RowStreamParams& p, cudaStream_t st) {
+static int launch_row_stream(RowStreamParams& p, cudaStream_t st) {
   p.ns = 0;
   while (p.ns < kMaxStreams && p.s[p.ns].base != nullptr) ++p.ns;  // active streams are a prefix
-  if (p.ns == 0) return;
+  if (p.ns == 0) return 0;
+  if (p.C > kMaxC || (p.C & 63) != 0 || p.B < 1 || p.H < 1 || p.W < 1) return -int(cudaErrorInvalidValue);
   {
+    // L2 policy of the streamed loads: evict-first.  Keeping the backward reduce pass's streams resident for the apply
+    // pass that follows was measured (tests/gpu/rows_probe.cu, "reduce -> apply") and does not help: 67 MB streamed
+    // cyclically do not survive in the 126 MB L2, and the reduce pass itself runs 15 % slower without the hint.
     static const int ef = []() { const char* e = getenv("SGGAN_ROWS_EVICT_FIRST"); return (e && e[0] == '0') ? 0 : 1; }();
     p.evict_first = ef;
   }
-  p.CW = kPipeBytes / (kStages * p.ns) / (p.C * 2);
-  if (p.CW > p.W) p.CW = p.W;
+#ifdef SG_ROWS_DEBUG
+  p.dbg_launch = g_rows_dbg_launch++;
+#endif
+  // chunk width: as wide as the pipeline memory allows, then evened out over the row (128 pixels at 48 per chunk
+  // would be 48 + 48 + 32)
+  int cwmax = kPipeBytes / (kStages * p.ns) / (p.C * 2);
+  if (cwmax > p.W) cwmax = p.W;
+  const int cpr = (p.W + cwmax - 1) / cwmax;
+  p.CW = (p.W + cpr - 1) / cpr;
   p.chunk_bytes = p.CW * p.C * 2;
-  const size_t smem = size_t(kPipeBytes) + 128 + 2 * kConsumers * sizeof(float2);  // + staged statistics
+  const size_t smem = size_t(kPipeBytes) + 128 + kCoefBytes + kSumBytes;
   // one persistent block per SM; blocks never span images (per-image statistics)
   int gx = 148 / p.B;
   if (gx < 1) gx = 1;
-  const int nchunks = p.H * ((p.W + p.CW - 1) / p.CW);
+  const int nchunks = p.H * cpr;
   if (gx > nchunks) gx = nchunks;
   dim3 grid(gx, p.B);
-  if (p.ns == 1) launch_row_stream_ns<MODE, 1>(p, grid, smem, st);
-  else if (p.ns == 2) launch_row_stream_ns<MODE, 2>(p, grid, smem, st);
-  else launch_row_stream_ns<MODE, 3>(p, grid, smem, st);
+  if (p.ns == 1) return launch_row_stream_ns<MODE, 1>(p, grid, smem, st);
+  if (p.ns == 2) return launch_row_stream_ns<MODE, 2>(p, grid, smem, st);
+  return launch_row_stream_ns<MODE, 3>(p, grid, smem, st);
 }
 
 static StreamDesc plain_stream(const sg_bf16* base, int H, int W, int C, int act_index) {
@@ -553,7 +688,7 @@ static StreamDesc null_stream() {
   return d;
 }
 
-void launch_in_apply(const InApplyParams& a, cudaStream_t st) {
+int launch_in_apply(const InApplyParams& a, cudaStream_t st) {
   RowStreamParams p = {};
   p.B = a.B; p.H = a.H; p.W = a.W; p.C = a.C; p.nb_act = a.B; p.act_wrap = 0;
   p.s[0] = plain_stream(a.Y, a.H, a.W, a.C, 0);
@@ -566,7 +701,8 @@ void launch_in_apply(const InApplyParams& a, cudaStream_t st) {
   p.stats = a.stats; p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.act = a.act; p.alpha = a.act_alpha;
   p.stats_part = a.stats_part; p.stats_T = a.stats_T; p.stats_out = a.stats_out;
   p.dst = a.dst; p.dmap = a.dmap;
-  launch_row_stream<RS_APPLY>(p, st);
+  const int r = launch_row_stream<RS_APPLY>(p, st);
+  return r < 0 ? r : 0;
 }
 
 static void bwd_params(const InBwdParams& a, RowStreamParams& p) {
@@ -576,22 +712,25 @@ static void bwd_params(const InBwdParams& a, RowStreamParams& p) {
   p.s[2] = a.g2.ptr ? grad_stream(a.g2, a.C) : null_stream();
   p.g[0] = a.g1; p.g[1] = a.g2;
   p.stats = a.stats; p.gamma = a.gamma; p.beta = a.beta; p.eps = a.eps; p.act = a.act; p.alpha = a.act_alpha;
-  p.sums = a.sums; p.dst = a.dst; p.dmap = a.dmap;
-  p.dgamma = a.dgamma; p.dbeta = a.dbeta; p.nb_param = a.nb_param;
+  p.sums = a.sums; p.sums_part = a.sums_part; p.sums_nblk = a.sums_nblk; p.dst = a.dst; p.dmap = a.dmap;
   p.gather_dst = a.gather_dst;
 }
-void launch_in_bwd_reduce(const InBwdParams& a, cudaStream_t st) {
+int launch_in_bwd_reduce(const InBwdParams& a, cudaStream_t st) {
   RowStreamParams p = {};
   bwd_params(a, p);
-  launch_row_stream<RS_BWD_REDUCE>(p, st);
+  if (a.sums_part == nullptr) return -int(cudaErrorInvalidValue);
+  return launch_row_stream<RS_BWD_REDUCE>(p, st);  // blocks per image = partial sums per image
 }
-void launch_in_bwd_apply(const InBwdParams& a, cudaStream_t st) {
+int launch_in_bwd_apply(const InBwdParams& a, cudaStream_t st) {
   RowStreamParams p = {};
   bwd_params(a, p);
-  launch_row_stream<RS_BWD_APPLY>(p, st);
+  if (a.sums_part == nullptr || a.sums_nblk < 1) return -int(cudaErrorInvalidValue);
+  const int r = launch_row_stream<RS_BWD_APPLY>(p, st);
+  return r < 0 ? r : 0;
 }
+size_t in_bwd_partials_bytes(int C) { return size_t(160) * C * 2 * sizeof(float); }  // <= 148 blocks per launch
 
-void launch_grad_gather(const GradSrc& g1, const GradSrc& g2, int B, int H, int W, int C, sg_bf16* out, cudaStream_t st) {
+int launch_grad_gather(const GradSrc& g1, const GradSrc& g2, int B, int H, int W, int C, sg_bf16* out, cudaStream_t st) {
   RowStreamParams p = {};
   p.B = B; p.H = H; p.W = W; p.C = C; p.nb_act = B; p.act_wrap = 0;
   p.s[0] = g1.ptr ? grad_stream(g1, C) : null_stream();
@@ -599,7 +738,8 @@ void launch_grad_gather(const GradSrc& g1, const GradSrc& g2, int B, int H, int 
   p.s[2] = null_stream();
   p.g[0] = g1; p.g[1] = g2;
   p.dst = out;
-  launch_row_stream<RS_GATHER>(p, st);
+  const int r = launch_row_stream<RS_GATHER>(p, st);
+  return r < 0 ? r : 0;
 }
 
 }  // namespace sggan

@@ -185,14 +185,12 @@ struct InBwdParams {
   int act;
   float act_alpha;
   GradSrc g1, g2;
-  float* sums;  // [B][C][2]
+  float* sums;       // [B][C][2]: reduced (sum dzh, sum dzh * xhat), published by the apply pass (for dgamma / dbeta)
+  float* sums_part;  // [B][sums_nblk][C][2] scratch: per-block partials of the reduce pass (in_bwd_partials_bytes(C))
+  int sums_nblk;     // apply pass: value returned by launch_in_bwd_reduce
   sg_bf16* dst;
   FrameMap dmap;
   // optional (reduce pass): also store the summed, border-folded gradient g1 + g2 as plain [B][H][W][C] bf16 -- the
   // residual-stream gradient gather of the generator blocks, fused with the statistics of the layer that reads it
   sg_bf16* gather_dst;
-  // optional (apply pass): dgamma[c] = sum_b sums[b][c].y, dbeta[c] = sum_b sums[b][c].x over the first nb_param images
-  float* dgamma;
-  float* dbeta;
-  int nb_param;
 };

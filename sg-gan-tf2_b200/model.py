@@ -67,16 +67,25 @@ class sggan(object):
     # ---- plan -----------------------------------------------------------------------------------------
     def _ensure_runtime(self, B, H, W, mask_hw):
         rt = self.runtime
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        if world != self.world_size and rt is not None:
+            raise L.SgganError("the process group changed after the first train_step (world size %d -> %d)" %
+                               (self.world_size, world))
+        self.world_size = world  # read lazily: init_process_group may follow the constructor
         if rt is not None and (rt.cfg.batch, rt.cfg.image_height, rt.cfg.image_width, rt.cfg.mask_height,
                                rt.cfg.mask_width) == (B, H, W, mask_hw[0], mask_hw[1]):
+            # the training runtime must own both networks' master weights (a stand-alone G(x) / D([x, m]) call at
+            # another shape never takes ownership, but a first call before training may have bound another plan)
+            if self.generator.runtime is not rt:
+                self.generator.bind(rt)
+            if self.discriminator.runtime is not rt:
+                self.discriminator.bind(rt)
             return rt
         rt = module.Runtime(B, H, W, segment_class=self.segment_class, n_blocks=self.generator.n_blocks,
                             mask_hw=mask_hw, loss_mode=L.LOSS_P2P if self.loss_mode == "p2p" else L.LOSS_SGGAN,
                             use_lsgan=int(self.use_lsgan), lr=self.lr, beta1=self.beta1, L1_lambda=self.L1_lambda,
                             Lg_lambda=self.Lg_lambda, world_size=self.world_size)
-        self.generator.runtime = None
-        self.discriminator.runtime = None
-        self.generator.bind(rt)
+        self.generator.bind(rt)       # carries Adam m / v and the step count over from a previous plan
         self.discriminator.bind(rt)
         if self.world_size > 1:  # identical replicas: broadcast rank 0's weights
             for net in (L.NET_G, L.NET_D):

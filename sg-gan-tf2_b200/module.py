@@ -45,9 +45,11 @@ class Runtime:
 
     @classmethod
     def get(cls, batch, height, width, **kw):
+        """Cached plan for stand-alone forward calls; one at a time (workspaces are GBs).  A runtime that owns a
+        network's weights stays alive through that network's reference even after it leaves the cache."""
         key = (batch, height, width, tuple(sorted(kw.items())))
         if key not in cls._cache:
-            cls._cache.clear()  # one live plan at a time: workspaces are GBs
+            cls._cache.clear()
             cls._cache[key] = cls(batch, height, width, **kw)
         return cls._cache[key]
 
@@ -72,15 +74,34 @@ class _Net:
         return self._vars
 
     def bind(self, runtime):
-        """Move the variables into `runtime`'s flat parameter buffer (they become views of it)."""
+        """Make `runtime` the OWNER of this network's master weights: the variables move into its flat parameter
+        buffer and become views of it.  If another runtime owned them (a re-plan for a new batch / image size), the
+        Adam slots and the step count are carried over, so the optimizer continues instead of silently restarting."""
         if self.runtime is runtime:
             return
+        old = self.runtime
         eng = runtime.engine
         eng.set_weights(self.net_id, self._vars)
+        if old is not None:
+            for what in (2, 3):  # Adam m, v
+                eng.flat(self.net_id, what).copy_(old.engine.flat(self.net_id, what))
+            L.check(L.lib().sggan_set_step_count(eng.h, max(L.lib().sggan_step_count(eng.h),
+                                                             L.lib().sggan_step_count(old.engine.h))))
         self._vars = eng.tensors(self.net_id, 0)
         self.runtime = runtime
         runtime.bound[self.net_id] = self
         eng.weights_changed()
+
+    def _infer_runtime(self, key_kw, batch, height, width):
+        """A runtime for an off-plan forward call (e.g. sampling one image in the middle of training,
+        model.py:528-532): it gets a COPY of the current master weights on every call; ownership stays with the
+        training runtime, so training, save_weights and later samples keep seeing the trained weights."""
+        rt = Runtime.get(batch, height, width, **key_kw)
+        if rt is self.runtime:
+            return rt
+        rt.engine.set_weights(self.net_id, self._vars)
+        rt.engine.weights_changed()
+        return rt
 
     def get_weights(self):
         return [v.detach().cpu().numpy().copy() for v in self._vars]
@@ -143,9 +164,11 @@ class GeneratorResnet(_Net):
             if H < 128 or W < 128:
                 # the discriminator stack needs >= 128 px (Appendix B); plan it on a dummy grid instead
                 raise L.SgganError("generator_resnet: images smaller than 128x128 are not supported by the joint plan")
-            rt = Runtime.get(B, H, W, **kw)
-            self.runtime = None
-            self.bind(rt)
+            if rt is None:
+                rt = Runtime.get(B, H, W, **kw)
+                self.bind(rt)
+            else:
+                rt = self._infer_runtime(kw, B, H, W)
         return rt.engine.gen_forward(x)
 
 
@@ -178,9 +201,12 @@ class Discriminator(_Net):
         want = (B, H, W, int(mask.shape[1]), int(mask.shape[2]))
         if rt is None or (rt.cfg.batch, rt.cfg.image_height, rt.cfg.image_width, rt.cfg.mask_height,
                           rt.cfg.mask_width) != want:
-            rt = Runtime.get(B, H, W, segment_class=self.segment_class, mask_hw=(mask.shape[1], mask.shape[2]))
-            self.runtime = None
-            self.bind(rt)
+            kw = dict(segment_class=self.segment_class, mask_hw=(int(mask.shape[1]), int(mask.shape[2])))
+            if rt is None:
+                rt = Runtime.get(B, H, W, **kw)
+                self.bind(rt)
+            else:
+                rt = self._infer_runtime(kw, B, H, W)
         return rt.engine.disc_forward(x, mask)
 
 

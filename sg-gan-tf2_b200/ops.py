@@ -116,7 +116,7 @@ def instance_norm_bwd_raw(x, gamma, beta, dz, eps=1e-3, act=None, alpha=0.3):
     dx = torch.empty_like(x)
     dg = torch.empty(Cc, dtype=torch.float32, device=x.device)
     dbt = torch.empty(Cc, dtype=torch.float32, device=x.device)
-    ws = _workspace(x.numel() * 6 + 2 * B * Cc * 8 + 8192, x.device)
+    ws = _workspace(x.numel() * 6 + 2 * B * Cc * 8 + 160 * Cc * 8 + 16384, x.device)
     P = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     L.check(L.lib().sggan_instance_norm_bwd(P(x), P(gamma), P(beta), P(dz), P(dx), P(dg), P(dbt), B, H, W, Cc, eps, _ACT[act],
                                             alpha, P(ws), ws.numel(), L.stream_ptr()))

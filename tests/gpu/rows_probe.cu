@@ -25,7 +25,7 @@ using namespace sggan;
 
 struct Set {
   sg_bf16 *Y, *X, *R, *dX, *dY, *gat;
-  float *part, *stats, *sums, *gamma, *beta, *dg, *db;
+  float *part, *stats, *sums, *gamma, *beta, *bpart;
 };
 
 int main(int argc, char** argv) {
@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&s.dX, ndX * 2)); CK(cudaMalloc(&s.dY, ndY * 2 + 4096)); CK(cudaMalloc(&s.gat, nY * 2));
     CK(cudaMalloc(&s.part, size_t(B) * T * C * 8)); CK(cudaMalloc(&s.stats, size_t(B) * C * 8));
     CK(cudaMalloc(&s.sums, size_t(B) * C * 8)); CK(cudaMalloc(&s.gamma, C * 4)); CK(cudaMalloc(&s.beta, C * 4));
-    CK(cudaMalloc(&s.dg, C * 4)); CK(cudaMalloc(&s.db, C * 4));
+    CK(cudaMalloc(&s.bpart, in_bwd_partials_bytes(C))); CK(cudaMemset(s.bpart, 0, in_bwd_partials_bytes(C)));
     CK(cudaMemcpy(s.Y, h.data(), nY * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.R, h.data(), nX * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.dX, h.data(), ndX * 2, cudaMemcpyHostToDevice));
@@ -58,7 +58,7 @@ int main(int argc, char** argv) {
     CK(cudaMemset(s.X, 0, nX * 2)); CK(cudaMemset(s.dY, 0, ndY * 2));
   }
   long long* dbg;
-  CK(cudaMalloc(&dbg, 4096 * 8 * 8));
+  CK(cudaMalloc(&dbg, 8 * 256 * 16 * 8));
   cudaStream_t st;
   CK(cudaStreamCreate(&st));
   cudaEvent_t e0, e1;
@@ -81,15 +81,16 @@ int main(int argc, char** argv) {
     p.beta = s.beta; p.eps = 1e-3f; p.act = SG_ACT_RELU;
     p.g1.ptr = s.dX; p.g1.f32 = 0; p.g1.Hs = H + 2; p.g1.Ws = P; p.g1.oy = 1; p.g1.ox = 1; p.g1.fold = 1;
     if (gather) { p.g2 = p.g1; p.g2.ptr = s.R; p.gather_dst = s.gat; }
-    p.sums = s.sums; p.dst = s.dY; p.dmap = dym; p.dgamma = s.dg; p.dbeta = s.db; p.nb_param = B;
+    p.sums = s.sums; p.sums_part = s.bpart; p.dst = s.dY; p.dmap = dym;
     if (which == 0) launch_in_bwd_reduce(p, st);
-    else { p.gather_dst = nullptr; launch_in_bwd_apply(p, st); }
+    else { p.gather_dst = nullptr; p.sums_nblk = 148 / B > 0 ? 148 / B : 1; launch_in_bwd_apply(p, st); }
   };
   struct Case { const char* name; int kind; double mb; };
   const double mY = nY * 2 / 1e6;
   Case cases[] = {{"apply (stats given)", 0, 2 * mY},       {"apply + finalize", 1, 2 * mY},
                   {"apply + residual + finalize", 2, 3 * mY}, {"bwd reduce", 3, 2 * mY},
-                  {"bwd reduce + gather", 4, 4 * mY},        {"bwd apply", 5, 3 * mY}};
+                  {"bwd reduce + gather", 4, 4 * mY},        {"bwd apply", 5, 3 * mY},
+                  {"bwd reduce -> apply (same set)", 6, 5 * mY}};
   printf("rows_probe B %d H %d W %d C %d  (tensor %.1f MB)  stages %d consumers %d\n", B, H, W, C, mY, kStages, kConsumers);
   for (auto& c : cases) {
     auto run = [&](Set& s) {
@@ -100,6 +101,7 @@ int main(int argc, char** argv) {
         case 3: bwd(s, 0, false); break;
         case 4: bwd(s, 0, true); break;
         case 5: bwd(s, 1, false); break;
+        case 6: bwd(s, 0, false); bwd(s, 1, false); break;
       }
     };
     for (int i = 0; i < NSETS; ++i) run(sets[i]);
@@ -112,27 +114,36 @@ int main(int argc, char** argv) {
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     const double us = ms * 1e3 / ITERS;
-    // (b) phase stamps of one cold launch
-    CK(cudaMemset(dbg, 0, 4096 * 8 * 8));
+    // (b) phase stamps of three back-to-back launches (cycles within a block; %globaltimer across blocks / launches)
+    CK(cudaMemset(dbg, 0, 8 * 256 * 16 * 8));
     CK(cudaMemcpyToSymbol(g_rows_dbg, &dbg, sizeof(dbg)));
-    run(sets[0]);
+    g_rows_dbg_launch = 0;
+    for (int i = 0; i < 3; ++i) run(sets[i]);
     CK(cudaStreamSynchronize(st));
     long long* nullp = nullptr;
     CK(cudaMemcpyToSymbol(g_rows_dbg, &nullp, sizeof(nullp)));
-    std::vector<long long> hd(4096 * 8);
+    std::vector<long long> hd(8 * 256 * 16);
     CK(cudaMemcpy(hd.data(), dbg, hd.size() * 8, cudaMemcpyDeviceToHost));
     double acc[8] = {0};
     int nblk = 0;
-    for (int bk = 0; bk < 4096; ++bk) {
-      const long long* d = &hd[bk * 8];
-      if (d[0] == 0) continue;
-      for (int k = 1; k < 7; ++k) acc[k] += double(d[k] - d[0]);
-      ++nblk;
+    long long s0[3], s1[3], e0[3], e1[3];
+    for (int l = 0; l < 3; ++l) {
+      s0[l] = e0[l] = (1ll << 62); s1[l] = e1[l] = 0;
+      for (int bk = 0; bk < 256; ++bk) {
+        const long long* d = &hd[(l * 256 + bk) * 16];
+        if (d[0] == 0) continue;
+        s0[l] = std::min(s0[l], d[8]); s1[l] = std::max(s1[l], d[8]);
+        e0[l] = std::min(e0[l], d[9]); e1[l] = std::max(e1[l], d[9]);
+        if (l == 1) { for (int k = 1; k < 7; ++k) acc[k] += double(d[k] - d[0]); ++nblk; }
+      }
     }
     printf("%-30s %7.2f us/launch  %6.0f GB/s (algorithmic %.0f MB) | blocks %d, avg cycles from block start: dep-wait %.0f "
            "coeffs %.0f first-chunk %.0f last-load-issued %.0f last-consumed %.0f end %.0f\n",
            c.name, us, c.mb / us * 1e3, c.mb, nblk, acc[1] / nblk, acc[2] / nblk, acc[3] / nblk, acc[6] / nblk,
            acc[4] / nblk, acc[5] / nblk);
+    printf("    launch 2 of 3 (ns): first block start 0, last block start %lld, first block end %lld, last block end %lld | "
+           "previous launch's last block ended at %lld, next launch's first block started at %lld\n",
+           s1[1] - s0[1], e0[1] - s0[1], e1[1] - s0[1], e1[0] - s0[1], s0[2] - s0[1]);
   }
   return 0;
 }

@@ -651,7 +651,8 @@ static int run_mma_rate() {
 // ------------------------------------------------------------------------------------------
 // Experiment: L2 -> SM delivery rate of TMA tiles when the CTAs of a cluster all need the SAME tile
 // (unicast: every CTA loads it; multicast: each CTA loads 1/csz of it for everybody).
-__global__ void __launch_bounds__(64, 1) tma_share_kernel(const __grid_constant__ CUtensorMap tm, int iters, int mode,
+__global__ void __launch_bounds__(64, 1) tma_share_kernel(const __grid_constant__ CUtensorMap tm,
+                                                          const __grid_constant__ CUtensorMap tm_strided, int iters, int mode,
                                                           int ntiles, long long* cycles_out, const uint8_t* raw) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -672,9 +673,15 @@ __global__ void __launch_bounds__(64, 1) tma_share_kernel(const __grid_constant_
     for (int it = 0; it < iters; ++it) {
       const int s = it & 3;
       mbar_wait(&empty[s], ((it >> 2) & 1) ^ 1, 71);
-      const int tile = int((uint64_t(cid) * 977u + uint64_t(it)) % uint64_t(ntiles));
+      int tile = int((uint64_t(cid) * 977u + uint64_t(it)) % uint64_t(ntiles));
+      if (mode == 5 || mode == 6) tile = it % 36;  // every CTA walks the SAME 36 tiles (1.2 MB: one layer's weights)
       mbar_arrive_expect_tx(&full[s], kTileBytes);
-      if (mode == 0) {
+      if (mode == 4 || mode == 6) {
+        // rows of 128 B strided by 512 B (a 64-channel slice of a [pixel][256 channel] tensor): tile -> (row block, slice)
+        const int rb = tile >> 2, cb = tile & 3;
+        tma_load_2d(&tm_strided, &full[s], smem + s * kTileBytes, cb * 64, rb * kRows);
+        tma_load_2d(&tm_strided, &full[s], smem + s * kTileBytes + kTileBytes / 2, cb * 64, rb * kRows + kRows / 2);
+      } else if (mode == 0 || mode == 5) {
         tma_load_2d(&tm, &full[s], smem + s * kTileBytes, 0, tile * kRows);
         tma_load_2d(&tm, &full[s], smem + s * kTileBytes + kTileBytes / 2, 0, tile * kRows + kRows / 2);
       } else if (mode == 2) {  // the same bytes as ONE 1-D bulk copy (what the row-stream kernels issue)
@@ -712,15 +719,17 @@ static int run_tma_share() {
   uint16_t* d;
   CK(cudaMalloc(&d, rows * 128));
   CK(cudaMemset(d, 0, rows * 128));
-  CUtensorMap tm;
+  CUtensorMap tm, tm_strided;
   int r = make_tmap_bf16_2d(&tm, d, 64, rows, 128, 64, 128);
   if (r) { printf("tmap failed %d\n", r); return 1; }
+  r = make_tmap_bf16_2d(&tm_strided, d, 256, rows / 4, 512, 64, 128);  // the same memory seen as [rows/4][256 channels]
+  if (r) { printf("strided tmap failed %d\n", r); return 1; }
   long long* dc;
   CK(cudaMalloc(&dc, 148 * sizeof(long long)));
   CK(cudaFuncSetAttribute(tma_share_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 32768 + 1024));
   const int iters = 2000, ntiles = int(rows / 256);
   for (int csz : {1, 2}) {
-    for (int mode : {0, 1, 2, 3}) {
+    for (int mode : {0, 1, 2, 3, 4, 5, 6}) {
       if (csz == 1 && mode == 1) continue;
       if (csz == 2 && mode >= 2) continue;
       cudaLaunchConfig_t cfg = {};
@@ -732,7 +741,7 @@ static int run_tma_share() {
       at[0].val.clusterDim.x = csz; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       for (int rep = 0; rep < 2; ++rep) {
-        cudaError_t e = cudaLaunchKernelEx(&cfg, tma_share_kernel, tm, iters, mode, ntiles, dc, (const uint8_t*)d);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tma_share_kernel, tm, tm_strided, iters, mode, ntiles, dc, (const uint8_t*)d);
         if (e != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); return 1; }
         e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("sync failed: %s (watchdog %d)\n", cudaGetErrorString(e), read_tc_watchdog()); return 1; }
@@ -743,7 +752,7 @@ static int run_tma_share() {
       for (auto v : h) avg += double(v);
       avg /= 148;
       printf("TMA_SHARE cluster %d %s: %.1f B/clk delivered per SM (%.0f cycles per 32 KB tile), chip %.0f B/clk\n", csz,
-             mode == 1 ? "multicast" : (mode == 0 ? "unicast 2-D boxes" : (mode == 2 ? "1-D bulk 32 KB" : "1-D bulk 2x16 KB")), iters * 32768.0 / avg, avg / iters, 148 * iters * 32768.0 / avg);
+             mode == 1 ? "multicast" : (mode == 0 ? "unicast 2-D boxes" : (mode == 2 ? "1-D bulk 32 KB" : (mode == 3 ? "1-D bulk 2x16 KB" : (mode == 4 ? "2-D boxes, 128 B rows strided by 512 B" : (mode == 5 ? "dense boxes, all CTAs read the same 36 tiles" : "strided boxes, all CTAs read the same 36 tiles"))))), iters * 32768.0 / avg, avg / iters, 148 * iters * 32768.0 / avg);
     }
   }
   return 0;

@@ -475,3 +475,41 @@ def test_config_sweep():
                          text=True, timeout=900)
     assert out.returncode == 0 and "DEVIATES" not in out.stdout and "rejected loudly" in out.stdout, \
         out.stdout[-3000:] + out.stderr[-1000:]
+
+
+def test_master_weights_have_one_owner(L, O, tmp_path):
+    """sampling at another shape in the middle of training (the reference's sample_model /
+    generate_test_images, model.py:528-532) must not move the master weights away from the training engine: later
+    steps, save_weights and later samples all have to see the TRAINED weights; a re-plan carries Adam over."""
+    M = importlib.import_module("sg-gan-tf2_b200.model")
+    ns = argparse.Namespace(batch_size=1, image_width=256, image_height=128, segment_class=34, use_resnet=True,
+                            checkpoint_dir=str(tmp_path), dataset_dir="city")
+    m = M.sggan(ns)
+    real_A, seg_A, mask, _ = O.synthetic_batch(2, 128, 256, 34, seed=2)
+    m.real_A, m.seg_A, m.mask_A = real_A[:1], seg_A[:1], mask[:1]
+    m.train_step(ns)
+    rt = m.runtime
+    w1 = rt.engine.flat(L.NET_G, 0).clone()
+    sample = m.generate_test_images(real_A)          # batch 2: off-plan forward
+    assert m.generator.runtime is rt and m.runtime is rt, "sampling must not take ownership of the weights"
+    assert rel(sample[:1], m.generate_test_images(real_A[:1])) < 1e-2  # same weights on both plans
+    m.train_step(ns)
+    w2 = rt.engine.flat(L.NET_G, 0)
+    assert (w2 - w1).abs().max() > 1e-4              # the training engine kept training
+    for v, t in zip(m.generator.trainable_variables, rt.engine.tensors(L.NET_G, 0)):
+        assert v.data_ptr() == t.data_ptr()          # the variables ARE the engine's parameters
+    m.save(str(tmp_path), 1)
+    m2 = M.sggan(ns)
+    assert m2.load(str(tmp_path))
+    got = torch.cat([v.reshape(-1).cpu() for v in m2.generator.trainable_variables])
+    assert torch.equal(got, w2.cpu())                # the checkpoint holds the trained weights, not a stale copy
+    # a later sample at the other shape sees the new weights too
+    assert rel(m.generate_test_images(real_A)[:1], m.generate_test_images(real_A[:1])) < 1e-2
+    # re-plan (new batch size): Adam slots and the step count move with the weights
+    steps = L.lib().sggan_step_count(rt.engine.h)
+    mG = rt.engine.flat(L.NET_G, 2).clone()
+    m.real_A, m.seg_A, m.mask_A = real_A, seg_A, mask
+    rt2 = m._ensure_runtime(2, 128, 256, (int(mask.shape[1]), int(mask.shape[2])))
+    assert rt2 is not rt and m.generator.runtime is rt2 and m.discriminator.runtime is rt2
+    assert L.lib().sggan_step_count(rt2.engine.h) == steps == 2
+    assert torch.equal(rt2.engine.flat(L.NET_G, 2), mG) and torch.equal(rt2.engine.flat(L.NET_G, 0), w2)
