@@ -42,9 +42,21 @@ def parse():
     ap.add_argument("--height", type=int, default=256)
     ap.add_argument("--width", type=int, default=512)
     ap.add_argument("--classes", type=int, default=34)
+    ap.add_argument("--config", default=None, choices=["c2", "c3", "c5"],
+                    help="BASELINE.json configs: c2 generator-only inference 256x512 batch 1; c3 (default) full step 256x512 "
+                         "batch 8 C=34; c5 full step 512x1024 batch 4 C=19")
+    ap.add_argument("--loss-mode", default="p2p", choices=["p2p", "sggan"])
+    ap.add_argument("--sustained-seconds", type=float, default=5.0, help="length of the extra power-capped-regime loop (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == "c2":
+        a.batch, a.height, a.width, a.classes = 1, 256, 512, 34
+    elif a.config == "c5":
+        a.batch, a.height, a.width, a.classes = 4, 512, 1024, 19
+    elif a.config == "c3":
+        a.batch, a.height, a.width, a.classes = 8, 256, 512, 34
+    return a
 
 
 class ClockSampler(threading.Thread):
@@ -155,11 +167,21 @@ def main():
     mask_h = (ids[..., None] == np.arange(C)).astype(np.float32)
     real_d, seg_d, mask_d = (torch.as_tensor(x).cuda() for x in (real_h, seg_h, mask_h))
 
-    ns = argparse.Namespace(batch_size=B, image_width=W, image_height=H, segment_class=C, use_resnet=True)
+    ns = argparse.Namespace(batch_size=B, image_width=W, image_height=H, segment_class=C, use_resnet=True,
+                            loss_mode=args.loss_mode)
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):  # the builders print their names like the reference (module.py:220,273)
         model = M.sggan(ns)
-    model.real_A, model.seg_A, model.mask_A = real_d, seg_d, mask_d
+    infer = args.config == "c2"
+    if infer:
+        # BASELINE config 2: generator-only inference (model.py:528-532); the plan is made by the first call
+        def step():
+            return model.generate_test_images(real_d)
+    else:
+        model.real_A, model.seg_A, model.mask_A = real_d, seg_d, mask_d
+
+        def step():
+            model.train_step(ns)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -167,53 +189,107 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
     for _ in range(max(args.warmup, 3)):
-        model.train_step(ns)
-    eng = model.runtime.engine
+        step()
+    eng = (model.generator.runtime if infer else model.runtime).engine
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # ---- timed region 1: inputs resident in HBM
+    # ---- timed region 1: inputs resident in HBM, nothing but the step's own launches on the stream
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.profile_begin(18 * args.steps + 8)
     e0.record()
     for _ in range(args.steps):
-        model.train_step(ns)
+        step()
     e1.record()
     sync_all()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = eng.kernel_launches
-    conv_ms, conv_n, conv_flops = eng.profile_end()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    losses = [float(model.gen_loss), float(model.disc_loss)]
+    losses = None if infer else [float(model.gen_loss), float(model.disc_loss)]
+    clocks_timed = sampler.summary() if rank == 0 else None
     # ---- timed region 2: end to end through the reference-facing API with host batches
     e2e = None
     if not args.no_e2e:
         # host batches in page-locked memory (made once, outside the timed region); every timed step copies them
-        # host -> device and reads both losses back
-        model.real_A, model.seg_A, model.mask_A = (torch.from_numpy(x).pin_memory() for x in (real_h, seg_h, mask_h))
+        # host -> device and reads the step's result back
+        real_p, seg_p, mask_p = (torch.from_numpy(x).pin_memory() for x in (real_h, seg_h, mask_h))
+        if infer:
+            out_host = torch.empty((B, H, W, 3), dtype=torch.float32).pin_memory()
+
+            def step_e2e():
+                out_host.copy_(model.generate_test_images(real_p), non_blocking=True)
+                torch.cuda.current_stream().synchronize()  # the caller reads the image (model.py:561-567 saves it)
+            h2d, d2h = int(real_h.nbytes), int(out_host.numel() * 4)
+        else:
+            model.real_A, model.seg_A, model.mask_A = real_p, seg_p, mask_p
+
+            def step_e2e():
+                model.train_step(ns)
+                return (float(model.gen_loss), float(model.disc_loss))  # the reference prints both every step (model.py:260)
+            h2d, d2h = int(real_h.nbytes + seg_h.nbytes + mask_h.nbytes), 8
         for _ in range(2):
-            model.train_step(ns)
-            float(model.gen_loss)
+            step_e2e()
         sync_all()
         e0.record()
         for _ in range(args.steps):
-            model.train_step(ns)
-            _ = (float(model.gen_loss), float(model.disc_loss))  # the reference prints both every step (model.py:260)
+            step_e2e()
         e1.record()
         sync_all()
-        ms2 = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms2], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms2 = t.item()
-        e2e = {"value": B * world * args.steps / (ms2 * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(real_h.nbytes + seg_h.nbytes + mask_h.nbytes), "d2h_bytes_per_step": 8,
-               "ms_per_step": ms2 / args.steps}
+        ms2 = max_over_ranks(e0.elapsed_time(e1))
+        e2e = {"value": B * world * args.steps / (ms2 * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms2 / args.steps}
+        if not infer:
+            model.real_A, model.seg_A, model.mask_A = real_d, seg_d, mask_d
+    # ---- profiling passes (separate from the timed regions: the events sit between the step's launches): the
+    #      residual-block convolution (tensor roofline) and the two instance-norm passes around it (HBM roofline)
+    prof = {}
+    if not infer:
+        for kind in (0, 1, 2):
+            eng.profile_begin(18 * max(4, min(args.steps, 10)) + 8, kind=kind)
+            for _ in range(max(4, min(args.steps, 10))):
+                step()
+            sync_all()
+            prof[kind] = eng.profile_end()  # (ms, launches, work per launch)
+    else:
+        eng.profile_begin(18 * 12 + 8, kind=0)
+        for _ in range(10):
+            step()
+        sync_all()
+        prof[0] = eng.profile_end()
+        eng.profile_begin(18 * 12 + 8, kind=1)
+        for _ in range(10):
+            step()
+        sync_all()
+        prof[1] = eng.profile_end()
+    # ---- sustained regime: the same step for several seconds (the 20-step region above is a 0.2 s burst that never
+    #      reaches the 1 kW power cap); its own clock summary
+    sustained = None
+    if args.sustained_seconds > 0 and not infer:
+        n_s = max(args.steps, int(args.sustained_seconds * 1e3 / (ms / args.steps)))
+        if rank == 0:
+            sampler.rows = []
+        sync_all()
+        e0.record()
+        for _ in range(n_s):
+            step()
+        e1.record()
+        sync_all()
+        ms3 = max_over_ranks(e0.elapsed_time(e1))
+        eng.profile_begin(18 * 12 + 8, kind=0)
+        for _ in range(10):
+            step()
+        sync_all()
+        c_ms, c_n, c_fl = eng.profile_end()
+        sustained = {"steps": n_s, "seconds": ms3 * 1e-3, "value": B * world * n_s / (ms3 * 1e-3), "unit": UNIT,
+                     "ms_per_step": ms3 / n_s, "clocks": sampler.summary() if rank == 0 else None,
+                     "conv_tflops_after": (c_fl * c_n / (c_ms * 1e-3) / 1e12) if c_ms > 0 else None}
     sampler.stop_flag = True
     if rank != 0:
         if world > 1:
@@ -225,32 +301,66 @@ def main():
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_burst = peaks.get("bf16_tflops", 1590.0)
+    peak_hbm = peaks.get("hbm_gbs", 6650.0)
+    src = "MEASURED_PEAKS.json (of measured)" if peaks else "B200_PROFILING.md fallback (of fallback)"
+    conv_ms, conv_n, conv_flops = prof[0]
     achieved = conv_flops * conv_n / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
     ms_step = ms / args.steps
     value = B * world * args.steps / (ms * 1e-3)
     gf = GFLOP_PER_IMG.get((H, W, C))
+    # ncu --set full capture of the same kernel (dram__bytes_read.sum + dram__bytes_write.sum per launch); committed
+    # under profiles/, valid for the c3 workload only -- not measured by this run
+    traffic_file = os.path.join(ROOT, "profiles", "r02_ncu_conv_res.json")
+    traffic, traffic_src = None, None
+    if (H, W, B) == (256, 512, 8) and os.path.exists(traffic_file):
+        try:
+            tj = json.load(open(traffic_file))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r02_ncu_conv_res.json (ncu --set full, not measured in this run)"
+        except Exception:
+            pass
+
+    def hbm_obj(kind, name):
+        if kind not in prof or prof[kind][0] <= 0:
+            return None
+        t_ms, n_l, bytes_l = prof[kind]
+        gbs = bytes_l * n_l / (t_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm, "traffic": None,
+                "kernel": "%s (%d launches timed with CUDA events in a separate pass; algorithmic %.1f MB per launch, "
+                          "%.1f us per launch)" % (name, n_l, bytes_l / 1e6, t_ms * 1e3 / n_l), "peak_source": src}
+
+    if infer:
+        metric = "G inference img/s at %dx%d" % (H, W)
+        workload = ("SG-GAN generator_resnet (9 blocks) inference A->B, %dx%d, batch %d (BASELINE config 2: forward conv / "
+                    "deconv + instance_norm path)" % (H, W, B))
+    else:
+        metric = METRIC if (H, W) == (256, 512) else "G+D train img/s at %dx%d" % (H, W)
+        workload = ("SG-GAN full G+D train step (generator_resnet 9 blocks + semantic-aware D, fwd+bwd+Adam), "
+                    "%dx%d, batch %d per GPU, C=%d, loss %s" % (H, W, B, C, args.loss_mode))
     line = {
-        "metric": METRIC if (H, W) == (256, 512) else "G+D train img/s at %dx%d" % (H, W), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "SG-GAN full G+D train step (generator_resnet 9 blocks + semantic-aware D, fwd+bwd+Adam), "
-                               "%dx%d, batch %d per GPU, C=%d, loss p2p" % (H, W, B, C),
-                   "global_batch": B * world, "parallelism": "dp%d" % world,
+        "config": {"workload": workload, "global_batch": B * world, "parallelism": "dp%d" % world,
                    "l2": "working set %.1f GB per step >> 126 MB L2 (no flush needed)" % (L.workspace_bytes(eng.cfg) / 2 ** 30)},
-        "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches * args.steps,
+        "clocks": clocks_timed, "e2e": e2e, "gpu_launches": launches * args.steps,
         "losses_last_step": losses,
-        "step_tflops": (gf * B / ms_step) if gf else None,
+        "step_tflops": (gf * B / ms_step) if (gf and not infer) else None,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (achieved / peak_tf) if achieved else None,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one such launch at 256x512 batch 8 from the
-                     # ncu --set full capture summarised in profiles/r01_ncu_conv_res_summary.txt (the 33.6 MB
-                     # output mostly stays in the 126 MB L2); only valid for that workload
-                     "traffic": 37.8e6 if (H, W, B) == (256, 512, 8) else None, "traffic_unit": "bytes/launch",
+                     "frac_of_burst_peak": (achieved / peak_burst) if achieved else None, "peak_burst": peak_burst,
+                     "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
                      "kernel": "conv_gemm_tc_kernel, residual-block 3x3 256->256 forward (%d launches timed with CUDA events "
-                               "inside the steps; algorithmic %.2f GFLOP per launch)" % (conv_n, conv_flops / 1e9),
-                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback"},
+                               "in a separate pass after the timed region; algorithmic %.2f GFLOP per launch)" % (conv_n, conv_flops / 1e9),
+                     "peak_source": "bf16_tflops_sustained / bf16_tflops of " + src},
+        "roofline_hbm": [x for x in (hbm_obj(1, "row_stream_kernel<APPLY>: instance norm + ReLU + reflect-pad frame behind the first "
+                                                 "conv of each residual block, read Y + write X"),
+                                     hbm_obj(2, "row_stream_kernel<BWD_REDUCE> + <BWD_APPLY>: instance-norm backward of the same layers (two "
+                                                "launches timed together, side stream joined first); algorithmic = read Y + read dX + "
+                                                "write dY, the reduce pass re-reads Y and dX on top of that")) if x],
+        "sustained": sustained,
     }
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and not infer:
         line["cpu_baseline"] = cpu_baseline(H, W, C, 3, 1)[0]
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -113,8 +113,13 @@ const float* sggan_last_fake(const sggan_handle* h);
 
 /* Device-side timing of the dominant kernel: CUDA events on the step's stream around every launch of the
  * residual-block 3x3 convolution (forward) while profiling is on.  flops_per_launch = algorithmic
- * 2*B*H*W*Cin*Cout*9 of one launch. */
+ * 2*B*H*W*Cin*Cout*9 of one launch (bytes for the norm passes, see sggan_profile_select).  The events sit between
+ * the launches of the step's stream, so they perturb it slightly: profile in a separate pass, not in a timed one. */
 int sggan_profile_begin(sggan_handle* h, int max_launches);
+/* Which launches sggan_profile_begin/end bracket (default 0): 0 = the residual-block 3x3 convolutions (forward; work =
+ * FLOPs), 1 = the instance-norm + ReLU apply pass behind the first convolution of every block (work = algorithmic bytes:
+ * read Y, write the next frame), 2 = the instance-norm backward of the same layers (read Y and dX, write dY). */
+int sggan_profile_select(sggan_handle* h, int kind);
 int sggan_profile_end(sggan_handle* h, double* total_ms, int* launches, double* flops_per_launch);
 
 /* Debug / test access to internal activations.  kind: 0 input frame X, 1 raw conv output Y,
@@ -169,6 +174,12 @@ int sggan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int
 /* one_hot + nearest resample of a class-id map to the D logit grid (utils.py:158-165,190):
  * ids [B,H,W] uint8 -> mask [B,hd,wd,C] fp32 */
 int sggan_onehot_mask(const uint8_t* ids, float* mask, int B, int H, int W, int hd, int wd, int C, void* stream);
+/* one_hot + scipy.ndimage.zoom(..., order 3, mode "nearest") of the class-id map -- the loader's mask construction
+ * (utils.py:190,197-199) -- without the one-hot volume: mask[b,i,j,c] = round(sum_y sum_x wy[i][y] wx[j][x] [ids == c]).
+ * wy [ho][wh] / wx [wo][ww]: windows of the per-axis spline weights (fp64, device), y0 [ho] / x0 [wo]: first input row /
+ * column of each window (host helper: utils.zoom_weights).  ids [B,H,W] uint8 -> mask [B,ho,wo,C] fp32 (integers). */
+int sggan_zoom_mask(const uint8_t* ids, const double* wy, const int* y0, const double* wx, const int* x0, int wh, int ww,
+                    float* mask, int B, int H, int W, int ho, int wo, int C, void* stream);
 /* RGB -> class id LUT (segment_class.py:60-70,95-97): rgb [n,3] uint8 -> ids [n] uint8 */
 int sggan_rgb_to_class(const uint8_t* rgb, uint8_t* ids, int64_t n, void* stream);
 

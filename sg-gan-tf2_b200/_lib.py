@@ -65,6 +65,7 @@ SYMBOLS = {
     "sggan_kernel_launches": (_I, [_P]),
     "sggan_last_fake": (_P, [_P]),
     "sggan_profile_begin": (_I, [_P, _I]),
+    "sggan_profile_select": (_I, [_P, _I]),
     "sggan_profile_end": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I), C.POINTER(C.c_double)]),
     "sggan_debug_buffer": (_P, [_P, _I, _I, _I, C.POINTER(_I64)]),
     "sggan_num_layers": (_I, [_P, _I]),
@@ -84,6 +85,7 @@ SYMBOLS = {
     "sggan_adam_step": (_I, [_P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _P]),
     "sggan_onehot_mask": (_I, [_P, _P] + [_I] * 6 + [_P]),
     "sggan_rgb_to_class": (_I, [_P, _P, _I64, _P]),
+    "sggan_zoom_mask": (_I, [_P, _P, _P, _P, _P, _I, _I, _P] + [_I] * 6 + [_P]),
 }
 
 _lib = None
@@ -263,7 +265,10 @@ class Engine:
         n = c.batch * c.image_height * c.image_width * 3
         return self.workspace[off:off + 4 * n].view(torch.float32).view(c.batch, c.image_height, c.image_width, 3)
 
-    def profile_begin(self, max_launches=8192):
+    def profile_begin(self, max_launches=8192, kind=0):
+        """kind 0: residual-block convolutions (work = FLOPs); 1: their norm-apply passes; 2: their norm backward
+        (work = algorithmic bytes)."""
+        check(lib().sggan_profile_select(self.h, kind))
         check(lib().sggan_profile_begin(self.h, max_launches))
 
     def profile_end(self):

@@ -227,6 +227,11 @@ int sggan_profile_begin(sggan_handle* h, int max_launches) {
   e.prof_on = true;
   return 0;
 }
+int sggan_profile_select(sggan_handle* h, int kind) {
+  if (kind < 0 || kind > 2) { g_err = "profile kind must be 0, 1 or 2"; return SGGAN_E_INVALID; }
+  h->e.prof_kind = kind;
+  return 0;
+}
 int sggan_profile_end(sggan_handle* h, double* total_ms, int* launches, double* flops_per_launch) {
   Engine& e = h->e;
   e.prof_on = false;
@@ -240,7 +245,12 @@ int sggan_profile_end(sggan_handle* h, double* total_ms, int* launches, double* 
   if (total_ms) *total_ms = tot;
   if (launches) *launches = int(e.prof_used / 2);
   const Layer& l = e.G.L[3];
-  if (flops_per_launch) *flops_per_launch = 2.0 * l.nb * l.Hout * l.Wout * double(l.Cout) * l.Cin * l.k * l.k;
+  if (flops_per_launch) {
+    const double tensor_bytes = 2.0 * l.nb * l.Hout * l.Wout * double(l.Cout);  // one bf16 activation tensor of the layer
+    if (e.prof_kind == 0) *flops_per_launch = 2.0 * l.nb * l.Hout * l.Wout * double(l.Cout) * l.Cin * l.k * l.k;
+    else if (e.prof_kind == 1) *flops_per_launch = 2.0 * tensor_bytes;  // read Y, write the next frame
+    else *flops_per_launch = 3.0 * tensor_bytes;                        // read Y and dX, write dY
+  }
   return 0;
 }
 
@@ -567,6 +577,50 @@ __global__ void rgb_to_class_kernel(const uint8_t* __restrict__ rgb, uint8_t* id
     default: v = 0;
   }
   ids[i] = v;
+}
+// one_hot + scipy.ndimage.zoom(order 3) of a class-id map (utils.py:190,197-199) as ONE pass over the id map: the spline
+// prefilter and the cubic B-spline evaluation are linear and separable, so zoom(one_hot(ids))[i, j, c] =
+// sum_y sum_x wy[i][y] wx[j][x] [ids[y][x] == c] with per-axis weight rows that the host derives once per size
+// (utils.zoom_weights; they decay like 0.27^|d|, so a window of a few dozen pixels carries everything above 1e-18).
+// The reference materialises a 570 MB fp64 one-hot volume and filters it along three axes on the CPU (seconds per
+// file); here a block per output position reads its window of the uint8 map.  fp64, fixed summation order, scipy's
+// rounding of integer outputs (half away from zero).
+__global__ void __launch_bounds__(64) zoom_mask_kernel(const uint8_t* __restrict__ ids, const double* __restrict__ wy,
+                                                       const int* __restrict__ y0, const double* __restrict__ wx,
+                                                       const int* __restrict__ x0, int wh, int ww, float* mask, int H, int W,
+                                                       int ho, int wo, int C) {
+  extern __shared__ uint8_t zsm[];
+  double* swy = reinterpret_cast<double*>(zsm);
+  double* swx = swy + wh;
+  uint8_t* win = reinterpret_cast<uint8_t*>(swx + ww);
+  const int i = blockIdx.x / wo, j = blockIdx.x - i * wo, b = blockIdx.y;
+  const int ys = y0[i], xs = x0[j];
+  for (int t = threadIdx.x; t < wh; t += blockDim.x) swy[t] = wy[int64_t(i) * wh + t];
+  for (int t = threadIdx.x; t < ww; t += blockDim.x) swx[t] = wx[int64_t(j) * ww + t];
+  for (int t = threadIdx.x; t < wh * ww; t += blockDim.x) {
+    const int y = t / ww, x = t - y * ww;
+    win[t] = ids[(int64_t(b) * H + (ys + y)) * W + (xs + x)];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double acc = 0.0;
+    for (int y = 0; y < wh; ++y) {
+      double row = 0.0;
+      const uint8_t* wr = win + y * ww;
+      for (int x = 0; x < ww; ++x) row += (wr[x] == c) ? swx[x] : 0.0;
+      acc += swy[y] * row;
+    }
+    const double r = acc > 0.0 ? acc + 0.5 : acc - 0.5;  // NI_ZoomShift's conversion to an integer output type
+    mask[((int64_t(b) * ho + i) * wo + j) * C + c] = float((long long)r);
+  }
+}
+extern "C" int sggan_zoom_mask(const uint8_t* ids, const double* wy, const int* y0, const double* wx, const int* x0, int wh,
+                               int ww, float* mask, int B, int H, int W, int ho, int wo, int C, void* stream) {
+  if (wh < 1 || ww < 1 || wh > H || ww > W || C < 1 || C > 256) return SGGAN_E_INVALID;
+  const size_t smem = size_t(wh + ww) * sizeof(double) + size_t(wh) * ww;
+  if (smem > 48 * 1024) return SGGAN_E_INVALID;
+  zoom_mask_kernel<<<dim3(ho * wo, B), 64, smem, (cudaStream_t)stream>>>(ids, wy, y0, wx, x0, wh, ww, mask, H, W, ho, wo, C);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
 extern "C" int sggan_onehot_mask(const uint8_t* ids, float* mask, int B, int H, int W, int hd, int wd, int C,
                                  void* stream) {

@@ -433,7 +433,7 @@ static Layer make_layer(Net& n, LayerType type, int k, PadMode pad, int Cin, int
   Layer l;
   l.type = type; l.k = k; l.pad = pad; l.Cin = Cin; l.Cout = Cout; l.Hin = Hin; l.Win = Win;
   l.has_norm = norm; l.act = act; l.alpha = alpha; l.nb = nb; l.nbv = nbv;
-  l.X = l.Y = l.dY = nullptr; l.dX = nullptr; l.Yf32 = nullptr; l.stats = l.bsums = l.stats_part = nullptr; l.Wf = l.Wd = nullptr;
+  l.X = l.Y = l.dY = nullptr; l.dX = nullptr; l.Yf32 = nullptr; l.stats = l.bsums = l.stats_part = nullptr; l.bsync = nullptr; l.Wf = l.Wd = nullptr;
   l.wscratch = nullptr;
   l.ti_w = int(n.T.size());
   if (type == LT_DECONV) add_tensor(n, 4, k, k, Cout, Cin); else add_tensor(n, 4, k, k, Cin, Cout);
@@ -499,6 +499,7 @@ void Engine::alloc_and_prepare(Net& n, Arena& a, bool zero_part) {
       l.stats = l.has_norm ? (float*)a.take(size_t(l.nb) * l.Cout * 2 * 4) : nullptr;
       l.stats_part = l.has_norm ? (float*)a.take(size_t(l.nb) * l.stats_T_max * l.Cout * 2 * 4) : nullptr;
       l.bsums = l.has_norm ? (float*)a.take(size_t(l.nbv) * l.Cout * 2 * 4) : nullptr;
+      l.bsync = l.has_norm ? (int*)a.take(size_t(l.nbv) * sizeof(int)) : nullptr;  // arrival counters of the fused norm backward
       l.wscratch = l.wscratch_elems ? (float*)a.take(size_t(l.wscratch_elems) * 4) : nullptr;
     }
     return;
@@ -735,6 +736,18 @@ void Engine::in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb
   p.g1 = g1; p.g2 = g2; p.sums = l.bsums; p.sums_part = in_part; p.dst = l.dY; p.dmap = l.dymap;
   (void)nb_param;  // dgamma / dbeta are taken from l.bsums by run_wgrad (side stream)
   p.gather_dst = gather_dst;  // reduce pass also materialises g1 + g2 (the residual-stream gradient) ...
+  // Opt-in (SGGAN_FUSE_INBWD=1): both passes in ONE launch, the blocks of an image meeting on l.bsync.  Measured on
+  // B200 it is correct but not faster than the two launches (55 us vs 52 us at the residual blocks): every block waits
+  // for the slowest block of its image at the barrier, and pass 2 starts with an empty pipeline because all stages
+  // still hold pass-1 data (DESIGN.md, row streams).
+  static const bool fused = []() { const char* e = getenv("SGGAN_FUSE_INBWD"); return e && e[0] == '1'; }();
+  if (fused) {
+    p.sync_ctr = l.bsync;
+    const int r = launch_in_bwd_fused(p, st);
+    if (r < 0 && glue_err == 0) glue_err = 5;
+    ++nlaunch;
+    return;
+  }
   const int nblk = launch_in_bwd_reduce(p, st);
   if (nblk <= 0) { if (glue_err == 0) glue_err = 2; return; }
   if (gather_dst != nullptr) {  // ... which is then the single source of the apply pass
@@ -758,15 +771,18 @@ int Engine::gen_forward(const float* real_A, float* fake_out) {
   for (int li = 0; li < nl; ++li) {
     Layer& l = G.L[li];
     const bool in_block = (li >= 3 && li < 3 + 2 * cfg.n_blocks);
-    const bool timed = prof_on && in_block && prof_used + 2 <= prof_ev.size();
+    const bool block_b = in_block && ((li - 3) & 1) == 1;
+    const bool timed = prof_on && prof_kind == 0 && in_block && prof_used + 2 <= prof_ev.size();
     if (timed) cudaEventRecord(prof_ev[prof_used++], st);
     if ((r = run_conv_list(l.fwd))) return r;
     if (timed) cudaEventRecord(prof_ev[prof_used++], st);
     if (!l.has_norm) continue;
     Layer& nx = G.L[li + 1];
-    const bool block_b = in_block && ((li - 3) & 1) == 1;
+    const bool timed_a = prof_on && prof_kind == 1 && in_block && !block_b && prof_used + 2 <= prof_ev.size();
+    if (timed_a) cudaEventRecord(prof_ev[prof_used++], st);
     if (block_b) in_apply(G, li, nx.X, nx.xmap, G.L[li - 1].X, &G.L[li - 1].xmap);  // y + x (module.py:217)
     else in_apply(G, li, nx.X, nx.xmap, nullptr, nullptr);
+    if (timed_a) cudaEventRecord(prof_ev[prof_used++], st);
   }
   if (fake_out != nullptr && fake_out != fake)
     if (cudaMemcpyAsync(fake_out, fake, size_t(B) * H * W * 3 * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return SGGAN_E_CUDA;
@@ -898,7 +914,13 @@ int Engine::step_bwd_g() {
         in_bwd(G, li, gres, no_src(), l.nb, 0, l.nb);
       }
     } else {
+      const bool timed_b = prof_on && prof_kind == 2 && in_blocks && prof_used + 2 <= prof_ev.size();
+      if (timed_b) {  // time the pass alone: without this, the previous layer's weight gradient (side stream) shares the SMs
+        join_side();
+        cudaEventRecord(prof_ev[prof_used++], st);
+      }
       in_bwd(G, li, dx_src(up), no_src(), l.nb, 0, l.nb);
+      if (timed_b) cudaEventRecord(prof_ev[prof_used++], st);
     }
     if ((r = run_wgrad(l, G))) return r;
     if (li == 0) break;

@@ -42,6 +42,7 @@ struct Layer {
   float* Yf32;
   int dxH, dxW, dx_oy, dx_ox, dx_fold, dx_f32;
   float *stats, *bsums;
+  int* bsync;  // per-image arrival counters of the fused norm backward (in the zeroed-every-step range)
   float* stats_part;  // per-tile partial statistics written by the conv epilogue
   int stats_T, stats_T_max;
   sg_bf16 *Wf, *Wd;
@@ -104,6 +105,7 @@ struct Engine {
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
   bool prof_on = false;
+  int prof_kind = 0;  // 0 residual-block conv forward, 1 norm-apply forward of those layers, 2 their norm backward
 
   int build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t stream, bool dry_run, size_t* need);
   int pack_weights(int net, cudaStream_t s = nullptr);

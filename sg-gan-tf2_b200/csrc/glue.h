@@ -19,6 +19,7 @@ void launch_prep_image3(const float* src, int B, int H, int W, sg_bf16* dst, con
 int launch_in_apply(const InApplyParams& p, cudaStream_t st);
 int launch_in_bwd_reduce(const InBwdParams& p, cudaStream_t st);
 int launch_in_bwd_apply(const InBwdParams& p, cudaStream_t st);
+int launch_in_bwd_fused(const InBwdParams& p, cudaStream_t st);  // reduce + apply in one launch (needs sync_ctr)
 size_t in_bwd_partials_bytes(int C);  // size of InBwdParams::sums_part
 
 // out[b,i,j,c] (plain bf16 [B][H][W][C]) = g1 + g2 (either may fold a reflected border back).

@@ -188,6 +188,7 @@ struct InBwdParams {
   float* sums;       // [B][C][2]: reduced (sum dzh, sum dzh * xhat), published by the apply pass (for dgamma / dbeta)
   float* sums_part;  // [B][sums_nblk][C][2] scratch: per-block partials of the reduce pass (in_bwd_partials_bytes(C))
   int sums_nblk;     // apply pass: value returned by launch_in_bwd_reduce
+  int* sync_ctr;     // fused form (launch_in_bwd_fused): [B] arrival counters, zero before the launch
   sg_bf16* dst;
   FrameMap dmap;
   // optional (reduce pass): also store the summed, border-folded gradient g1 + g2 as plain [B][H][W][C] bf16 -- the

@@ -26,12 +26,13 @@ using namespace sggan;
 struct Set {
   sg_bf16 *Y, *X, *R, *dX, *dY, *gat;
   float *part, *stats, *sums, *gamma, *beta, *bpart;
+  int* ctr;
 };
 
 int main(int argc, char** argv) {
   int B = 8, H = 64, W = 128, C = 256;
   if (argc >= 5) { B = atoi(argv[1]); H = atoi(argv[2]); W = atoi(argv[3]); C = atoi(argv[4]); }
-  const int NSETS = 4, ITERS = 24;
+  const int NSETS = argc >= 6 ? atoi(argv[5]) : 4, ITERS = 24;  // 1 set: the whole working set stays L2-resident
   const int P = W + 2, T = (H * P + 127) / 128 + 1;
   FrameMap xm;
   memset(&xm, 0, sizeof(xm));
@@ -49,6 +50,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&s.dX, ndX * 2)); CK(cudaMalloc(&s.dY, ndY * 2 + 4096)); CK(cudaMalloc(&s.gat, nY * 2));
     CK(cudaMalloc(&s.part, size_t(B) * T * C * 8)); CK(cudaMalloc(&s.stats, size_t(B) * C * 8));
     CK(cudaMalloc(&s.sums, size_t(B) * C * 8)); CK(cudaMalloc(&s.gamma, C * 4)); CK(cudaMalloc(&s.beta, C * 4));
+    CK(cudaMalloc(&s.ctr, 64 * sizeof(int)));
     CK(cudaMalloc(&s.bpart, in_bwd_partials_bytes(C))); CK(cudaMemset(s.bpart, 0, in_bwd_partials_bytes(C)));
     CK(cudaMemcpy(s.Y, h.data(), nY * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(s.R, h.data(), nX * 2, cudaMemcpyHostToDevice));
@@ -82,7 +84,12 @@ int main(int argc, char** argv) {
     p.g1.ptr = s.dX; p.g1.f32 = 0; p.g1.Hs = H + 2; p.g1.Ws = P; p.g1.oy = 1; p.g1.ox = 1; p.g1.fold = 1;
     if (gather) { p.g2 = p.g1; p.g2.ptr = s.R; p.gather_dst = s.gat; }
     p.sums = s.sums; p.sums_part = s.bpart; p.dst = s.dY; p.dmap = dym;
-    if (which == 0) launch_in_bwd_reduce(p, st);
+    if (which == 2) {
+      CK(cudaMemsetAsync(s.ctr, 0, 64 * sizeof(int), st));
+      p.sync_ctr = s.ctr;
+      const int r = launch_in_bwd_fused(p, st);
+      if (r < 0) { printf("fused launch failed %d\n", r); exit(3); }
+    } else if (which == 0) launch_in_bwd_reduce(p, st);
     else { p.gather_dst = nullptr; p.sums_nblk = 148 / B > 0 ? 148 / B : 1; launch_in_bwd_apply(p, st); }
   };
   struct Case { const char* name; int kind; double mb; };
@@ -90,7 +97,8 @@ int main(int argc, char** argv) {
   Case cases[] = {{"apply (stats given)", 0, 2 * mY},       {"apply + finalize", 1, 2 * mY},
                   {"apply + residual + finalize", 2, 3 * mY}, {"bwd reduce", 3, 2 * mY},
                   {"bwd reduce + gather", 4, 4 * mY},        {"bwd apply", 5, 3 * mY},
-                  {"bwd reduce -> apply (same set)", 6, 5 * mY}};
+                  {"bwd reduce -> apply (same set)", 6, 5 * mY}, {"bwd fused (reduce + apply)", 7, 3 * mY},
+                  {"bwd fused + gather", 8, 5 * mY}};
   printf("rows_probe B %d H %d W %d C %d  (tensor %.1f MB)  stages %d consumers %d\n", B, H, W, C, mY, kStages, kConsumers);
   for (auto& c : cases) {
     auto run = [&](Set& s) {
@@ -102,6 +110,8 @@ int main(int argc, char** argv) {
         case 4: bwd(s, 0, true); break;
         case 5: bwd(s, 1, false); break;
         case 6: bwd(s, 0, false); bwd(s, 1, false); break;
+        case 7: bwd(s, 2, false); break;
+        case 8: bwd(s, 2, true); break;
       }
     };
     for (int i = 0; i < NSETS; ++i) run(sets[i]);
@@ -118,7 +128,7 @@ int main(int argc, char** argv) {
     CK(cudaMemset(dbg, 0, 8 * 256 * 16 * 8));
     CK(cudaMemcpyToSymbol(g_rows_dbg, &dbg, sizeof(dbg)));
     g_rows_dbg_launch = 0;
-    for (int i = 0; i < 3; ++i) run(sets[i]);
+    for (int i = 0; i < 3; ++i) run(sets[i % NSETS]);
     CK(cudaStreamSynchronize(st));
     long long* nullp = nullptr;
     CK(cudaMemcpyToSymbol(g_rows_dbg, &nullp, sizeof(nullp)));
@@ -136,6 +146,17 @@ int main(int argc, char** argv) {
         e0[l] = std::min(e0[l], d[9]); e1[l] = std::max(e1[l], d[9]);
         if (l == 1) { for (int k = 1; k < 7; ++k) acc[k] += double(d[k] - d[0]); ++nblk; }
       }
+    }
+    // per block-x position (averaged over the images): lifetime after the dependency wait, in cycles
+    {
+      const int gx = nblk / B > 0 ? nblk / B : 1;
+      printf("    block x -> cycles from dep-wait to end (avg over images):");
+      for (int x = 0; x < gx; ++x) {
+        double a = 0;
+        for (int bb = 0; bb < B; ++bb) { const long long* d = &hd[(1 * 256 + bb * gx + x) * 16]; a += double(d[5] - d[1]); }
+        printf(" %.0f", a / B);
+      }
+      printf("\n");
     }
     printf("%-30s %7.2f us/launch  %6.0f GB/s (algorithmic %.0f MB) | blocks %d, avg cycles from block start: dep-wait %.0f "
            "coeffs %.0f first-chunk %.0f last-load-issued %.0f last-consumed %.0f end %.0f\n",

@@ -513,3 +513,23 @@ def test_master_weights_have_one_owner(L, O, tmp_path):
     assert rt2 is not rt and m.generator.runtime is rt2 and m.discriminator.runtime is rt2
     assert L.lib().sggan_step_count(rt2.engine.h) == steps == 2
     assert torch.equal(rt2.engine.flat(L.NET_G, 2), mG) and torch.equal(rt2.engine.flat(L.NET_G, 0), w2)
+
+
+def test_mask_pipeline_against_reference_shipped_files(L, O):
+    """The loader's mask construction on the GPU against what the REFERENCE's own files say: the LUT against the class
+    PNG segment_class.py wrote (datasets/gta), one_hot + cubic-spline zoom against scipy on full-resolution Cityscapes
+    label maps (datasets/city), both bit-exact (tests/golden/make_reference_fixtures.py)."""
+    U = importlib.import_module("sg-gan-tf2_b200.utils")
+    fix = np.load(os.path.join(ROOT, "tests", "golden", "reference_fixtures.npz"))
+    got = U.rgb_to_class(fix["gta_rgb"]).cpu().numpy()
+    assert np.array_equal(got, fix["gta_class"])
+    names = [str(n) for n in fix["city_names"]]
+    ids = np.stack([fix["city_ids_" + n] for n in names])
+    for (H, W) in ((256, 512), (512, 1024)):
+        ref = np.stack([fix["city_mask_%s_%dx%d" % (n, H, W)] for n in names])
+        m = U.seg_mask(ids, H, W, 34)
+        assert tuple(m.shape) == ref.shape and np.array_equal(m.cpu().numpy().astype(np.int64), ref.astype(np.int64)), (H, W)
+        one = U.seg_mask(ids[1], H, W, 34, flip=True)  # single image + the loader's fliplr (utils.py:201-204)
+        assert np.array_equal(one[0].cpu().numpy().astype(np.int64), ref[1][:, ::-1].astype(np.int64))
+    hot = U.one_hot(ids[0][:64, :64].astype(np.int64), 34).cpu().numpy()
+    assert np.array_equal(hot, O.one_hot(ids[0][:64, :64].astype(np.int64), 34))

@@ -173,3 +173,44 @@ def test_mask_construction_integer(O, golden):
     assert len(lut) == 21 and lut[(1, 2, 3)] == 0 and lut[(107, 142, 35)] == 7
     nm = O.nearest_mask(ids.astype(np.int64), 5, 13, 34)
     assert nm.shape == (5, 13, 34) and (nm.sum(-1) == 1).all()
+
+
+# ---------------------------------------------------------------------------------------------- reference-shipped fixtures
+@pytest.fixture(scope="module")
+def ref_fix():
+    return np.load(os.path.join(HERE, "golden", "reference_fixtures.npz"))
+
+
+def test_lut_against_the_class_png_the_reference_ships(O, ref_fix):
+    """datasets/gta/trainA_seg_class/00005.png was written by the reference's own segment_class.py (lines 87-97) from
+    datasets/gta/trainA_seg/00005.png: a golden vector OF THE REFERENCE for the RGB -> class-id LUT (every 4th pixel of
+    both files, tests/golden/make_reference_fixtures.py).  This pins the oracle's restatement, not just itself."""
+    rgb, cls = ref_fix["gta_rgb"], ref_fix["gta_class"]
+    got = O.rgb_to_class(rgb)
+    assert got.shape == cls.shape and np.array_equal(got.astype(np.uint8), cls)
+    assert set(np.unique(cls)) == {0, 1, 2, 4, 5, 6, 7}  # the classes this image exercises
+
+
+def test_mask_zoom_restatement_equals_scipy_on_shipped_label_maps(O, ref_fix):
+    """utils.py:190,197-199 on full-resolution Cityscapes label maps the reference ships: the oracle (which calls
+    scipy.ndimage.zoom exactly as the reference does) against the committed outputs, and the product's separable
+    restatement of the same spline (sg-gan-tf2_b200/utils.py zoom_weights) evaluated with numpy -- integer for integer."""
+    import importlib
+    U = importlib.import_module("sg-gan-tf2_b200.utils")
+    for name in ref_fix["city_names"]:
+        ids = ref_fix["city_ids_" + str(name)].astype(np.int64)
+        for (H, W) in ((256, 512), (512, 1024)):
+            ref = ref_fix["city_mask_%s_%dx%d" % (name, H, W)]
+            if str(name) == str(ref_fix["city_names"][0]) and (H, W) == (256, 512):
+                assert np.array_equal(O.build_mask(ids, H, W, 34), ref)  # scipy here == scipy when the fixture was made
+            Wy, Wx = U.zoom_weights(ids.shape[0], ref.shape[0]), U.zoom_weights(ids.shape[1], ref.shape[1])
+            hot = (ids[..., None] == np.arange(34)).astype(np.float64)
+            t = np.einsum("jx,ixc->ijc", Wx, np.einsum("iy,yxc->ixc", Wy, hot))
+            got = np.where(t > 0, t + 0.5, t - 0.5).astype(np.int64)
+            assert np.array_equal(got, ref), (name, H, W, int((got != ref).sum()))
+            wy, y0, wh = U._windows(Wy)
+            assert wh <= 96 and np.abs(Wy).sum(1).max() < 2.0  # the kernel's window carries the whole row of weights
+            for o in range(Wy.shape[0]):
+                full = np.zeros(Wy.shape[1])
+                full[y0[o]:y0[o] + wh] = wy[o]
+                assert np.abs(full - Wy[o]).max() < 1e-17
