@@ -94,6 +94,12 @@ int sggan_step_adam(sggan_handle* h, int net);
 int sggan_step_adam_async(sggan_handle* h, int net);
 int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask,
                      float* losses_out);
+/* The same step as ONE CUDA graph: capture once for a set of (stable) device pointers, then replay.  A replay is one
+ * cudaGraphLaunch on the handle's stream and does exactly what sggan_train_step does (Adam's time step is read from a
+ * device-side counter, so it advances from replay to replay).  Needs a non-default stream at sggan_create; run one
+ * eager sggan_train_step first (lazy kernel attributes). */
+int sggan_graph_capture(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask, float* losses_out);
+int sggan_graph_launch(sggan_handle* h);
 int64_t sggan_step_count(const sggan_handle* h);
 /* Resume support: set the number of completed steps (Adam's bias correction uses t = count + 1); the Adam slots
  * themselves are the flat buffers what = 2 / 3 of sggan_flat_buffer.  model.py:450-503 saves weights only; carrying
@@ -138,6 +144,20 @@ int sggan_conv2d_fwd(const float* x, const float* kernel, const float* bias, flo
 /* ops.deconv2d (ops.py:30-34) / Conv2DTranspose(3, strides 2, 'same'): kernel (kh,kw,Cout,Cin). */
 int sggan_deconv2d_fwd(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W,
                        int Cin, int Cout, void* workspace, size_t workspace_bytes, void* stream);
+/* The fp32-accurate tier of the same two operators (north_star: "rel 1e-4 tf32"): activations stay fp32, the operands
+ * are rounded to tf32 and multiplied by tcgen05.mma.kind::tf32 with fp32 accumulation; any Cin / Cout (padded
+ * internally).  The reference computes in fp32 (Keras defaults); bf16 storage (the training path) deviates by ~5e-3
+ * per layer, this tier by ~3e-4 (10-bit mantissa of tf32; tests/test_gpu_tf32.py). */
+size_t sggan_conv2d_tf32_workspace(int B, int H, int W, int Cin, int Cout, int k, int stride, int padding);
+int sggan_conv2d_fwd_tf32(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
+                          int Cout, int k, int stride, int padding, void* workspace, size_t workspace_bytes, void* stream);
+int sggan_deconv2d_fwd_tf32(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
+                            int Cout, void* workspace, size_t workspace_bytes, void* stream);
+/* InstanceNormalization (+ activation, + residual) on fp32 storage with double-precision statistics; any C.
+ * workspace: B * C * 16 bytes. */
+int sggan_instance_norm_fwd_f32(const float* x, const float* gamma, const float* beta, const float* residual, float* y, int B,
+                                int H, int W, int C, float eps, int act, float alpha, void* workspace, size_t workspace_bytes,
+                                void* stream);
 /* Gradients of the same two operators (what gen_tape / disc_tape.gradient compute, model.py:196-197), through the
  * step's own dgrad / wgrad tensor-core kernels: dy [B,Ho,Wo,Cout] -> dx (shape of x), dw (shape of kernel), db [Cout]
  * (db may be null).  sggan_conv2d_bwd_workspace(..., stride = -2, ...) sizes the transposed-convolution case. */
@@ -182,6 +202,15 @@ int sggan_zoom_mask(const uint8_t* ids, const double* wy, const int* y0, const d
                     float* mask, int B, int H, int W, int ho, int wo, int C, void* stream);
 /* RGB -> class id LUT (segment_class.py:60-70,95-97): rgb [n,3] uint8 -> ids [n] uint8 */
 int sggan_rgb_to_class(const uint8_t* rgb, uint8_t* ids, int64_t n, void* stream);
+
+/* ---- evaluation that follows the path each epoch (metric.py:18-47,71-77; model.py:307-378) ---- */
+/* scores_seg_fake's label adapter: labels[b, w, h] = argmax_c uint8(255 * img[b, h, w, c]) (first maximum; note the
+ * reference's (0,3,2,1) transpose).  img [B,H,W,3] fp32 -> labels [B,W,H] int32. */
+int sggan_rgb_argmax_labels(const float* img, int32_t* labels, int B, int H, int W, void* stream);
+/* _fast_hist: hist[t * n_class + p] += 1 over n label pairs with 0 <= t < n_class (hist: n_class^2 int64, accumulated
+ * into -- zero it first for a fresh matrix).  n_class <= 96. */
+int sggan_fast_hist(const int32_t* label_true, const int32_t* label_pred, int64_t n, int n_class, int64_t* hist,
+                    void* stream);
 
 #ifdef __cplusplus
 }

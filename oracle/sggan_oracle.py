@@ -535,3 +535,21 @@ def synthetic_batch(B, H, W, C, seed=19, dtype=torch.float32):
     hd, wd = disc_logit_grid(H, W)
     mask = np.stack([nearest_mask(ids[b], hd, wd, C) for b in range(B)]).astype(np.float32)
     return (torch.as_tensor(real_A).to(dtype), torch.as_tensor(seg_A).to(dtype), torch.as_tensor(mask).to(dtype), ids)
+
+
+# --------------------------------------------------------------------------------------------
+# evaluation scores -- integer work, bit-exact (metric.py:18-47,71-77)
+
+
+def fast_hist(label_true, label_pred, n_class):
+    """metric.py:18-24."""
+    label_true, label_pred = np.asarray(label_true).reshape(-1), np.asarray(label_pred).reshape(-1)
+    keep = (label_true >= 0) & (label_true < n_class)
+    return np.bincount(n_class * label_true[keep].astype(int) + label_pred[keep], minlength=n_class ** 2).reshape(n_class, n_class)
+
+
+def seg_fake_labels(seg_image, fake_img):
+    """metric.py:71-77: argmax over the channels of the uint8-quantised images, in the (0,3,2,1) orientation."""
+    a = np.argmax((255 * np.asarray(seg_image)).astype(np.uint8).transpose(0, 3, 2, 1), axis=1)
+    b = np.argmax((255 * np.asarray(fake_img)).astype(np.uint8).transpose(0, 3, 2, 1), axis=1)
+    return a, b

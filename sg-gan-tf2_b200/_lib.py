@@ -58,6 +58,8 @@ SYMBOLS = {
     "sggan_step_adam": (_I, [_P, _I]),
     "sggan_step_adam_async": (_I, [_P, _I]),
     "sggan_train_step": (_I, [_P, _P, _P, _P, _P]),
+    "sggan_graph_capture": (_I, [_P, _P, _P, _P, _P]),
+    "sggan_graph_launch": (_I, [_P]),
     "sggan_step_count": (_I64, [_P]),
     "sggan_set_step_count": (_I, [_P, _I64]),
     "sggan_set_stream": (_I, [_P, _P]),
@@ -72,6 +74,10 @@ SYMBOLS = {
     "sggan_conv2d_workspace": (_SZ, [_I] * 8),
     "sggan_conv2d_fwd": (_I, [_P, _P, _P, _P] + [_I] * 8 + [_P, _SZ, _P]),
     "sggan_deconv2d_fwd": (_I, [_P, _P, _P, _P] + [_I] * 5 + [_P, _SZ, _P]),
+    "sggan_conv2d_tf32_workspace": (_SZ, [_I] * 8),
+    "sggan_conv2d_fwd_tf32": (_I, [_P, _P, _P, _P] + [_I] * 8 + [_P, _SZ, _P]),
+    "sggan_deconv2d_fwd_tf32": (_I, [_P, _P, _P, _P] + [_I] * 5 + [_P, _SZ, _P]),
+    "sggan_instance_norm_fwd_f32": (_I, [_P] * 5 + [_I] * 4 + [_F, _I, _F, _P, _SZ, _P]),
     "sggan_conv2d_bwd_workspace": (_SZ, [_I] * 8),
     "sggan_conv2d_bwd": (_I, [_P] * 6 + [_I] * 8 + [_P, _SZ, _P]),
     "sggan_deconv2d_bwd": (_I, [_P] * 6 + [_I] * 5 + [_P, _SZ, _P]),
@@ -85,6 +91,8 @@ SYMBOLS = {
     "sggan_adam_step": (_I, [_P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _P]),
     "sggan_onehot_mask": (_I, [_P, _P] + [_I] * 6 + [_P]),
     "sggan_rgb_to_class": (_I, [_P, _P, _I64, _P]),
+    "sggan_rgb_argmax_labels": (_I, [_P, _P, _I, _I, _I, _P]),
+    "sggan_fast_hist": (_I, [_P, _P, _I64, _I, _P, _P]),
     "sggan_zoom_mask": (_I, [_P, _P, _P, _P, _P, _I, _I, _P] + [_I] * 6 + [_P]),
 }
 
@@ -153,8 +161,26 @@ def workspace_bytes(cfg):
     return n
 
 
+class _EngineStream:
+    """Every engine call runs on the engine's own (non-default, graph-capturable) stream, ordered after whatever the
+    caller enqueued on its current stream and before whatever it enqueues next -- whichever stream is current at call
+    time, so `with torch.cuda.stream(...)` around a call, NCCL work handles and DLPack producers all stay correct."""
+
+    def __init__(self, eng):
+        self.eng = eng
+
+    def __enter__(self):
+        self.cur = torch.cuda.current_stream(self.eng.device)
+        self.eng.stream.wait_stream(self.cur)
+        return self.eng.stream
+
+    def __exit__(self, *exc):
+        self.cur.wait_stream(self.eng.stream)
+        return False
+
+
 class Engine:
-    """One SG-GAN step engine bound to the current CUDA device and stream."""
+    """One SG-GAN step engine bound to a CUDA device (launches on its own stream, see _EngineStream)."""
 
     def __init__(self, cfg: Config, device=None):
         if not torch.cuda.is_available():
@@ -163,11 +189,16 @@ class Engine:
         self.device = torch.device(device or ("cuda:%d" % torch.cuda.current_device()))
         nbytes = workspace_bytes(cfg)
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.stream = torch.cuda.Stream(self.device)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
-            check(lib().sggan_create(C.byref(cfg), C.c_void_p(self.workspace.data_ptr()), nbytes, stream_ptr(),
-                                     C.byref(h)))
+            with _EngineStream(self):  # the workspace is zero-filled on the engine's stream
+                check(lib().sggan_create(C.byref(cfg), C.c_void_p(self.workspace.data_ptr()), nbytes,
+                                         C.c_void_p(self.stream.cuda_stream), C.byref(h)))
         self.h = h
+        self._graph_key = None      # device pointers the captured step graph is valid for
+        self._eager_steps = 0
+        self.use_graph = os.environ.get("SGGAN_GRAPH", "1") != "0"
         self._flat = {}
         self.losses = torch.zeros(2, dtype=torch.float32, device=self.device)
         Ho = max(disc_logit_grid(cfg.image_height, cfg.image_width)[0], cfg.mask_height)
@@ -220,42 +251,69 @@ class Engine:
             dst.copy_(w.to(self.device, torch.float32))
 
     def weights_changed(self):
-        check(lib().sggan_weights_changed(self.h))
+        with _EngineStream(self):
+            check(lib().sggan_weights_changed(self.h))
 
     # ---- forward / step ------------------------------------------------------------------------
     def gen_forward(self, real_A):
         x = as_cuda_f32(real_A, self.device)
         out = torch.empty_like(x)
-        check(lib().sggan_gen_forward(self.h, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr())))
+        with _EngineStream(self):
+            check(lib().sggan_gen_forward(self.h, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr())))
         return out
 
     def disc_forward(self, x, mask):
         x, mask = as_cuda_f32(x, self.device), as_cuda_f32(mask, self.device)
         out = torch.empty((x.shape[0],) + self.out_grid + (1,), dtype=torch.float32, device=self.device)
-        check(lib().sggan_disc_forward(self.h, C.c_void_p(x.data_ptr()), C.c_void_p(mask.data_ptr()),
-                                       C.c_void_p(out.data_ptr())))
+        with _EngineStream(self):
+            check(lib().sggan_disc_forward(self.h, C.c_void_p(x.data_ptr()), C.c_void_p(mask.data_ptr()),
+                                           C.c_void_p(out.data_ptr())))
         return out
 
     def step_forward_backward_d(self, real_A, seg_A, mask):
         self._keep = (as_cuda_f32(real_A, self.device), as_cuda_f32(seg_A, self.device), as_cuda_f32(mask, self.device))
         a, s, m = self._keep
-        check(lib().sggan_step_forward_backward_d(self.h, C.c_void_p(a.data_ptr()), C.c_void_p(s.data_ptr()),
-                                                  C.c_void_p(m.data_ptr()), C.c_void_p(self.losses.data_ptr())))
+        with _EngineStream(self):
+            check(lib().sggan_step_forward_backward_d(self.h, C.c_void_p(a.data_ptr()), C.c_void_p(s.data_ptr()),
+                                                      C.c_void_p(m.data_ptr()), C.c_void_p(self.losses.data_ptr())))
 
     def step_backward_g(self):
-        check(lib().sggan_step_backward_g(self.h))
+        with _EngineStream(self):
+            check(lib().sggan_step_backward_g(self.h))
 
     def step_adam(self, net, overlapped=False):
         """Adam + weight re-pack of one net; overlapped=True issues it on the engine's side stream (joined by the next
         engine call), so that it runs underneath whatever is enqueued next."""
-        check((lib().sggan_step_adam_async if overlapped else lib().sggan_step_adam)(self.h, net))
+        with _EngineStream(self):
+            check((lib().sggan_step_adam_async if overlapped else lib().sggan_step_adam)(self.h, net))
+
+    def allreduce_grads(self, net, nccl_comm, stream=None):
+        """In-place NCCL sum of this rank's flat gradient buffer(s) through the C ABI (sggan_allreduce_grads)."""
+        with _EngineStream(self):
+            check(lib().sggan_allreduce_grads(self.h, net, C.c_void_p(nccl_comm),
+                                              C.c_void_p(stream if stream is not None else self.stream.cuda_stream)))
 
     def train_step(self, real_A, seg_A, mask):
-        """One full G+D step; returns the device tensor [gen_loss, disc_loss] (no host sync)."""
+        """One full G+D step; returns the device tensor [gen_loss, disc_loss] (no host sync).  From the second call
+        with the same device buffers on, the step is ONE CUDA-graph launch (SGGAN_GRAPH=0 keeps the 250 eager launches)."""
         self._keep = (as_cuda_f32(real_A, self.device), as_cuda_f32(seg_A, self.device), as_cuda_f32(mask, self.device))
         a, s, m = self._keep
-        check(lib().sggan_train_step(self.h, C.c_void_p(a.data_ptr()), C.c_void_p(s.data_ptr()),
-                                     C.c_void_p(m.data_ptr()), C.c_void_p(self.losses.data_ptr())))
+        key = (a.data_ptr(), s.data_ptr(), m.data_ptr())
+        with _EngineStream(self):
+            if self.use_graph and self._eager_steps >= 1 and not getattr(self, "_profiling", False):
+                if self._graph_key != key and key == getattr(self, "_last_key", None):  # same buffers twice in a row
+                    rc = lib().sggan_graph_capture(self.h, C.c_void_p(key[0]), C.c_void_p(key[1]), C.c_void_p(key[2]),
+                                                   C.c_void_p(self.losses.data_ptr()))
+                    self._graph_key = key if rc == 0 else None
+                    if rc != 0:
+                        self.use_graph = False  # capture refused (still the same kernels, launched one by one)
+                if self._graph_key == key:
+                    check(lib().sggan_graph_launch(self.h))
+                    return self.losses
+            self._last_key = key
+            check(lib().sggan_train_step(self.h, C.c_void_p(a.data_ptr()), C.c_void_p(s.data_ptr()),
+                                         C.c_void_p(m.data_ptr()), C.c_void_p(self.losses.data_ptr())))
+            self._eager_steps += 1
         return self.losses
 
     def last_fake(self):
@@ -270,11 +328,13 @@ class Engine:
         (work = algorithmic bytes)."""
         check(lib().sggan_profile_select(self.h, kind))
         check(lib().sggan_profile_begin(self.h, max_launches))
+        self._profiling = True  # the events are recorded by eager launches: no graph replay while profiling
 
     def profile_end(self):
         """-> (total ms, launches, algorithmic flops per launch) of the residual-block conv kernel."""
         ms, n, fl = C.c_double(), C.c_int(), C.c_double()
         check(lib().sggan_profile_end(self.h, C.byref(ms), C.byref(n), C.byref(fl)))
+        self._profiling = False
         return ms.value, n.value, fl.value
 
     @property

@@ -80,6 +80,8 @@ void sggan_destroy(sggan_handle* h) {
   if (e.ev_fork) cudaEventDestroy(e.ev_fork);
   if (e.ev_join) cudaEventDestroy(e.ev_join);
   if (e.ev_comm) cudaEventDestroy(e.ev_comm);
+  if (e.gexec) cudaGraphExecDestroy(e.gexec);
+  if (e.graph) cudaGraphDestroy(e.graph);
   for (auto ev : e.prof_ev) cudaEventDestroy(ev);
   delete h;
 }
@@ -118,6 +120,7 @@ int sggan_weights_changed(sggan_handle* h) {
   } while (0)
 
 int sggan_gen_forward(sggan_handle* h, const float* real_A, float* fake_A) {
+  h->e.nlaunch = 0;
   FWD_ERR(h->e.gen_forward(real_A, fake_A));
   return 0;
 }
@@ -137,7 +140,12 @@ int sggan_step_backward_g(sggan_handle* h) {
 // both optimizers of a step use the same Adam time step; the counter advances when the second one has run
 static void adam_mark(Engine& e, int net) {
   e.adam_mask |= 1 << (net == SGGAN_NET_G ? 0 : 1);
-  if (e.adam_mask == 3) { e.step += 1; e.adam_mask = 0; }
+  if (e.adam_mask == 3) {
+    e.join_side();  // an asynchronous update still reads the counter
+    launch_bump_step(e.step_dev, e.st);
+    e.step += 1;
+    e.adam_mask = 0;
+  }
 }
 int sggan_step_adam(sggan_handle* h, int net) {
   FWD_ERR(h->e.step_adam(net));
@@ -157,7 +165,53 @@ int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, c
   FWD_ERR(h->e.step_adam(SGGAN_NET_D, true));
   FWD_ERR(h->e.step_bwd_g());
   FWD_ERR(h->e.step_adam(SGGAN_NET_G));
+  launch_bump_step(h->e.step_dev, h->e.st);  // both updates are ordered before it (the side stream joined in step_bwd_g)
   h->e.step += 1;
+  return 0;
+}
+
+// ---- the whole step as ONE CUDA graph ---------------------------------------------------------------------------
+// 250+ launches, two streams and their events are captured once; a replay is a single cudaGraphLaunch, which takes the
+// launch overhead of the step (~0.6 ms of host time, exposed whenever the host waits for the previous step's losses,
+// as the reference's train loop does, model.py:260) off the critical path.  The pointers are part of the graph.
+int sggan_graph_capture(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask, float* losses_out) {
+  Engine& e = h->e;
+  if (!e.weights_ready) { g_err = "weights not set"; return SGGAN_E_STATE; }
+  if (e.gexec) { cudaGraphExecDestroy(e.gexec); e.gexec = nullptr; }
+  if (e.graph) { cudaGraphDestroy(e.graph); e.graph = nullptr; }
+  e.join_side();
+  if (cudaStreamBeginCapture(e.st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    g_err = "cudaStreamBeginCapture failed (is the handle's stream the legacy default stream?)";
+    cudaGetLastError();
+    return SGGAN_E_CUDA;
+  }
+  const int64_t step0 = e.step;
+  int r = sggan_train_step(h, real_A, seg_A, mask, losses_out);
+  e.step = step0;  // nothing ran: the capture only recorded the launches
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(e.st, &g);
+  if (r != 0 || ce != cudaSuccess || g == nullptr) {
+    if (g) cudaGraphDestroy(g);
+    if (r == 0) g_err = std::string("stream capture failed: ") + cudaGetErrorString(ce);
+    cudaGetLastError();
+    return r != 0 ? r : SGGAN_E_CUDA;
+  }
+  if (cudaGraphInstantiate(&e.gexec, g, 0) != cudaSuccess) {
+    g_err = "cudaGraphInstantiate failed";
+    cudaGraphDestroy(g);
+    e.gexec = nullptr;
+    cudaGetLastError();
+    return SGGAN_E_CUDA;
+  }
+  e.graph = g;
+  e.gptr[0] = real_A; e.gptr[1] = seg_A; e.gptr[2] = mask; e.gptr[3] = losses_out;
+  return 0;
+}
+int sggan_graph_launch(sggan_handle* h) {
+  Engine& e = h->e;
+  if (!e.gexec) { g_err = "no captured step (call sggan_graph_capture)"; return SGGAN_E_STATE; }
+  if (cudaGraphLaunch(e.gexec, e.st) != cudaSuccess) { g_err = "cudaGraphLaunch failed"; return SGGAN_E_CUDA; }
+  e.step += 1;
   return 0;
 }
 int64_t sggan_step_count(const sggan_handle* h) { return h->e.step; }
@@ -165,6 +219,9 @@ int sggan_set_step_count(sggan_handle* h, int64_t completed_steps) {
   if (completed_steps < 0) { g_err = "negative step count"; return SGGAN_E_INVALID; }
   h->e.step = completed_steps;
   h->e.adam_mask = 0;
+  const long long v = completed_steps;
+  if (cudaMemcpyAsync(h->e.step_dev, &v, sizeof(v), cudaMemcpyHostToDevice, h->e.st) != cudaSuccess ||
+      cudaStreamSynchronize(h->e.st) != cudaSuccess) { g_err = "step counter upload failed"; return SGGAN_E_CUDA; }
   return 0;
 }
 int sggan_set_stream(sggan_handle* h, void* stream) {
@@ -350,6 +407,95 @@ int sggan_deconv2d_fwd(const float* x, const float* kernel, const float* bias, f
   Layer l;
   if (conv_layer_for_op(l, B, H, W, Cin, Cout, 3, 2, 1, true)) { g_err = "unsupported deconv2d shape"; return SGGAN_E_INVALID; }
   return conv_op_run(l, x, kernel, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- the fp32-accurate tier: the same implicit-GEMM kernel with tcgen05.mma.kind::tf32 on fp32 frames ----------------
+static int pad_channels_tf32(int c) {
+  if (c <= 32) return 32;
+  if (c <= 64) return 64;
+  if (c <= 128) return 128;
+  return (c + 255) / 256 * 256;
+}
+static int conv_layer_for_op_tf32(Layer& l, int B, int H, int W, int Cin, int Cout, int k, int stride, int padding, bool deconv) {
+  memset(&l.xmap, 0, sizeof(l.xmap));
+  if (Cin < 1 || Cout < 1) return SGGAN_E_INVALID;
+  l.k = k; l.Cin = (Cin + 31) / 32 * 32; l.Cout = Cout; l.Hin = H; l.Win = W; l.has_norm = false; l.act = SG_ACT_NONE; l.alpha = 0.f;
+  l.nb = l.nbv = B;
+  if (deconv) { l.type = LT_DECONV; l.pad = PAD_ZERO; }
+  else if (stride == 1) {
+    l.type = LT_S1;
+    l.pad = padding == 0 ? PAD_VALID : (padding == 1 ? PAD_ZERO : PAD_REFLECT);
+    if (!(k & 1) || k * k > SGGAN_MAX_TAPS) return SGGAN_E_INVALID;
+  } else if (stride == 2 && k == 3 && padding != 2) {
+    l.type = LT_S2;
+    l.pad = padding == 0 ? PAD_VALID : PAD_ZERO;
+  } else return SGGAN_E_INVALID;
+  int r = layer_geometry(l);
+  if (r) return r;
+  l.CoutN = pad_channels_tf32(Cout);
+  l.packf.N = l.CoutN; l.packf.K = l.Cin; l.packf.Cin = Cin; l.packf.Cout = Cout;
+  return 0;
+}
+static size_t conv_op_bytes_tf32(const Layer& l, int64_t* offW, int64_t* offX) {
+  size_t off = 0;
+  *offW = off; off = align256(off + size_t(l.packf.T) * l.packf.N * l.packf.K * 4);
+  *offX = off; off = align256(off + size_t(l.nb) * l.xmap.frame_pix * l.xmap.C * 4 + 4096);
+  return off;
+}
+size_t sggan_conv2d_tf32_workspace(int B, int H, int W, int Cin, int Cout, int k, int stride, int padding) {
+  Layer l;
+  if (conv_layer_for_op_tf32(l, B, H, W, Cin, Cout, k, stride, padding, stride == -2)) return 0;
+  int64_t a, b;
+  return conv_op_bytes_tf32(l, &a, &b);
+}
+static int conv_op_run_tf32(Layer& l, int Cin, const float* x, const float* kernel, const float* bias, float* y, void* ws,
+                            size_t ws_bytes, cudaStream_t st) {
+  int64_t oW, oX;
+  const size_t need = conv_op_bytes_tf32(l, &oW, &oX);
+  if (!ws || ws_bytes < need) { g_err = "operator workspace too small"; return SGGAN_E_WORKSPACE; }
+  uint8_t* base = (uint8_t*)ws;
+  float* Wf = (float*)(base + oW);
+  float* X = (float*)(base + oX);
+  if (cudaMemsetAsync(X, 0, size_t(l.nb) * l.xmap.frame_pix * l.xmap.C * 4 + 4096, st) != cudaSuccess) return SGGAN_E_CUDA;
+  PackParams pf = l.packf;
+  pf.src = kernel; pf.dst = nullptr;
+  launch_pack_weights_f32(pf, Wf, st);
+  launch_f32_to_frame_f32(x, l.nb, l.Hin, l.Win, Cin, X, l.xmap, st);
+  FrameMap om;
+  memset(&om, 0, sizeof(om));
+  om.frame_pix = int64_t(l.Hout) * l.Wout; om.C = l.Cout; om.H = l.Hout; om.W = l.Wout; om.P = l.Wout;
+  l.Wf = (sg_bf16*)Wf;  // addresses only: the launch parameters below are re-typed by the tf32 flag
+  l.X = (sg_bf16*)X;
+  int r = layer_prepare_fwd(l, bias, y, om, 1, true);  // dry: parameters only
+  if (r) { g_err = "conv prepare failed " + std::to_string(r); return SGGAN_E_CUDA; }
+  for (auto& L : l.fwd) {
+    ConvGemmParams q = L.p;
+    q.tf32 = 1;
+    q.stats = nullptr;
+    ConvGemmLaunch T;
+    if ((r = prepare_conv_gemm(q, &T))) { g_err = "tf32 conv prepare failed " + std::to_string(r); return SGGAN_E_CUDA; }
+    if ((r = run_conv_gemm(T, st))) { g_err = "tf32 conv launch failed " + std::to_string(r); return SGGAN_E_CUDA; }
+  }
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+int sggan_conv2d_fwd_tf32(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
+                          int Cout, int k, int stride, int padding, void* workspace, size_t workspace_bytes, void* stream) {
+  Layer l;
+  if (conv_layer_for_op_tf32(l, B, H, W, Cin, Cout, k, stride, padding, false)) { g_err = "unsupported conv2d shape"; return SGGAN_E_INVALID; }
+  return conv_op_run_tf32(l, Cin, x, kernel, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int sggan_deconv2d_fwd_tf32(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
+                            int Cout, void* workspace, size_t workspace_bytes, void* stream) {
+  Layer l;
+  if (conv_layer_for_op_tf32(l, B, H, W, Cin, Cout, 3, 2, 1, true)) { g_err = "unsupported deconv2d shape"; return SGGAN_E_INVALID; }
+  return conv_op_run_tf32(l, Cin, x, kernel, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+int sggan_instance_norm_fwd_f32(const float* x, const float* gamma, const float* beta, const float* residual, float* y, int B,
+                                int H, int W, int C, float eps, int act, float alpha, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  if (!workspace || workspace_bytes < size_t(B) * C * 2 * sizeof(double)) { g_err = "operator workspace too small"; return SGGAN_E_WORKSPACE; }
+  launch_instance_norm_f32(x, gamma, beta, residual, y, B, H * W, C, eps, act, alpha, (double*)workspace, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
 
 // ---- backward of one convolution / transposed convolution through the step's own dgrad + wgrad kernels -------------

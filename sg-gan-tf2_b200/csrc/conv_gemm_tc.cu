@@ -131,7 +131,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smB = smem + sa_stages * a_stage_bytes;
   const int mstep = p.shift_kw > 0 ? MT - (p.shift_kw - 1) : MT;
   const int m0 = blockIdx.x * mstep, n0 = blockIdx.y * BN, b = blockIdx.z;
-  const int cchunks = p.Cin / kChunkK;
+  const int ck = p.tf32 ? kChunkK / 2 : kChunkK;  // elements per 128-byte swizzled row: 64 bf16 or 32 fp32 (tf32)
+  const int cchunks = p.Cin / ck;
   const int agroups = p.nruns * cchunks;  // A tiles this CTA consumes
   // staged epilogue (see below): bf16 output and a full tile of channels
   const bool staged = p.shift_kw == 0 && !p.out_f32 && (p.omap.C & 7) == 0 && n0 + BN <= p.Cout;
@@ -167,8 +168,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint8_t* sa = smA + s * a_stage_bytes;
         const int row0 = m0 + p.run_off[r];
         mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
-        for (int a = 0; a < NA; ++a) tma_load_3d(&tmA, &a_full[s], sa + a * kABytes, cc * kChunkK, row0 + a * kTileM, b);
-        tma_load_3d(&tmA8, &a_full[s], sa + NA * kABytes, cc * kChunkK, row0 + MT, b);
+        for (int a = 0; a < NA; ++a) tma_load_3d(&tmA, &a_full[s], sa + a * kABytes, cc * ck, row0 + a * kTileM, b);
+        tma_load_3d(&tmA8, &a_full[s], sa + NA * kABytes, cc * ck, row0 + MT, b);
       }
     }
   } else if (warp == 2) {
@@ -182,13 +183,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t ph = (it / sb_stages) & 1;
             mbar_wait(&b_empty[s], ph ^ 1, 4);
             mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
-            tma_load_2d(&tmB, &b_full[s], smB + s * b_stage_bytes, cc * kChunkK, int(p.run_w[t0 + q]) * p.CoutPad + n0);
+            tma_load_2d(&tmB, &b_full[s], smB + s * b_stage_bytes, cc * ck, int(p.run_w[t0 + q]) * p.CoutPad + n0);
           }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = idesc_bf16_f32(kTileM, BN, 0, 0);
+      const bool tf32 = p.tf32 != 0;
+      const uint32_t idesc = tf32 ? idesc_tf32_f32(kTileM, BN) : idesc_bf16_f32(kTileM, BN, 0, 0);
       int it = 0, g = 0;
       for (int r = 0; r < p.nruns; ++r)
         for (int cc = 0; cc < cchunks; ++cc, ++g) {
@@ -204,10 +206,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int a = 0; a < NA; ++a) {
               // tap q of the run: the A view starts q rows (q * 128 B) into the tile
               const uint64_t adesc = desc_kmajor_sw128(a_base + uint32_t(a * kTileM + q) * 128u);
+              if (tf32) {
 #pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
-                umma_bf16(tmem_acc + uint32_t(a * BN), adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc,
-                          (it | k) != 0);
+                for (int k = 0; k < 4; ++k)  // UMMA_K = 8 tf32 = 32 bytes inside the swizzle row
+                  umma_tf32(tmem_acc + uint32_t(a * BN), adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, (it | k) != 0);
+              } else {
+#pragma unroll
+                for (int k = 0; k < kChunkK / 16; ++k)  // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
+                  umma_bf16(tmem_acc + uint32_t(a * BN), adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc,
+                            (it | k) != 0);
+              }
             }
             umma_commit(&b_empty[sb_i]);  // frees the weight slot once these MMAs retire
           }
@@ -1131,7 +1139,9 @@ static void build_runs(ConvGemmParams& p) {
 
 int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
   ConvGemmParams p = pin;
-  if (p.Cin % 64 != 0 || p.Cin <= 0) return -10;
+  const int esz = p.tf32 ? 4 : 2, ck = p.tf32 ? 32 : 64;  // element size, elements per 128-byte row
+  if (p.Cin % ck != 0 || p.Cin <= 0) return -10;
+  if (p.tf32 && (!p.out_f32 || p.shift_kw > 0)) return -15;
   if (!(p.BN == 32 || p.BN == 64 || p.BN == 128 || p.BN == 256)) return -11;
   if (p.CoutPad % p.BN != 0 || p.ntaps < 1 || p.ntaps > SGGAN_MAX_TAPS) return -12;
   build_runs(p);
@@ -1173,7 +1183,7 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
     // against ~168 in the single-CTA kernel, so both end within 2 % of each other (kernels)
     const char* env = getenv("SGGAN_CONV_PAIR");
     const bool allow = env && env[0] == '1';
-    if (allow && p.BN == 256 && p.CoutPad == 256 && p.shift_kw == 0 && int64_t(T128) * p.B >= 148) {
+    if (allow && !p.tf32 && p.BN == 256 && p.CoutPad == 256 && p.shift_kw == 0 && int64_t(T128) * p.B >= 148) {
       L->pair = 1;
       L->T128 = T128;
       L->npairs = (T128 * p.B + 1) / 2;
@@ -1193,7 +1203,7 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
     const bool shift_ok = p.shift_kw > 0 && p.BN == 32 && p.shift_kw * 4 <= 32 && p.Cout <= 4 && p.stats == nullptr;
     const int tstep = p.shift_kw > 0 ? 256 - (p.shift_kw - 1) : 256;
     const int T = (p.M + tstep - 1) / tstep;
-    if (allow && !L->pair && (plain_ok || shift_ok) && p.wt_taps * p.CoutPad >= 128 &&
+    if (allow && !p.tf32 && !L->pair && (plain_ok || shift_ok) && p.wt_taps * p.CoutPad >= 128 &&
         int64_t(T) * p.B * ((p.Cout + 127) / 128) >= 32) {
       L->swap = 1;
       L->T256 = T;
@@ -1216,12 +1226,12 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
       L->swap_smem = size_t(ps) * kSwapPStage + size_t(ws) * kSwapWStage + epi + 1024;
     }
   }
-  const uint64_t rs = uint64_t(p.a_row_stride) * 2, fs = uint64_t(p.a_frame_pix) * p.a_row_stride * 2;
-  int r = make_tmap_bf16_3d(&L->tmA, p.A, p.Cin, p.a_frame_pix, p.B, rs, fs, 64, 128);
+  const uint64_t rs = uint64_t(p.a_row_stride) * esz, fs = uint64_t(p.a_frame_pix) * p.a_row_stride * esz;
+  int r = make_tmap_3d(&L->tmA, p.A, p.Cin, p.a_frame_pix, p.B, rs, fs, ck, 128, p.tf32);
   if (r) return -1000 - r;
-  r = make_tmap_bf16_3d(&L->tmA8, p.A, p.Cin, p.a_frame_pix, p.B, rs, fs, 64, kHaloRows);
+  r = make_tmap_3d(&L->tmA8, p.A, p.Cin, p.a_frame_pix, p.B, rs, fs, ck, kHaloRows, p.tf32);
   if (r) return -1500 - r;
-  r = make_tmap_bf16_2d(&L->tmB, p.Wt, p.Cin, uint64_t(p.wt_taps) * p.CoutPad, uint64_t(p.Cin) * 2, 64, p.BN);
+  r = make_tmap_2d(&L->tmB, p.Wt, p.Cin, uint64_t(p.wt_taps) * p.CoutPad, uint64_t(p.Cin) * esz, ck, p.BN, p.tf32);
   if (r) return -2000 - r;
   if (L->pair || L->swap) {
     r = make_tmap_bf16_2d(&L->tmBh, p.Wt, p.Cin, uint64_t(p.wt_taps) * p.CoutPad, uint64_t(p.Cin) * 2, 64, 128);

@@ -593,6 +593,7 @@ int Engine::build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t
   for (int i = 0; i < 2; ++i) resG[i] = (sg_bf16*)a.take(size_t(B) * rb.Hin * rb.Win * rb.Cin * 2);
   wg_part_elems = size_t(160) * 256 * 256;  // one (2 x 128) x 256 fp32 tile per CTA of a single-wave split-K launch
   wg_part = (float*)a.take(wg_part_elems * 4);
+  step_dev = (long long*)a.take(sizeof(long long));
   in_part = (float*)a.take(in_bwd_partials_bytes(512));  // per-block partial sums of the norm-backward reduce pass
   for (int i = 0; i < 2; ++i) {
     pack_jobs[i] = (PackParams*)a.take(kMaxPackJobs * sizeof(PackParams));
@@ -950,11 +951,9 @@ int Engine::step_adam(int net, bool on_side_stream) {
     s = st2;
     side_used = true;
   }
-  const int64_t t = step + 1;
-  const float alpha_t = float(double(cfg.lr) * sqrt(1.0 - pow(double(cfg.beta2), double(t))) /
-                              (1.0 - pow(double(cfg.beta1), double(t))));
-  launch_adam(n.p, n.g, n.m, n.v, n.nparams, alpha_t, cfg.beta1, cfg.beta2, cfg.adam_eps,
-              1.f / float(cfg.world_size > 0 ? cfg.world_size : 1), s);
+  // Keras Adam; the time step comes from the device-side counter (workspace is zero-initialised: step 0)
+  launch_adam(n.p, n.g, n.m, n.v, n.nparams, 0.f, cfg.beta1, cfg.beta2, cfg.adam_eps,
+              1.f / float(cfg.world_size > 0 ? cfg.world_size : 1), s, step_dev, cfg.lr);
   ++nlaunch;
   return pack_weights(net, s);
 }

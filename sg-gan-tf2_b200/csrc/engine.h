@@ -97,6 +97,10 @@ struct Engine {
   size_t wg_part_elems;
   uint8_t *zero_begin, *zero_end;
   int64_t step;
+  long long* step_dev = nullptr;  // the same count on the device (Adam reads it: a captured graph must not bake t in)
+  cudaGraph_t graph = nullptr;    // captured sggan_train_step (sggan_graph_capture) and the pointers it was captured with
+  cudaGraphExec_t gexec = nullptr;
+  const void* gptr[4] = {nullptr, nullptr, nullptr, nullptr};
   int adam_mask = 0;  // which nets have been updated in the current step (bit 0 G, bit 1 D)
   int nlaunch;
   bool weights_ready;

@@ -179,6 +179,89 @@ void launch_lrelu(const float* x, float* y, int64_t n, float leak, cudaStream_t 
   lrelu_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(x, y, n, leak);
 }
 
+// ------------------------------------------------------------------------------------------ fp32 / tf32 tier
+// Helpers of the fp32-accurate operator tier (ops.conv2d / deconv2d / instance_norm with precision="tf32"): activations
+// stay fp32 in HBM, the convolution's operands are rounded to tf32 (cvt.rna: nearest, what cuDNN's TF32 mode feeds the
+// tensor cores) when the frame / the weight slabs are built, accumulation is fp32.  Parity-first, not tuned.
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__global__ void f32_to_frame_f32_kernel(const float* __restrict__ src, int B, int H, int W, int Cs, float* dst, FrameMap m) {
+  const int C4 = m.C >> 2;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= int64_t(B) * H * W * C4) return;
+  const int cg = int(idx % C4);
+  const int64_t pix = idx / C4;
+  const int b = int(pix / (int64_t(H) * W));
+  const int r = int(pix - int64_t(b) * H * W);
+  const int i = r / W, j = r - i * W;
+  float4 v;
+  float* vv = &v.x;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) vv[e] = (cg * 4 + e < Cs) ? round_tf32(src[pix * Cs + cg * 4 + e]) : 0.f;
+  float* base = dst + int64_t(b) * m.frame_pix * m.C + cg * 4;
+  if (m.kind == 0 && m.reflect > 0) {
+    int rr[3], cc[3];
+    const int nr = reflect_set(i, m.H, m.reflect, rr), nc = reflect_set(j, m.W, m.reflect, cc);
+    for (int a = 0; a < nr; ++a)
+      for (int q = 0; q < nc; ++q) *reinterpret_cast<float4*>(base + frame_pixel(m, rr[a], cc[q]) * m.C) = v;
+  } else {
+    *reinterpret_cast<float4*>(base + frame_pixel(m, i, j) * m.C) = v;
+  }
+}
+void launch_f32_to_frame_f32(const float* src, int B, int H, int W, int Cs, float* dst, const FrameMap& dmap, cudaStream_t st) {
+  const int64_t tot = int64_t(B) * H * W * (dmap.C / 4);
+  f32_to_frame_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(src, B, H, W, Cs, dst, dmap);
+}
+// instance-norm statistics of a plain fp32 [B][HW][C] tensor in double precision: stats[b][c] = (sum, sum of squares)
+__global__ void __launch_bounds__(256) in_stats_f32_kernel(const float* __restrict__ x, int HW, int C, double* stats, int ppb) {
+  __shared__ double sh[8][32][2];
+  const int b = blockIdx.y, c = blockIdx.x * 32 + threadIdx.x, ty = threadIdx.y;
+  const int pix0 = blockIdx.z * ppb, pix1 = min(HW, pix0 + ppb);
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C)
+    for (int pix = pix0 + ty; pix < pix1; pix += 8) {
+      const double v = x[(int64_t(b) * HW + pix) * C + c];
+      s1 += v;
+      s2 += v * v;
+    }
+  sh[ty][threadIdx.x][0] = s1;
+  sh[ty][threadIdx.x][1] = s2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    for (int q = 1; q < 8; ++q) { s1 += sh[q][threadIdx.x][0]; s2 += sh[q][threadIdx.x][1]; }
+    atomicAdd(stats + (int64_t(b) * C + c) * 2, s1);
+    atomicAdd(stats + (int64_t(b) * C + c) * 2 + 1, s2);
+  }
+}
+__global__ void in_apply_f32_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ res, float* y, int HW, int C,
+                                    int64_t n, float eps, int act, float alpha) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = int(i % C);
+  const int b = int(i / (int64_t(HW) * C));
+  const double mu = stats[(int64_t(b) * C + c) * 2] / HW;
+  const double var = fmax(stats[(int64_t(b) * C + c) * 2 + 1] / HW - mu * mu, 0.0);
+  const float inv = float(1.0 / sqrt(var + double(eps))) * (gamma ? gamma[c] : 1.f);
+  float z = (x[i] - float(mu)) * inv + (beta ? beta[c] : 0.f);
+  z = act_fwd(z, act, alpha);
+  if (res != nullptr) z += res[i];
+  y[i] = z;
+}
+void launch_instance_norm_f32(const float* x, const float* gamma, const float* beta, const float* res, float* y, int B, int HW,
+                              int C, float eps, int act, float alpha, double* stats, cudaStream_t st) {
+  cudaMemsetAsync(stats, 0, size_t(B) * C * 2 * sizeof(double), st);
+  int splits = (148 * 4) / (B * ((C + 31) / 32));
+  splits = splits < 1 ? 1 : (splits > 64 ? 64 : splits);
+  const int ppb = (HW + splits - 1) / splits;
+  in_stats_f32_kernel<<<dim3((C + 31) / 32, B, (HW + ppb - 1) / ppb), dim3(32, 8), 0, st>>>(x, HW, C, stats, ppb);
+  const int64_t n = int64_t(B) * HW * C;
+  in_apply_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(x, stats, gamma, beta, res, y, HW, C, n, eps, act, alpha);
+}
+
 // ------------------------------------------------------------------------------------------ IN fwd
 __global__ void __launch_bounds__(kGlueThreads) in_stats_kernel(const sg_bf16* __restrict__ y, int HW, int C,
                                                                 float* stats, int ppb) {
@@ -576,7 +659,19 @@ void launch_criterion(const float* a, const float* b, int64_t n, int mode, float
 // ------------------------------------------------------------------------------------------ Adam
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                   float alpha_t, float beta1, float beta2, float eps, float gscale) {
+                                                   float alpha_t, float beta1, float beta2, float eps, float gscale,
+                                                   const long long* __restrict__ step_dev, float lr) {
+  if (step_dev != nullptr) {
+    // the number of completed steps lives on the device so that a captured CUDA graph of the step stays valid from
+    // one replay to the next: alpha_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), t = completed + 1 (Keras, A.8)
+    __shared__ float s_alpha;
+    if (threadIdx.x == 0) {
+      const double t = double(*step_dev + 1);
+      s_alpha = float(double(lr) * sqrt(1.0 - pow(double(beta2), t)) / (1.0 - pow(double(beta1), t)));
+    }
+    __syncthreads();
+    alpha_t = s_alpha;
+  }
   const int64_t n4 = n >> 2;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i],
@@ -604,9 +699,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float alpha_t, float beta1, float beta2,
-                 float eps, float gscale, cudaStream_t st) {
-  adam_kernel<<<148 * 8, 256, 0, st>>>(p, g, m, v, n, alpha_t, beta1, beta2, eps, gscale);
+                 float eps, float gscale, cudaStream_t st, const long long* step_dev, float lr) {
+  adam_kernel<<<148 * 8, 256, 0, st>>>(p, g, m, v, n, alpha_t, beta1, beta2, eps, gscale, step_dev, lr);
 }
+__global__ void bump_step_kernel(long long* step_dev) { *step_dev += 1; }
+void launch_bump_step(long long* step_dev, cudaStream_t st) { bump_step_kernel<<<1, 1, 0, st>>>(step_dev); }
 
 // ------------------------------------------------------------------------------------------ packing
 // Source layouts (Keras): conv kernel [KH][KW][Cin][Cout]; transposed-conv kernel [KH][KW][Cout][Cin]
@@ -654,6 +751,19 @@ __device__ __forceinline__ void pack_one(const PackParams& p, int64_t idx8) {
   reinterpret_cast<uint4*>(p.dst)[idx8] = w;
 }
 __global__ void pack_weights_kernel(const PackParams p) { pack_one(p, int64_t(blockIdx.x) * blockDim.x + threadIdx.x); }
+// the same slabs as fp32 elements rounded to tf32 (dst is float [T][N][K])
+__global__ void pack_weights_f32_kernel(const PackParams p, float* dst) {
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t tot = int64_t(p.T) * p.N * p.K;
+  if (idx >= tot) return;
+  const int k = int(idx % p.K);
+  const int64_t tn = idx / p.K;
+  dst[idx] = round_tf32(pack_value(p, int(tn / p.N), int(tn % p.N), k));
+}
+void launch_pack_weights_f32(const PackParams& p, float* dst, cudaStream_t st) {
+  const int64_t tot = int64_t(p.T) * p.N * p.K;
+  pack_weights_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(p, dst);
+}
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackParams* __restrict__ jobs,
                                                                  const int* __restrict__ starts, int njobs) {
   __shared__ PackParams sp;

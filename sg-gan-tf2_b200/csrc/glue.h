@@ -89,8 +89,10 @@ void launch_gradloss(const float* in, const float* target, const float* weight, 
 void launch_criterion(const float* a, const float* b, int64_t n, int mode, float* out, cudaStream_t st);
 
 // Keras Adam (Appendix A.8) over a flat fp32 buffer; g is scaled by gscale first.
+// step_dev != null: alpha_t is computed on the device from *step_dev (completed steps) and lr instead of being passed in.
 void launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float alpha_t, float beta1, float beta2,
-                 float eps, float gscale, cudaStream_t st);
+                 float eps, float gscale, cudaStream_t st, const long long* step_dev = nullptr, float lr = 0.f);
+void launch_bump_step(long long* step_dev, cudaStream_t st);  // *step_dev += 1
 
 // fp32 Keras-layout weights -> bf16 GEMM slabs [T][N][K]; see glue.cu for the modes.
 struct PackParams {
@@ -111,6 +113,12 @@ void launch_in_param_grad(const float* sums, int nb, int C, float* dgamma, float
 // mask-multiply + channel sum as a standalone op (the K9 export): out[b,I,J] = sum_c x * mask
 void launch_mask_reduce(const float* x, const float* mask, int B, int Hd, int Wd, int hm, int wm, int Cs,
                         float* out, cudaStream_t st);
+// fp32 / tf32 operator tier (see glue.cu): fp32 frame with tf32-rounded values (Cs source channels, dmap.C >= Cs padded
+// with zeros), tf32-rounded fp32 weight slabs, instance norm on fp32 storage with double-precision statistics
+void launch_f32_to_frame_f32(const float* src, int B, int H, int W, int Cs, float* dst, const FrameMap& dmap, cudaStream_t st);
+void launch_pack_weights_f32(const PackParams& p, float* dst, cudaStream_t st);
+void launch_instance_norm_f32(const float* x, const float* gamma, const float* beta, const float* res, float* y, int B, int HW,
+                              int C, float eps, int act, float alpha, double* stats, cudaStream_t st);
 // elementwise helpers for ops.py
 void launch_lrelu(const float* x, float* y, int64_t n, float leak, cudaStream_t st);
 void launch_f32_to_frame(const float* src, int B, int H, int W, int C, sg_bf16* dst, const FrameMap& dmap,

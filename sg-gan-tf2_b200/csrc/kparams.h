@@ -94,6 +94,9 @@ struct ConvGemmParams {
   // 7x fewer tensor-core instructions than one tap per (kh, kw) at N = 32 (tcgen05.mma has a ~156-cycle
   // floor per instruction regardless of N).
   int shift_kw;
+  // tf32 mode (the fp32-accurate tier): A and Wt hold fp32 elements (pre-rounded to tf32), K per tap is a multiple of 32,
+  // the tensor cores run kind::tf32, the output is fp32.  conv_gemm_tc_kernel only.
+  int tf32;
   long long* dbg;  // optional per-CTA clock64 stamps [grid][8] (tests/gpu/tc_probe.cu); null in production
 };
 

@@ -164,6 +164,20 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N, int a_mn_maj
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
+// kind::tf32, fp32 operands read as tf32 (19 significant bits) -> fp32, dense, both operands K-major.
+__host__ __device__ constexpr uint32_t idesc_tf32_f32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {

@@ -62,6 +62,7 @@ class sggan(object):
         self.runtime = None
         self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._pinned = {}
+        self._dev = {}
         self._h2d_done = {}
 
     # ---- plan -----------------------------------------------------------------------------------------
@@ -99,7 +100,14 @@ class sggan(object):
         if isinstance(x, torch.Tensor) and x.is_cuda:
             return x.float().contiguous()
         if isinstance(x, torch.Tensor) and x.dtype == torch.float32 and x.is_contiguous() and x.is_pinned():
-            return x.to("cuda", non_blocking=True)  # already page-locked: one asynchronous H2D copy, no staging
+            # already page-locked: one asynchronous H2D copy into a persistent device buffer (stable pointers keep the
+            # captured step graph valid)
+            dev = self._dev.get(name)
+            if dev is None or dev.shape != x.shape:
+                dev = torch.empty(tuple(x.shape), dtype=torch.float32, device="cuda")
+                self._dev[name] = dev
+            dev.copy_(x, non_blocking=True)
+            return dev
         x = torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float32))) if not isinstance(x, torch.Tensor) \
             else x.float().contiguous()
         buf = self._pinned.get(name)
@@ -110,7 +118,11 @@ class sggan(object):
         if ev is not None:
             ev.synchronize()  # the previous step's asynchronous copy out of this staging buffer has finished
         buf.copy_(x)  # multi-threaded host copy into the page-locked staging buffer
-        dev = buf.to("cuda", non_blocking=True)
+        dev = self._dev.get(name)
+        if dev is None or dev.shape != buf.shape:
+            dev = torch.empty(tuple(buf.shape), dtype=torch.float32, device="cuda")
+            self._dev[name] = dev
+        dev.copy_(buf, non_blocking=True)
         ev = ev or torch.cuda.Event()
         ev.record()
         self._h2d_done[name] = ev

@@ -533,3 +533,55 @@ def test_mask_pipeline_against_reference_shipped_files(L, O):
         assert np.array_equal(one[0].cpu().numpy().astype(np.int64), ref[1][:, ::-1].astype(np.int64))
     hot = U.one_hot(ids[0][:64, :64].astype(np.int64), 34).cpu().numpy()
     assert np.array_equal(hot, O.one_hot(ids[0][:64, :64].astype(np.int64), 34))
+
+
+def test_eval_scores_bit_exact(L, O):
+    """metric.py on the GPU: the argmax label adapter and the confusion matrix are integer work -> equal to numpy; the
+    scores derived from the matrix follow."""
+    Mt = importlib.import_module("sg-gan-tf2_b200.metric")
+    rng = np.random.RandomState(3)
+    seg = rng.rand(2, 48, 80, 3).astype(np.float32)
+    fake = rng.rand(2, 48, 80, 3).astype(np.float32)
+    fake[0, :8] = seg[0, :8]                      # ties and agreements
+    seg[1, 5, 7] = [0.5, 0.5, 0.5]                # exact tie: first maximum wins
+    lt, lp = Mt.scores_seg_fake(seg, fake)
+    rt, rp = O.seg_fake_labels(seg, fake)
+    assert tuple(lt.shape) == rt.shape == (2, 80, 48)
+    assert np.array_equal(lt.cpu().numpy(), rt) and np.array_equal(lp.cpu().numpy(), rp)
+    a = rng.randint(-1, 36, size=50000)           # labels outside [0, n_class) are ignored (true) / never produced (pred)
+    b = rng.randint(0, 34, size=50000)
+    h = Mt._fast_hist(a, b, 34).cpu().numpy()
+    assert np.array_equal(h, O.fast_hist(a, b, 34)) and h.sum() == ((a >= 0) & (a < 34)).sum()
+    sc = Mt.scores(list(lt), list(lp), 34)
+    hist = sum(O.fast_hist(x, y, 34) for x, y in zip(rt, rp)).astype(np.float64)
+    assert abs(sc["Overall Acc"] - np.diag(hist).sum() / hist.sum()) < 1e-12
+    iu = np.diag(hist)[:3] / (hist.sum(1) + hist.sum(0) - np.diag(hist))[:3]
+    assert abs(sc["Mean IoU"] - iu.mean()) < 1e-12 and set(sc) == {"Overall Acc", "Mean Acc", "FreqW Acc", "Mean IoU", "Class IoU"}
+
+
+def test_graph_replay_matches_eager_launches(L, O):
+    """The step captured as one CUDA graph (sggan_graph_capture / sggan_graph_launch) does what the 250 eager launches do:
+    same losses and same weights, and Adam's time step keeps advancing from replay to replay (it is read from a
+    device-side counter, not baked into the graph).  Compared after two steps (the second is the first replay): later
+    steps of a GAN on random data amplify the 1e-7 noise of the few remaining atomic reductions chaotically."""
+    B, H, W, nb = 1, 128, 256, 2
+    real_A, seg_A, mask, _ = O.synthetic_batch(B, H, W, 34, seed=8)
+    dev = [t.cuda() for t in (real_A, seg_A, mask)]
+    runs = {}
+    for mode in ("eager", "graph"):
+        eng, gw, dw = _engine(L, O, B, H, W, nb)
+        eng.use_graph = mode == "graph"
+        losses = [eng.train_step(*dev).clone() for _ in range(2)]
+        torch.cuda.synchronize()
+        two = (eng.flat(L.NET_G, 0).clone(), eng.flat(L.NET_D, 0).clone(), eng.flat(L.NET_G, 3).clone())
+        losses += [eng.train_step(*dev).clone() for _ in range(2)]
+        torch.cuda.synchronize()
+        assert (eng._graph_key is not None) == (mode == "graph")
+        assert lib_step_count(L, eng) == 4
+        runs[mode] = (torch.stack(losses).cpu(), two)
+    (l0, (g0, d0, v0)), (l1, (g1, d1, v1)) = runs["eager"], runs["graph"]
+    assert ((l0[:2] - l1[:2]).abs() < 1e-4 * l0[:2].abs()).all(), (l0, l1)
+    assert ((l0[2:] - l1[2:]).abs() < 2e-2 * l0[2:].abs()).all(), (l0, l1)
+    # a replay with a stale Adam time step would move the weights by alpha_1 instead of alpha_2 (6 % of the update)
+    upd = rel(g0, torch.cat([w.reshape(-1) for w in gw]).cuda())
+    assert upd > 1e-3 and rel(g1, g0) < 2e-2 * upd and rel(d1, d0) < 2e-2 * upd and rel(v1, v0) < 1e-3, (upd, rel(g1, g0))
