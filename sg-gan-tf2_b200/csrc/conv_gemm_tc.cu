@@ -159,7 +159,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------ A producer: one tile per (run, chunk)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       for (int g = 0; g < agroups; ++g) {
         const int s = g % sa_stages;
         const uint32_t ph = (g / sa_stages) & 1;
@@ -174,7 +174,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------ B producer: one weight tile per (tap, chunk)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int it = 0;
       for (int r = 0, t0 = 0; r < p.nruns; t0 += p.run_len[r], ++r)
         for (int cc = 0; cc < cchunks; ++cc)
@@ -188,7 +188,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const bool tf32 = p.tf32 != 0;
       const uint32_t idesc = tf32 ? idesc_tf32_f32(kTileM, BN) : idesc_bf16_f32(kTileM, BN, 0, 0);
       int it = 0, g = 0;
@@ -526,7 +526,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp == 0) {
     // ------------------------------------------------------------ A producer (both CTAs: own 128 rows)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int g = 0;
       for (int j = cl; j < npairs; j += ncl) {
         const int gt = 2 * j + int(rank);
@@ -547,7 +547,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------ B producer (both CTAs: own 128 channels)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int it = 0;
       for (int j = cl; j < npairs; j += ncl)
         for (int r = 0, t0 = 0; r < p.nruns; t0 += p.run_len[r], ++r)
@@ -562,7 +562,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one_sync()) {  // rank is CTA-uniform: the warp is converged at the election
       const uint32_t idesc = idesc_bf16_f32(256, 256, 0, 0);
       int it = 0, g = 0, k = 0;
       for (int j = cl; j < npairs; j += ncl, ++k) {
@@ -772,7 +772,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   if (warp == 0) {
     // ------------------------------------------------------------ pixel-tile producer: one tile per (run, chunk)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int g = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int pt = t / nblk;
@@ -792,7 +792,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------ weight-tile producer: one tile per (tap, chunk)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n0 = (t % nblk) * 128;
@@ -809,7 +809,7 @@ conv_gemm_swap_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = idesc_bf16_f32(128, kSwapPix, 0, 0);
       int it = 0, g = 0, k = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++k) {
@@ -1022,7 +1022,7 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const uint32_t tmem_acc = tmem_base_sh;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const int xoff = p.x_off[tap], yoff = p.y_off[tap];
       const int xoff2 = p.x_pair ? p.x_off2[tap] : xoff;
       const int xc0 = p.x_pair ? 0 : mt * kTileM * NA;
@@ -1045,7 +1045,7 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const uint32_t idesc = idesc_bf16_f32(kTileM, BN, 1, 1);
       for (int ks = 0; ks < ksteps; ++ks) {
         const int s = ks % stages;

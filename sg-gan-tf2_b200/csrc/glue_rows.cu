@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
     // ------------------------------------------------------------ producer: bookkeeping + bulk copies, `nst` ahead
     // (one thread; spreading the per-chunk bookkeeping over the lanes of the warp was measured and is slower: the
     // passes are bound by the consumers' per-chunk latency, not by this thread)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       const int src_band = (MODE == RS_APPLY) ? 0 : max(p.g[0].ptr ? p.g[0].fold : 0, p.g[1].ptr ? p.g[1].fold : 0);
       const int dst_band = ((MODE == RS_APPLY || MODE == RS_BWD_APPLY) && dkind == 0) ? p.dmap.reflect : 0;
       const int band = max(src_band, dst_band);

@@ -178,6 +178,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
+// One lane of a converged warp, chosen by the hardware.  Code under `if (elect_one_sync())` is known to the compiler to
+// run in a single lane, so tcgen05 / bulk-copy instructions are emitted back to back; under `if (lane == 0)` ptxas wraps
+// EVERY such instruction in an ELECT / BRA.U.ANY loop over the (possibly several) active lanes.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {

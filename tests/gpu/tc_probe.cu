@@ -496,7 +496,7 @@ static int run_shift_probe() {
 
 // ------------------------------------------------------------------------------------------
 // Experiment: raw tcgen05.mma issue rate with both operands resident in shared memory (no TMA traffic).
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_mma, int N, int nacc, long long* cycles_out) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_mma, int N, int nacc, long long* cycles_out, int elect) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_mma, int N, int 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (threadIdx.x == 0) {
+  if (elect == 0 && threadIdx.x == 0) {
     const uint32_t idesc = idesc_bf16_f32(128, N, 0, 0);
     const uint64_t adesc = desc_kmajor_sw128(smem_u32(smem));
     const uint64_t bdesc = desc_kmajor_sw128(smem_u32(smem) + 16384);
@@ -525,6 +525,25 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_mma, int N, int 
     mbar_wait(&bar, 0, 31);
     const long long t1 = clock64();
     cycles_out[blockIdx.x] = t1 - t0;
+  }
+  if (elect != 0 && warp == 0) {
+    // the same loop under elect.sync: ptxas emits the UTCHMMAs back to back (no ELECT / BRA.U.ANY wrapper per instruction)
+    if (elect_one_sync()) {
+      const uint32_t idesc = idesc_bf16_f32(128, N, 0, 0);
+      const uint64_t adesc = desc_kmajor_sw128(smem_u32(smem));
+      const uint64_t bdesc = desc_kmajor_sw128(smem_u32(smem) + 16384);
+      const long long t0 = clock64();
+      for (int i = 0; i < n_mma; i += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tbase + uint32_t(((i + k) % nacc) * N), adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, 1);
+      }
+      umma_commit(&bar);
+      mbar_wait(&bar, 0, 31);
+      const long long t1 = clock64();
+      cycles_out[blockIdx.x] = t1 - t0;
+    }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -557,7 +576,7 @@ mma_rate_pair_kernel(int n_mma, int N, int nacc, int per_commit, long long* cycl
   __syncthreads();
   cluster_sync_all();
   tc_fence_after();
-  if (threadIdx.x == 0) {
+  if (warp == 0 && elect_one_sync()) {  // elect.sync: no per-instruction ELECT / BRA.U.ANY wrapper (see mma_rate)
     const long long t0 = clock64();
     if (rank == 0) {
       const uint32_t idesc = idesc_bf16_f32(256, N, 0, 0);
@@ -620,6 +639,7 @@ static int run_mma_rate() {
   CK(cudaMalloc(&d, 148 * sizeof(long long)));
   CK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   const int Ns[] = {256, 128, 64, 32};
+  for (int elect : {0, 1})
   for (int grid : {1, 148})
     for (int N : Ns)
       for (int nacc : {1, 2}) {
@@ -628,9 +648,9 @@ static int run_mma_rate() {
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
-        mma_rate_kernel<<<grid, 128, 58 * 1024>>>(n_mma, N, nacc, d);
+        mma_rate_kernel<<<grid, 128, 58 * 1024>>>(n_mma, N, nacc, d, elect);
         CK(cudaEventRecord(e0));
-        mma_rate_kernel<<<grid, 128, 58 * 1024>>>(n_mma, N, nacc, d);
+        mma_rate_kernel<<<grid, 128, 58 * 1024>>>(n_mma, N, nacc, d, elect);
         CK(cudaEventRecord(e1));
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
@@ -642,7 +662,7 @@ static int run_mma_rate() {
         long long cyc;
         CK(cudaMemcpy(&cyc, d, sizeof(cyc), cudaMemcpyDeviceToHost));
         const double flops = 2.0 * 128 * N * 16 * double(n_mma) * grid;
-        printf("MMA_RATE grid %3d N %3d nacc %d: %.1f cycles/MMA (ideal %d), kernel %.3f ms, %.1f TFLOP/s\n", grid, N, nacc,
+        printf("MMA_RATE %s grid %3d N %3d nacc %d: %.1f cycles/MMA (ideal %d), kernel %.3f ms, %.1f TFLOP/s\n", elect ? "elect.sync" : "tid==0", grid, N, nacc,
                double(cyc) / n_mma, N / 2, ms, flops / ms * 1e-9);
       }
   return 0;
