@@ -1178,11 +1178,11 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
   L->pair = 0;
   {
     const int T128 = (p.M + 127) / 128;
-    // opt-in (SGGAN_CONV_PAIR=1): measured on B200 the pair kernel hides its epilogue completely but its
-    // MMAs retire at ~208 cycles each (178 for back-to-back cta_group::2 MMAs plus the multicast commits)
-    // against ~168 in the single-CTA kernel, so both end within 2 % of each other (kernels)
+    // default (SGGAN_CONV_PAIR=0 selects the single-CTA kernel): with the issue loops under elect.sync the pair's MMAs
+    // retire at the ideal 128 cycles each (probe PAIR stamps: 18432 cycles per 144-MMA tile) and only the last tile's
+    // epilogue is exposed: 58 us against 73 us for the residual convolution (1.34 against 1.06 PFLOP/s)
     const char* env = getenv("SGGAN_CONV_PAIR");
-    const bool allow = env && env[0] == '1';
+    const bool allow = !(env && env[0] == '0');
     if (allow && !p.tf32 && p.BN == 256 && p.CoutPad == 256 && p.shift_kw == 0 && int64_t(T128) * p.B >= 148) {
       L->pair = 1;
       L->T128 = T128;

@@ -496,16 +496,17 @@ static int run_shift_probe() {
 
 // ------------------------------------------------------------------------------------------
 // Experiment: raw tcgen05.mma issue rate with both operands resident in shared memory (no TMA traffic).
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_mma, int N, int nacc, long long* cycles_out, int elect) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_mma, int N, int nacc, long long* cycles_out, int elect, int per_commit = 0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tbase;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < (16384 + N * 128) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   fence_proxy_async_smem();
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    mbar_init(&bar2, 1);
     fence_barrier_init();
   }
   uint32_t cols = 32;
@@ -537,6 +538,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int n_mma, int N, int 
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tbase + uint32_t(((i + k) % nacc) * N), adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, 1);
+        if (per_commit > 0 && ((i + 4) % per_commit) == 0) umma_commit(&bar2);  // a stage release every per_commit MMAs
       }
       umma_commit(&bar);
       mbar_wait(&bar, 0, 31);
@@ -582,9 +584,11 @@ mma_rate_pair_kernel(int n_mma, int N, int nacc, int per_commit, long long* cycl
       const uint32_t idesc = idesc_bf16_f32(256, N, 0, 0);
       const uint64_t adesc = desc_kmajor_sw128(smem_u32(smem));
       const uint64_t bdesc = desc_kmajor_sw128(smem_u32(smem) + 16384);
-      for (int i = 0; i < n_mma; ++i) {
-        umma_bf16_pair(tbase + uint32_t((i % nacc) * N), adesc + uint64_t((i & 3) * 2), bdesc + uint64_t((i & 3) * 2), idesc, 1);
-        if (per_commit > 0 && (i % per_commit) == per_commit - 1) umma_commit_pair(&bar2);
+      for (int i = 0; i < n_mma; i += 4) {  // four MMAs per iteration hide the loop's integer work
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_pair(tbase + uint32_t(((i + k) & (nacc - 1)) * N), adesc + uint64_t(k * 2), bdesc + uint64_t(k * 2), idesc, 1);
+        if (per_commit > 0 && ((i + 4) % per_commit) == 0) umma_commit_pair(&bar2);
       }
       umma_commit_pair(&bar);
     }
@@ -608,7 +612,7 @@ static int run_mma_rate_pair() {
   for (int grid : {2, 148})
     for (int N : {256, 128, 64})
       for (int nacc : {1, 2})
-        for (int pc : {0, 4}) {
+        for (int pc : {0, 4, 12, 24}) {
           if (nacc * N > 512) continue;
           const int n_mma = 4096;
           cudaEvent_t e0, e1;
@@ -665,6 +669,15 @@ static int run_mma_rate() {
         printf("MMA_RATE %s grid %3d N %3d nacc %d: %.1f cycles/MMA (ideal %d), kernel %.3f ms, %.1f TFLOP/s\n", elect ? "elect.sync" : "tid==0", grid, N, nacc,
                double(cyc) / n_mma, N / 2, ms, flops / ms * 1e-9);
       }
+  for (int pc : {4, 8, 12, 24, 48}) {
+    const int n_mma = 4080;
+    mma_rate_kernel<<<148, 128, 58 * 1024>>>(n_mma, 256, 2, d, 1, pc);
+    mma_rate_kernel<<<148, 128, 58 * 1024>>>(n_mma, 256, 2, d, 1, pc);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("mma_rate commit sweep: CUDA error\n"); return 1; }
+    long long cyc;
+    CK(cudaMemcpy(&cyc, d, sizeof(cyc), cudaMemcpyDeviceToHost));
+    printf("MMA_RATE elect.sync grid 148 N 256 nacc 2, tcgen05.commit every %2d MMAs: %.1f cycles/MMA\n", pc, double(cyc) / n_mma);
+  }
   return 0;
 }
 
