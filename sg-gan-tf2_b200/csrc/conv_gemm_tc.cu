@@ -1118,6 +1118,159 @@ wgrad_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 }
 
 // =============================================================================================
+// CTA-pair weight gradient for the 256 x 256-channel layers (the residual blocks).
+//
+// The single-CTA kernel above streams 64 KB of operands from L2 per 8 MMAs (X [64 px][256] + dY [64 px][256]): 8 KB per
+// MMA against the ~46 B/clk an SM gets out of L2 when all of them pull (tc_probe tma_share) = 178 cycles per MMA at
+// best, 230 measured, against the 128 the tensor pipe needs.  Here a cluster of two CTAs runs cta_group::2 MMAs with
+// M = 256 input channels over the pair (128 each) and N = 256 output channels, of which each CTA stages only ITS HALF of
+// the dY tile; the two accumulators of a CTA (2 x 256 TMEM columns) belong to TWO TAPS that share that dY tile.  Per SM
+// and 64-pixel chunk: X(tap a) 16 KB + X(tap b) 16 KB + dY half 16 KB = 48 KB per 8 MMAs = 6 KB per MMA.
+// Work unit: (pair of taps with the same dY offset, 256-channel block, split-K slice); an odd tap runs alone with one
+// accumulator.  Partials leave exactly like the single-CTA kernel's (plain stores, fixed-order wgrad_reduce).
+constexpr int kWgPairStages = 4;
+constexpr int kWgPairOperand = 64 * 128 * 2;          // 64 pixels x 128 channels, bf16
+constexpr int kWgPairStage = 3 * kWgPairOperand;      // X tap a | X tap b | dY half
+constexpr int kWgPairSmem = kWgPairStages * kWgPairStage + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgradThreads, 1)
+wgrad_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                       const WgradParams p, const int ngroups) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ uint64_t full_bar[kWgPairStages];   // leader: both CTAs' operand bytes of a stage have landed
+  __shared__ uint64_t empty_bar[kWgPairStages];  // both CTAs: the pair's MMAs on a stage have retired (multicast commit)
+  __shared__ uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_sh;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cl = blockIdx.x >> 1;
+  const int grp = cl % ngroups, xblk = cl / ngroups;
+  const int ta = p.pair_a[grp], tb = int(p.pair_b[grp]) - 1;  // tb < 0: a single tap, one accumulator
+  const int NA = tb >= 0 ? 2 : 1;
+  const int n0 = blockIdx.y * 256;
+  const int nchunk = (p.Mpix + 63) / 64;
+  const int total = p.B * nchunk;
+  const int per = (total + p.ksplit - 1) / p.ksplit;
+  const int kbeg = blockIdx.z * per;
+  const int kend = min(total, kbeg + per);
+  const int ksteps = max(kend - kbeg, 0);  // prepare_wgrad_gemm gives every slice work; both CTAs of a pair agree
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgPairStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+  }
+  if (warp == 1) tmem_alloc_pair(&tmem_base_sh, 512);
+  pdl_launch_dependents();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_sh;
+  const uint32_t stage_tx = uint32_t(NA + 1) * kWgPairOperand;  // bytes one CTA loads per stage
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer (both CTAs: own 128 x / 128 y channels)
+    if (elect_one_sync()) {
+      const int xa = p.x_off[ta], xb = tb >= 0 ? p.x_off[tb] : 0, yoff = p.y_off[ta];
+      const int xc = xblk * 256 + int(rank) * 128, yc = n0 + int(rank) * 128;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int s = ks % kWgPairStages;
+        mbar_wait(&empty_bar[s], ((ks / kWgPairStages) & 1) ^ 1, 14);
+        const int c = kbeg + ks;
+        const int b = c / nchunk, mc = (c - b * nchunk) * 64;
+        uint8_t* sa = smem + s * kWgPairStage;
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * stage_tx);
+        const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+        for (int h = 0; h < 2; ++h) tma_load_3d_pair(&tmX, bar, sa + h * 8192, xc + h * 64, mc + xa, b);
+        if (tb >= 0)
+          for (int h = 0; h < 2; ++h) tma_load_3d_pair(&tmX, bar, sa + kWgPairOperand + h * 8192, xc + h * 64, mc + xb, b);
+        for (int h = 0; h < 2; ++h) tma_load_3d_pair(&tmY, bar, sa + 2 * kWgPairOperand + h * 8192, yc + h * 64, mc + yoff, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (rank == 0 && elect_one_sync()) {
+      const uint32_t idesc = idesc_bf16_f32(256, 256, 1, 1);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int s = ks % kWgPairStages;
+        mbar_wait(&full_bar[s], (ks / kWgPairStages) & 1, 15);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * kWgPairStage);
+        const uint64_t bdesc = desc_mnmajor_sw128(sa + 2 * kWgPairOperand, 8192);
+        for (int a = 0; a < NA; ++a) {
+          const uint64_t adesc = desc_mnmajor_sw128(sa + a * kWgPairOperand, 8192);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 16 pixels (= 16 rows of 128 B) per MMA
+            umma_bf16_pair(tmem_acc + uint32_t(a * 256), adesc + uint64_t(k * (2048 >> 4)), bdesc + uint64_t(k * (2048 >> 4)),
+                           idesc, (ks | k) != 0);
+        }
+        umma_commit_pair(&empty_bar[s]);
+      }
+      umma_commit_pair(&acc_bar);
+    }
+  } else if (ksteps > 0) {
+    // ------------------------------------------------------------ epilogue (both CTAs: own 128 rows of both taps)
+    mbar_wait(&acc_bar, 0, 16);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float* obase = p.part ? p.part + int64_t(blockIdx.z) * p.part_stride : p.dW;
+    const bool vec = (p.dw_sy == 1) && ((p.dw_sx & 3) == 0) && ((p.dw_tap_stride & 3) == 0) && ((p.part_stride & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(obase) & 15) == 0);
+    const bool plain = p.part != nullptr;
+    const int xg = xblk * 256 + int(rank) * 128 + row;
+    for (int a = 0; a < NA; ++a) {
+      float* dst = obase + int64_t(a ? tb : ta) * p.dw_tap_stride + int64_t(xg) * p.dw_sx;
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(a * 256 + c0), v);  // warp-collective
+        if (xg < p.nx_valid) {
+          if (vec && n0 + c0 + 32 <= p.ny_valid) {
+            float* d4 = dst + n0 + c0;
+            if (plain) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4*>(d4 + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            } else {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d4 + 4 * g), "f"(v[4 * g]),
+                             "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3])
+                             : "memory");
+            }
+          } else {
+            const int64_t sy = p.dw_sy;
+            float* d1 = dst + int64_t(n0 + c0) * sy;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (n0 + c0 + e < p.ny_valid) {
+                if (plain) d1[e * sy] = v[e];
+                else atomicAdd(d1 + e * sy, v[e]);
+              }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be signalling this CTA's barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_acc, 512);
+  }
+}
+
+// =============================================================================================
 // Host side
 // Sort the taps by pixel offset and group consecutive offsets into runs (at most kHaloRows taps each).
 static void build_runs(ConvGemmParams& p) {
@@ -1272,11 +1425,57 @@ int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
   return e == cudaSuccess ? 0 : -4000 - int(e);
 }
 
+// Tap groups of the CTA-pair weight-gradient kernel: two taps that read dY at the same offset share a group (and the dY
+// tile); 0 = the shape is not eligible.  pair_a[g] = first tap, pair_b[g] = second tap + 1 (0: none).
+int wgrad_pair_groups(const WgradParams& p, uint8_t* pair_a, uint8_t* pair_b) {
+  static const bool allow = []() { const char* e = getenv("SGGAN_WGRAD_PAIR"); return !(e && e[0] == '0'); }();
+  if (!allow || p.x_pair || p.Cx <= 0 || p.Cx % 256 != 0 || p.BN != 256 || p.Cy % 256 != 0) return 0;
+  bool used[SGGAN_MAX_TAPS] = {};
+  int n = 0;
+  for (int t = 0; t < p.ntaps; ++t) {
+    if (used[t]) continue;
+    used[t] = true;
+    int mate = -1;
+    for (int u = t + 1; u < p.ntaps; ++u)
+      if (!used[u] && p.y_off[u] == p.y_off[t]) { mate = u; break; }
+    if (mate >= 0) used[mate] = true;
+    if (pair_a) { pair_a[n] = uint8_t(t); pair_b[n] = uint8_t(mate + 1); }
+    ++n;
+  }
+  return n;
+}
+
 int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L) {
   if (p.Cx <= 0 || (p.x_pair ? p.Cx != 64 : p.Cx % 128 != 0)) return -20;
   if (!(p.BN == 64 || p.BN == 128 || p.BN == 256) || p.Cy % p.BN != 0) return -21;
   if (p.ntaps < 1 || p.ntaps > SGGAN_MAX_TAPS || p.ksplit < 1) return -22;
   L->p = p;
+  L->pair_groups = wgrad_pair_groups(p, L->p.pair_a, L->p.pair_b);
+  if (L->pair_groups > 0) {
+    L->na = 2;
+    L->stages = kWgPairStages;
+    L->tmem_cols = 512;
+    L->smem = kWgPairSmem;
+    L->grid_x = 2 * L->pair_groups * (p.Cx / 256);
+    L->grid_y = p.Cy / 256;
+    const int total = p.B * ((p.Mpix + 63) / 64);
+    const int per = (total + p.ksplit - 1) / p.ksplit;
+    L->p.ksplit = (total + per - 1) / per;
+    L->grid_z = L->p.ksplit;
+    int r = make_tmap_bf16_3d(&L->tmX, p.X, p.Cx, p.x_frame_pix, p.B, uint64_t(p.x_row_stride) * 2,
+                              uint64_t(p.x_frame_pix) * p.x_row_stride * 2, 64, 64);
+    if (r) return -1000 - r;
+    r = make_tmap_bf16_3d(&L->tmY, p.Y, p.Cy, p.y_frame_pix, p.B, uint64_t(p.y_row_stride) * 2,
+                          uint64_t(p.y_frame_pix) * p.y_row_stride * 2, 64, 64);
+    if (r) return -2000 - r;
+    static bool pair_attr_set = false;
+    if (!pair_attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgPairSmem);
+      if (e != cudaSuccess) return -3300 - int(e);
+      pair_attr_set = true;
+    }
+    return 0;
+  }
   L->na = (!p.x_pair && p.Cx % 256 == 0) ? 2 : 1;
   {
     int st = kSmemBudget / (L->na * kABytes + p.BN * 128);
@@ -1310,6 +1509,11 @@ int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L) {
 
 int run_wgrad_gemm(const WgradLaunch& L, cudaStream_t st) {
   dim3 grid(L.grid_x, L.grid_y, L.grid_z);
+  if (L.pair_groups > 0) {
+    cudaError_t e = launch_kernel_pdl(wgrad_gemm_pair_kernel, grid, dim3(kWgradThreads), L.smem, st, pdl_enabled(), L.tmX, L.tmY,
+                                      L.p, L.pair_groups);
+    return e == cudaSuccess ? 0 : -4300 - int(e);
+  }
   cudaError_t e = launch_kernel_pdl(wgrad_gemm_tc_kernel, grid, dim3(kWgradThreads), L.smem, st, pdl_enabled(), L.tmX, L.tmY,
                                     L.p, L.stages, L.tmem_cols, L.na);
   return e == cudaSuccess ? 0 : -4000 - int(e);

@@ -28,6 +28,7 @@ struct WgradLaunch {
   int grid_x, grid_y, grid_z;
   int stages;
   int na;  // accumulators (128 x-channels each) per CTA
+  int pair_groups = 0;  // > 0: the CTA-pair kernel with this many tap groups (wgrad_pair_groups)
   unsigned tmem_cols;
   size_t smem;
 };
@@ -36,6 +37,8 @@ struct WgradLaunch {
 int prepare_conv_gemm(const ConvGemmParams& p, ConvGemmLaunch* L);
 int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st);
 int prepare_wgrad_gemm(const WgradParams& p, WgradLaunch* L);
+// tap groups the CTA-pair weight-gradient kernel would use for this shape (0: not eligible); the arrays may be null
+int wgrad_pair_groups(const WgradParams& p, uint8_t* pair_a, uint8_t* pair_b);
 int run_wgrad_gemm(const WgradLaunch& L, cudaStream_t st);
 // dW[i] += sum over split-K slices (fixed order) of the partial tiles, i < numel
 void launch_wgrad_reduce(const WgradLaunch& L, int64_t numel, cudaStream_t st);

@@ -345,6 +345,11 @@ int layer_prepare_wgrad(Layer& l, float* dW, int nimg, bool dry, float* part, si
     const int chunks = nimg * ((Mpix + 63) / 64);
     // one CTA per SM holds a whole accumulator: fill exactly one wave of 148 SMs (no tail round)
     int ks = tiles >= 148 ? 1 : 148 / tiles;
+    const int pg = wgrad_pair_groups(q, nullptr, nullptr);
+    if (pg > 0) {  // CTA-pair kernel: one cluster per TPC, 74 clusters in a wave
+      const int clusters = pg * (q.Cx / 256) * (q.Cy / 256);
+      ks = clusters >= 74 ? 1 : 74 / clusters;
+    }
     if (ks > chunks / 8) ks = chunks / 8;
     if (ks < 1) ks = 1;
     q.ksplit = ks;

@@ -122,6 +122,7 @@ struct WgradParams {
   int x_off2[SGGAN_MAX_TAPS];
   int y_off[SGGAN_MAX_TAPS];
   int x_pair;
+  uint8_t pair_a[SGGAN_MAX_TAPS], pair_b[SGGAN_MAX_TAPS];  // CTA-pair kernel: tap groups (filled by prepare_wgrad_gemm)
   int nx_valid, ny_valid;  // rows / columns of the tile actually accumulated into dW
   int Mpix;
   float* dW;

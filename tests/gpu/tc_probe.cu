@@ -340,7 +340,7 @@ static int run_wgrad_case(int B, int H, int W, int Cx, int Cy, int BN, int k, in
     printf("prepare_wgrad_gemm failed %d\n", r);
     return 1;
   }
-  printf("grid %d x %d x %d, stages %d, smem %zu\n", L.grid_x, L.grid_y, L.grid_z, L.stages, L.smem);
+  printf("grid %d x %d x %d, stages %d, smem %zu%s\n", L.grid_x, L.grid_y, L.grid_z, L.stages, L.smem, L.pair_groups ? " (CTA-pair kernel)" : "");
   r = run_wgrad_gemm(L, 0);
   cudaError_t e = cudaDeviceSynchronize();
   if (r || e != cudaSuccess) {
@@ -855,6 +855,12 @@ int main(int argc, char** argv) {
     rc = run_conv_case(c, 0, true);
   } else if (!strcmp(t, "wgrad_small")) {
     rc = run_wgrad_case(2, 6, 20, 128, 64, 64, 3, 3, 0, true);
+  } else if (!strcmp(t, "wgrad_pair_small")) {  // CTA-pair kernel (Cx, Cy multiples of 256), every entry checked
+    rc = run_wgrad_case(2, 6, 20, 256, 256, 256, 3, 3, 0, true);
+  } else if (!strcmp(t, "wgrad_pair_wide")) {  // two x blocks and two y blocks, ragged pixel count
+    rc = run_wgrad_case(1, 5, 13, 512, 512, 256, 3, 2, 0, false);
+  } else if (!strcmp(t, "wgrad_res14")) {  // the split the engine picks for the pair kernel (5 tap groups x 14 slices)
+    rc = run_wgrad_case(8, 64, 128, 256, 256, 256, 3, 14, 10, false);
   } else if (!strcmp(t, "wgrad_res")) {
     rc = run_wgrad_case(8, 64, 128, 256, 256, 256, 3, 8, 10, false);
   } else if (!strcmp(t, "tma_share")) {
