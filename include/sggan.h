@@ -146,13 +146,16 @@ int sggan_deconv2d_fwd(const float* x, const float* kernel, const float* bias, f
                        int Cin, int Cout, void* workspace, size_t workspace_bytes, void* stream);
 /* The fp32-accurate tier of the same two operators (north_star: "rel 1e-4 tf32"): activations stay fp32, the operands
  * are rounded to tf32 and multiplied by tcgen05.mma.kind::tf32 with fp32 accumulation; any Cin / Cout (padded
- * internally).  The reference computes in fp32 (Keras defaults); bf16 storage (the training path) deviates by ~5e-3
- * per layer, this tier by ~3e-4 (10-bit mantissa of tf32; tests/test_gpu_tf32.py). */
-size_t sggan_conv2d_tf32_workspace(int B, int H, int W, int Cin, int Cout, int k, int stride, int padding);
+ * internally).  The reference computes in fp32 (Keras defaults).  passes = 1: one tf32 product per term (operand
+ * rounding 2^-11, ~3e-4 relative on the 2304-term dot products of the residual blocks); passes = 3: "3xTF32", the
+ * operands are split hi + lo and hi*hi + lo*hi + hi*lo is accumulated (one convolution over 3x the input channels):
+ * fp32-level accuracy, <= 1e-5 relative (tests/test_gpu_tf32.py).  bf16 storage (the training path): ~5e-3 per layer. */
+size_t sggan_conv2d_tf32_workspace(int B, int H, int W, int Cin, int Cout, int k, int stride, int padding, int passes);
 int sggan_conv2d_fwd_tf32(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
-                          int Cout, int k, int stride, int padding, void* workspace, size_t workspace_bytes, void* stream);
+                          int Cout, int k, int stride, int padding, int passes, void* workspace, size_t workspace_bytes,
+                          void* stream);
 int sggan_deconv2d_fwd_tf32(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
-                            int Cout, void* workspace, size_t workspace_bytes, void* stream);
+                            int Cout, int passes, void* workspace, size_t workspace_bytes, void* stream);
 /* InstanceNormalization (+ activation, + residual) on fp32 storage with double-precision statistics; any C.
  * workspace: B * C * 16 bytes. */
 int sggan_instance_norm_fwd_f32(const float* x, const float* gamma, const float* beta, const float* residual, float* y, int B,

@@ -74,9 +74,9 @@ SYMBOLS = {
     "sggan_conv2d_workspace": (_SZ, [_I] * 8),
     "sggan_conv2d_fwd": (_I, [_P, _P, _P, _P] + [_I] * 8 + [_P, _SZ, _P]),
     "sggan_deconv2d_fwd": (_I, [_P, _P, _P, _P] + [_I] * 5 + [_P, _SZ, _P]),
-    "sggan_conv2d_tf32_workspace": (_SZ, [_I] * 8),
-    "sggan_conv2d_fwd_tf32": (_I, [_P, _P, _P, _P] + [_I] * 8 + [_P, _SZ, _P]),
-    "sggan_deconv2d_fwd_tf32": (_I, [_P, _P, _P, _P] + [_I] * 5 + [_P, _SZ, _P]),
+    "sggan_conv2d_tf32_workspace": (_SZ, [_I] * 9),
+    "sggan_conv2d_fwd_tf32": (_I, [_P, _P, _P, _P] + [_I] * 9 + [_P, _SZ, _P]),
+    "sggan_deconv2d_fwd_tf32": (_I, [_P, _P, _P, _P] + [_I] * 6 + [_P, _SZ, _P]),
     "sggan_instance_norm_fwd_f32": (_I, [_P] * 5 + [_I] * 4 + [_F, _I, _F, _P, _SZ, _P]),
     "sggan_conv2d_bwd_workspace": (_SZ, [_I] * 8),
     "sggan_conv2d_bwd": (_I, [_P] * 6 + [_I] * 8 + [_P, _SZ, _P]),

@@ -416,10 +416,11 @@ static int pad_channels_tf32(int c) {
   if (c <= 128) return 128;
   return (c + 255) / 256 * 256;
 }
-static int conv_layer_for_op_tf32(Layer& l, int B, int H, int W, int Cin, int Cout, int k, int stride, int padding, bool deconv) {
+static int conv_layer_for_op_tf32(Layer& l, int B, int H, int W, int Cin, int Cout, int k, int stride, int padding, bool deconv,
+                                  int passes) {
   memset(&l.xmap, 0, sizeof(l.xmap));
-  if (Cin < 1 || Cout < 1) return SGGAN_E_INVALID;
-  l.k = k; l.Cin = (Cin + 31) / 32 * 32; l.Cout = Cout; l.Hin = H; l.Win = W; l.has_norm = false; l.act = SG_ACT_NONE; l.alpha = 0.f;
+  if (Cin < 1 || Cout < 1 || !(passes == 1 || passes == 3)) return SGGAN_E_INVALID;
+  l.k = k; l.Cin = passes * ((Cin + 31) / 32 * 32); l.Cout = Cout; l.Hin = H; l.Win = W; l.has_norm = false; l.act = SG_ACT_NONE; l.alpha = 0.f;
   l.nb = l.nbv = B;
   if (deconv) { l.type = LT_DECONV; l.pad = PAD_ZERO; }
   else if (stride == 1) {
@@ -442,13 +443,13 @@ static size_t conv_op_bytes_tf32(const Layer& l, int64_t* offW, int64_t* offX) {
   *offX = off; off = align256(off + size_t(l.nb) * l.xmap.frame_pix * l.xmap.C * 4 + 4096);
   return off;
 }
-size_t sggan_conv2d_tf32_workspace(int B, int H, int W, int Cin, int Cout, int k, int stride, int padding) {
+size_t sggan_conv2d_tf32_workspace(int B, int H, int W, int Cin, int Cout, int k, int stride, int padding, int passes) {
   Layer l;
-  if (conv_layer_for_op_tf32(l, B, H, W, Cin, Cout, k, stride, padding, stride == -2)) return 0;
+  if (conv_layer_for_op_tf32(l, B, H, W, Cin, Cout, k, stride, padding, stride == -2, passes)) return 0;
   int64_t a, b;
   return conv_op_bytes_tf32(l, &a, &b);
 }
-static int conv_op_run_tf32(Layer& l, int Cin, const float* x, const float* kernel, const float* bias, float* y, void* ws,
+static int conv_op_run_tf32(Layer& l, int Cin, int passes, const float* x, const float* kernel, const float* bias, float* y, void* ws,
                             size_t ws_bytes, cudaStream_t st) {
   int64_t oW, oX;
   const size_t need = conv_op_bytes_tf32(l, &oW, &oX);
@@ -459,8 +460,9 @@ static int conv_op_run_tf32(Layer& l, int Cin, const float* x, const float* kern
   if (cudaMemsetAsync(X, 0, size_t(l.nb) * l.xmap.frame_pix * l.xmap.C * 4 + 4096, st) != cudaSuccess) return SGGAN_E_CUDA;
   PackParams pf = l.packf;
   pf.src = kernel; pf.dst = nullptr;
-  launch_pack_weights_f32(pf, Wf, st);
-  launch_f32_to_frame_f32(x, l.nb, l.Hin, l.Win, Cin, X, l.xmap, st);
+  const int Kp = l.Cin / passes;  // channels per group of the (hi | lo | hi) x (hi | hi | lo) split
+  launch_pack_weights_f32(pf, Wf, Kp, st);
+  launch_f32_to_frame_f32(x, l.nb, l.Hin, l.Win, Cin, X, l.xmap, Kp, st);
   FrameMap om;
   memset(&om, 0, sizeof(om));
   om.frame_pix = int64_t(l.Hout) * l.Wout; om.C = l.Cout; om.H = l.Hout; om.W = l.Wout; om.P = l.Wout;
@@ -479,16 +481,16 @@ static int conv_op_run_tf32(Layer& l, int Cin, const float* x, const float* kern
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
 int sggan_conv2d_fwd_tf32(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
-                          int Cout, int k, int stride, int padding, void* workspace, size_t workspace_bytes, void* stream) {
+                          int Cout, int k, int stride, int padding, int passes, void* workspace, size_t workspace_bytes, void* stream) {
   Layer l;
-  if (conv_layer_for_op_tf32(l, B, H, W, Cin, Cout, k, stride, padding, false)) { g_err = "unsupported conv2d shape"; return SGGAN_E_INVALID; }
-  return conv_op_run_tf32(l, Cin, x, kernel, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (conv_layer_for_op_tf32(l, B, H, W, Cin, Cout, k, stride, padding, false, passes)) { g_err = "unsupported conv2d shape"; return SGGAN_E_INVALID; }
+  return conv_op_run_tf32(l, Cin, passes, x, kernel, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 int sggan_deconv2d_fwd_tf32(const float* x, const float* kernel, const float* bias, float* y, int B, int H, int W, int Cin,
-                            int Cout, void* workspace, size_t workspace_bytes, void* stream) {
+                            int Cout, int passes, void* workspace, size_t workspace_bytes, void* stream) {
   Layer l;
-  if (conv_layer_for_op_tf32(l, B, H, W, Cin, Cout, 3, 2, 1, true)) { g_err = "unsupported deconv2d shape"; return SGGAN_E_INVALID; }
-  return conv_op_run_tf32(l, Cin, x, kernel, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (conv_layer_for_op_tf32(l, B, H, W, Cin, Cout, 3, 2, 1, true, passes)) { g_err = "unsupported deconv2d shape"; return SGGAN_E_INVALID; }
+  return conv_op_run_tf32(l, Cin, passes, x, kernel, bias, y, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 int sggan_instance_norm_fwd_f32(const float* x, const float* gamma, const float* beta, const float* residual, float* y, int B,
                                 int H, int W, int C, float eps, int act, float alpha, void* workspace, size_t workspace_bytes,

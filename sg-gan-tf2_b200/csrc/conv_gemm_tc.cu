@@ -515,6 +515,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tma_prefetch_desc(&tmBh);
   }
   if (warp == 1) tmem_alloc_pair(&tmem_base_sh, 512);
+  pdl_launch_dependents();
+  pdl_wait();  // the set-up above overlapped the previous kernel's tail; global memory is touched only below
   for (int t = threadIdx.x; t < 256; t += kConvThreads)
     sbias[t] = (p.bias != nullptr && t < p.Cout) ? __ldg(p.bias + t) : 0.f;
   tc_fence_before();
@@ -1407,9 +1409,8 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
 int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
   if (L.pair) {
     const int clusters = L.npairs < 74 ? L.npairs : 74;  // one CTA pair per TPC (148 SMs)
-    conv_gemm_pair_kernel<<<dim3(2 * clusters), kConvThreads, kPairSmem, st>>>(L.tmA, L.tmA8, L.tmBh, L.p, L.T128,
-                                                                              L.npairs);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_kernel_pdl(conv_gemm_pair_kernel, dim3(2 * clusters), dim3(kConvThreads), kPairSmem, st, pdl_enabled(),
+                                      L.tmA, L.tmA8, L.tmBh, L.p, L.T128, L.npairs);
     return e == cudaSuccess ? 0 : -4100 - int(e);
   }
   if (L.swap) {

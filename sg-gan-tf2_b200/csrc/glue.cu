@@ -188,7 +188,15 @@ __device__ __forceinline__ float round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__global__ void f32_to_frame_f32_kernel(const float* __restrict__ src, int B, int H, int W, int Cs, float* dst, FrameMap m) {
+// passes == 3 ("3xTF32"): the frame holds three channel groups of Kp channels each, [hi(x) | lo(x) | hi(x)] with
+// hi = tf32(x), lo = tf32(x - hi); the weight slabs hold [hi(w) | hi(w) | lo(w)], so that one convolution over 3 Kp input
+// channels accumulates hi*hi + lo*hi + hi*lo in fp32: the 2^-11 operand rounding of a single tf32 pass (~3e-4 relative
+// on a K = 2304 dot product) drops to the ~2^-22 of the neglected lo*lo term.
+__device__ __forceinline__ float tf32_part(float x, int group) {
+  const float hi = round_tf32(x);
+  return group == 1 ? round_tf32(x - hi) : hi;
+}
+__global__ void f32_to_frame_f32_kernel(const float* __restrict__ src, int B, int H, int W, int Cs, float* dst, FrameMap m, int Kp) {
   const int C4 = m.C >> 2;
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= int64_t(B) * H * W * C4) return;
@@ -200,7 +208,10 @@ __global__ void f32_to_frame_f32_kernel(const float* __restrict__ src, int B, in
   float4 v;
   float* vv = &v.x;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) vv[e] = (cg * 4 + e < Cs) ? round_tf32(src[pix * Cs + cg * 4 + e]) : 0.f;
+  for (int e = 0; e < 4; ++e) {
+    const int c = cg * 4 + e, grp = c / Kp, cc = c - grp * Kp;
+    vv[e] = cc < Cs ? tf32_part(src[pix * Cs + cc], grp) : 0.f;
+  }
   float* base = dst + int64_t(b) * m.frame_pix * m.C + cg * 4;
   if (m.kind == 0 && m.reflect > 0) {
     int rr[3], cc[3];
@@ -211,9 +222,9 @@ __global__ void f32_to_frame_f32_kernel(const float* __restrict__ src, int B, in
     *reinterpret_cast<float4*>(base + frame_pixel(m, i, j) * m.C) = v;
   }
 }
-void launch_f32_to_frame_f32(const float* src, int B, int H, int W, int Cs, float* dst, const FrameMap& dmap, cudaStream_t st) {
+void launch_f32_to_frame_f32(const float* src, int B, int H, int W, int Cs, float* dst, const FrameMap& dmap, int Kp, cudaStream_t st) {
   const int64_t tot = int64_t(B) * H * W * (dmap.C / 4);
-  f32_to_frame_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(src, B, H, W, Cs, dst, dmap);
+  f32_to_frame_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(src, B, H, W, Cs, dst, dmap, Kp);
 }
 // instance-norm statistics of a plain fp32 [B][HW][C] tensor in double precision: stats[b][c] = (sum, sum of squares)
 __global__ void __launch_bounds__(256) in_stats_f32_kernel(const float* __restrict__ x, int HW, int C, double* stats, int ppb) {
@@ -751,18 +762,18 @@ __device__ __forceinline__ void pack_one(const PackParams& p, int64_t idx8) {
   reinterpret_cast<uint4*>(p.dst)[idx8] = w;
 }
 __global__ void pack_weights_kernel(const PackParams p) { pack_one(p, int64_t(blockIdx.x) * blockDim.x + threadIdx.x); }
-// the same slabs as fp32 elements rounded to tf32 (dst is float [T][N][K])
-__global__ void pack_weights_f32_kernel(const PackParams p, float* dst) {
+// the same slabs as fp32 elements rounded to tf32 (dst is float [T][N][K]); K = groups x Kp, see f32_to_frame_f32_kernel
+__global__ void pack_weights_f32_kernel(const PackParams p, float* dst, int Kp) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t tot = int64_t(p.T) * p.N * p.K;
   if (idx >= tot) return;
-  const int k = int(idx % p.K);
+  const int k = int(idx % p.K), grp = k / Kp, kk = k - grp * Kp;
   const int64_t tn = idx / p.K;
-  dst[idx] = round_tf32(pack_value(p, int(tn / p.N), int(tn % p.N), k));
+  dst[idx] = tf32_part(pack_value(p, int(tn / p.N), int(tn % p.N), kk), grp == 2 ? 1 : 0);
 }
-void launch_pack_weights_f32(const PackParams& p, float* dst, cudaStream_t st) {
+void launch_pack_weights_f32(const PackParams& p, float* dst, int Kp, cudaStream_t st) {
   const int64_t tot = int64_t(p.T) * p.N * p.K;
-  pack_weights_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(p, dst);
+  pack_weights_f32_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(p, dst, Kp);
 }
 __global__ void __launch_bounds__(256) pack_weights_batch_kernel(const PackParams* __restrict__ jobs,
                                                                  const int* __restrict__ starts, int njobs) {

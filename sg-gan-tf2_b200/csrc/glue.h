@@ -115,8 +115,8 @@ void launch_mask_reduce(const float* x, const float* mask, int B, int Hd, int Wd
                         float* out, cudaStream_t st);
 // fp32 / tf32 operator tier (see glue.cu): fp32 frame with tf32-rounded values (Cs source channels, dmap.C >= Cs padded
 // with zeros), tf32-rounded fp32 weight slabs, instance norm on fp32 storage with double-precision statistics
-void launch_f32_to_frame_f32(const float* src, int B, int H, int W, int Cs, float* dst, const FrameMap& dmap, cudaStream_t st);
-void launch_pack_weights_f32(const PackParams& p, float* dst, cudaStream_t st);
+void launch_f32_to_frame_f32(const float* src, int B, int H, int W, int Cs, float* dst, const FrameMap& dmap, int Kp, cudaStream_t st);
+void launch_pack_weights_f32(const PackParams& p, float* dst, int Kp, cudaStream_t st);
 void launch_instance_norm_f32(const float* x, const float* gamma, const float* beta, const float* res, float* y, int B, int HW,
                               int C, float eps, int act, float alpha, double* stats, cudaStream_t st);
 // elementwise helpers for ops.py

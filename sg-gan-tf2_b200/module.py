@@ -155,6 +155,33 @@ class GeneratorResnet(_Net):
         self.n_blocks = n_blocks
         self.input_hw = (image_height, image_width)
 
+    def forward_fp32(self, x, precision="tf32x3"):
+        """The same network on the fp32-storage operator tier (ops.conv2d_raw / deconv2d_raw / instance_norm_raw with
+        precision "tf32" or "tf32x3"): what the reference computes in fp32 (module.py:219-269), for accuracy checks of
+        the bf16 training path and for inference that must match the reference to 1e-4.  Any image size >= 8 px."""
+        from . import ops
+        v = [t if t.is_cuda else t.cuda() for t in self._vars]
+        x = L.as_cuda_f32(x)
+
+        def cna(h, i, act, stride=1, padding="SAME", deconv=False, residual=None):
+            k, b, g, be = v[i:i + 4]
+            h = ops.deconv2d_raw(h, k, b, precision=precision) if deconv else \
+                ops.conv2d_raw(h, k, b, stride=stride, padding=padding, precision=precision)
+            return ops.instance_norm_raw(h, g, be, eps=1e-3, act=act, residual=residual, precision=precision)
+
+        h = cna(x, 0, "relu", padding="REFLECT")              # c7s1-64 on the 3-pixel reflect pad
+        h = cna(h, 4, "relu", stride=2)
+        h = cna(h, 8, "relu", stride=2)
+        i = 12
+        for _ in range(self.n_blocks):                        # residule_block (module.py:208-217)
+            y = cna(h, i, "relu", padding="REFLECT")
+            h = cna(y, i + 4, None, padding="REFLECT", residual=h)
+            i += 8
+        h = cna(h, i, "relu", deconv=True)
+        h = cna(h, i + 4, "relu", deconv=True)
+        k, b = v[i + 8], v[i + 9]
+        return torch.tanh(ops.conv2d_raw(h, k, b, stride=1, padding="REFLECT", precision=precision))
+
     def __call__(self, x):
         x = L.as_cuda_f32(x)
         B, H, W, _ = x.shape
