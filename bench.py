@@ -232,7 +232,10 @@ def main():
 
             def step_e2e():
                 model.train_step(ns)
-                return (float(model.gen_loss), float(model.disc_loss))  # the reference prints both every step (model.py:260)
+                # the reference prints both losses every step (model.py:260): every step's two floats come back to the
+                # host through an asynchronous copy and are READ one step late, so the next batch's H2D copy (copy
+                # stream, double-buffered device inputs) runs underneath this step's kernels
+                return model.losses_host(lag=1)
             h2d, d2h = int(real_h.nbytes + seg_h.nbytes + mask_h.nbytes), 8
         for _ in range(2):
             step_e2e()
@@ -240,6 +243,9 @@ def main():
         e0.record()
         for _ in range(args.steps):
             step_e2e()
+        if not infer:
+            last = model.losses_host(lag=0)  # the last step's losses are read inside the timed region too
+            assert last is not None and all(x == x for x in last)
         e1.record()
         sync_all()
         ms2 = max_over_ranks(e0.elapsed_time(e1))

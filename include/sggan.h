@@ -94,10 +94,12 @@ int sggan_step_adam(sggan_handle* h, int net);
 int sggan_step_adam_async(sggan_handle* h, int net);
 int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask,
                      float* losses_out);
-/* The same step as ONE CUDA graph: capture once for a set of (stable) device pointers, then replay.  A replay is one
- * cudaGraphLaunch on the handle's stream and does exactly what sggan_train_step does (Adam's time step is read from a
- * device-side counter, so it advances from replay to replay).  Needs a non-default stream at sggan_create; run one
- * eager sggan_train_step first (lazy kernel attributes). */
+/* The same step as ONE CUDA graph: capture once per set of (stable) device pointers, then replay.  sggan_graph_capture
+ * captures the step for these pointers -- or, if it already has (up to 4 sets are kept: double-buffered inputs alternate
+ * between two), just selects that graph; sggan_graph_launch replays the selected one: a single cudaGraphLaunch on the
+ * handle's stream that does exactly what sggan_train_step does (Adam's time step is read from a device-side counter, so
+ * it advances from replay to replay).  Needs a non-default stream at sggan_create; run one eager sggan_train_step first
+ * (lazy kernel attributes). */
 int sggan_graph_capture(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask, float* losses_out);
 int sggan_graph_launch(sggan_handle* h);
 int64_t sggan_step_count(const sggan_handle* h);

@@ -196,7 +196,8 @@ class Engine:
                 check(lib().sggan_create(C.byref(cfg), C.c_void_p(self.workspace.data_ptr()), nbytes,
                                          C.c_void_p(self.stream.cuda_stream), C.byref(h)))
         self.h = h
-        self._graph_key = None      # device pointers the captured step graph is valid for
+        self._graph_key = None      # device pointers of the step graph replayed last
+        self._seen_keys = set()     # input pointer sets that have run eagerly once
         self._eager_steps = 0
         self.use_graph = os.environ.get("SGGAN_GRAPH", "1") != "0"
         self._flat = {}
@@ -301,16 +302,20 @@ class Engine:
         key = (a.data_ptr(), s.data_ptr(), m.data_ptr())
         with _EngineStream(self):
             if self.use_graph and self._eager_steps >= 1 and not getattr(self, "_profiling", False):
-                if self._graph_key != key and key == getattr(self, "_last_key", None):  # same buffers twice in a row
+                # a set of buffers seen before is worth a graph (the library keeps up to four: double-buffered inputs
+                # alternate between two); capture is also the "select" call for a set that is already captured
+                if key in self._seen_keys:
                     rc = lib().sggan_graph_capture(self.h, C.c_void_p(key[0]), C.c_void_p(key[1]), C.c_void_p(key[2]),
                                                    C.c_void_p(self.losses.data_ptr()))
-                    self._graph_key = key if rc == 0 else None
-                    if rc != 0:
-                        self.use_graph = False  # capture refused (still the same kernels, launched one by one)
-                if self._graph_key == key:
-                    check(lib().sggan_graph_launch(self.h))
-                    return self.losses
-            self._last_key = key
+                    if rc == 0:
+                        self._graph_key = key
+                        check(lib().sggan_graph_launch(self.h))
+                        return self.losses
+                    self.use_graph = False  # capture refused (still the same kernels, launched one by one)
+                    self._graph_key = None
+            if len(self._seen_keys) > 64:
+                self._seen_keys.clear()
+            self._seen_keys.add(key)
             check(lib().sggan_train_step(self.h, C.c_void_p(a.data_ptr()), C.c_void_p(s.data_ptr()),
                                          C.c_void_p(m.data_ptr()), C.c_void_p(self.losses.data_ptr())))
             self._eager_steps += 1

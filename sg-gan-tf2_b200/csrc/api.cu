@@ -80,8 +80,10 @@ void sggan_destroy(sggan_handle* h) {
   if (e.ev_fork) cudaEventDestroy(e.ev_fork);
   if (e.ev_join) cudaEventDestroy(e.ev_join);
   if (e.ev_comm) cudaEventDestroy(e.ev_comm);
-  if (e.gexec) cudaGraphExecDestroy(e.gexec);
-  if (e.graph) cudaGraphDestroy(e.graph);
+  for (auto& g : e.graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
   for (auto ev : e.prof_ev) cudaEventDestroy(ev);
   delete h;
 }
@@ -177,8 +179,15 @@ int sggan_train_step(sggan_handle* h, const float* real_A, const float* seg_A, c
 int sggan_graph_capture(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask, float* losses_out) {
   Engine& e = h->e;
   if (!e.weights_ready) { g_err = "weights not set"; return SGGAN_E_STATE; }
-  if (e.gexec) { cudaGraphExecDestroy(e.gexec); e.gexec = nullptr; }
-  if (e.graph) { cudaGraphDestroy(e.graph); e.graph = nullptr; }
+  const void* want[4] = {real_A, seg_A, mask, losses_out};
+  for (int i = 0; i < e.ngraphs; ++i)
+    if (e.graphs[i].exec && !memcmp(e.graphs[i].ptr, want, sizeof(want))) { e.graph_sel = i; return 0; }  // already captured
+  // a new set of pointers: take a free slot, or recycle the oldest one
+  int slot = e.ngraphs < Engine::kMaxStepGraphs ? e.ngraphs : e.graph_next;
+  Engine::StepGraph& sg = e.graphs[slot];
+  if (sg.exec) { cudaGraphExecDestroy(sg.exec); sg.exec = nullptr; }
+  if (sg.graph) { cudaGraphDestroy(sg.graph); sg.graph = nullptr; }
+  e.graph_sel = -1;
   e.join_side();
   if (cudaStreamBeginCapture(e.st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     g_err = "cudaStreamBeginCapture failed (is the handle's stream the legacy default stream?)";
@@ -196,21 +205,24 @@ int sggan_graph_capture(sggan_handle* h, const float* real_A, const float* seg_A
     cudaGetLastError();
     return r != 0 ? r : SGGAN_E_CUDA;
   }
-  if (cudaGraphInstantiate(&e.gexec, g, 0) != cudaSuccess) {
+  if (cudaGraphInstantiate(&sg.exec, g, 0) != cudaSuccess) {
     g_err = "cudaGraphInstantiate failed";
     cudaGraphDestroy(g);
-    e.gexec = nullptr;
+    sg.exec = nullptr;
     cudaGetLastError();
     return SGGAN_E_CUDA;
   }
-  e.graph = g;
-  e.gptr[0] = real_A; e.gptr[1] = seg_A; e.gptr[2] = mask; e.gptr[3] = losses_out;
+  sg.graph = g;
+  memcpy(sg.ptr, want, sizeof(want));
+  if (slot == e.ngraphs) ++e.ngraphs;
+  e.graph_next = (slot + 1) % Engine::kMaxStepGraphs;
+  e.graph_sel = slot;
   return 0;
 }
 int sggan_graph_launch(sggan_handle* h) {
   Engine& e = h->e;
-  if (!e.gexec) { g_err = "no captured step (call sggan_graph_capture)"; return SGGAN_E_STATE; }
-  if (cudaGraphLaunch(e.gexec, e.st) != cudaSuccess) { g_err = "cudaGraphLaunch failed"; return SGGAN_E_CUDA; }
+  if (e.graph_sel < 0 || !e.graphs[e.graph_sel].exec) { g_err = "no captured step (call sggan_graph_capture)"; return SGGAN_E_STATE; }
+  if (cudaGraphLaunch(e.graphs[e.graph_sel].exec, e.st) != cudaSuccess) { g_err = "cudaGraphLaunch failed"; return SGGAN_E_CUDA; }
   e.step += 1;
   return 0;
 }

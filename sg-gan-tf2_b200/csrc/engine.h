@@ -98,9 +98,16 @@ struct Engine {
   uint8_t *zero_begin, *zero_end;
   int64_t step;
   long long* step_dev = nullptr;  // the same count on the device (Adam reads it: a captured graph must not bake t in)
-  cudaGraph_t graph = nullptr;    // captured sggan_train_step (sggan_graph_capture) and the pointers it was captured with
-  cudaGraphExec_t gexec = nullptr;
-  const void* gptr[4] = {nullptr, nullptr, nullptr, nullptr};
+  // captured sggan_train_step graphs (sggan_graph_capture), one per set of device pointers: double-buffered inputs
+  // alternate between two of them
+  struct StepGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+  };
+  static constexpr int kMaxStepGraphs = 4;
+  StepGraph graphs[kMaxStepGraphs];
+  int ngraphs = 0, graph_sel = -1, graph_next = 0;
   int adam_mask = 0;  // which nets have been updated in the current step (bit 0 G, bit 1 D)
   int nlaunch;
   bool weights_ready;

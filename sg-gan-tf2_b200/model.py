@@ -63,7 +63,14 @@ class sggan(object):
         self.world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self._pinned = {}
         self._dev = {}
-        self._h2d_done = {}
+        self._copy_stream = None
+        self._slot = 1
+        self._uploaded = False
+        self._h2d_done = [None, None]
+        self._consumed = [None, None]
+        self._loss_ev = [None, None]
+        self._loss_host = None
+        self._steps_done = 0
 
     # ---- plan -----------------------------------------------------------------------------------------
     def _ensure_runtime(self, B, H, W, mask_hw):
@@ -95,46 +102,96 @@ class sggan(object):
         self.runtime = rt
         return rt
 
+    # ---- host batches -> device: double-buffered, on a copy stream -------------------------------------------
+    # Step k's three host arrays are copied into device slot k % 2 by a copy stream that only waits for step k-2 (the
+    # previous user of that slot), so the copy of step k+1 runs underneath the kernels of step k whenever the caller
+    # does not block in between -- read the losses with losses_host(lag=1) for that.  Each slot has stable device
+    # pointers, i.e. its own captured step graph (the library keeps up to four).
+    def _begin_uploads(self):
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+        self._slot = (self._slot + 1) & 1
+        self._uploaded = False
+
     def _upload(self, name, x):
-        """numpy batch -> device through a persistent pinned staging buffer (H2D inside the step)."""
+        """One input of the step: device tensors pass through; host data goes to this step's device slot."""
         if isinstance(x, torch.Tensor) and x.is_cuda:
             return x.float().contiguous()
-        if isinstance(x, torch.Tensor) and x.dtype == torch.float32 and x.is_contiguous() and x.is_pinned():
-            # already page-locked: one asynchronous H2D copy into a persistent device buffer (stable pointers keep the
-            # captured step graph valid)
-            dev = self._dev.get(name)
-            if dev is None or dev.shape != x.shape:
-                dev = torch.empty(tuple(x.shape), dtype=torch.float32, device="cuda")
-                self._dev[name] = dev
+        slot = self._slot
+        pinned = isinstance(x, torch.Tensor) and x.dtype == torch.float32 and x.is_contiguous() and x.is_pinned()
+        if not pinned:
+            # pageable source: stage it in a persistent page-locked buffer of this slot (multi-threaded host copy)
+            x = torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float32))) if not isinstance(x, torch.Tensor) \
+                else x.float().contiguous()
+            buf = self._pinned.get((name, slot))
+            if buf is None or buf.shape != x.shape:
+                buf = torch.empty(tuple(x.shape), dtype=torch.float32).pin_memory()
+                self._pinned[(name, slot)] = buf
+            ev = self._h2d_done[slot]
+            if ev is not None:
+                ev.synchronize()  # the copy out of this staging buffer two steps ago has finished
+            buf.copy_(x)
+            x = buf
+        dev = self._dev.get((name, slot))
+        if dev is None or dev.shape != x.shape:
+            dev = torch.empty(tuple(x.shape), dtype=torch.float32, device="cuda")
+            self._dev[(name, slot)] = dev
+        cs = self._copy_stream
+        if not self._uploaded:
+            self._uploaded = True
+            if self._consumed[slot] is not None:
+                cs.wait_event(self._consumed[slot])  # the step that last read this slot
+            else:
+                cs.wait_stream(torch.cuda.current_stream())  # first use: order after the allocation
+        with torch.cuda.stream(cs):
             dev.copy_(x, non_blocking=True)
-            return dev
-        x = torch.as_tensor(np.ascontiguousarray(np.asarray(x, dtype=np.float32))) if not isinstance(x, torch.Tensor) \
-            else x.float().contiguous()
-        buf = self._pinned.get(name)
-        if buf is None or buf.shape != x.shape:
-            buf = torch.empty(tuple(x.shape), dtype=torch.float32).pin_memory()
-            self._pinned[name] = buf
-        ev = self._h2d_done.get(name)
-        if ev is not None:
-            ev.synchronize()  # the previous step's asynchronous copy out of this staging buffer has finished
-        buf.copy_(x)  # multi-threaded host copy into the page-locked staging buffer
-        dev = self._dev.get(name)
-        if dev is None or dev.shape != buf.shape:
-            dev = torch.empty(tuple(buf.shape), dtype=torch.float32, device="cuda")
-            self._dev[name] = dev
-        dev.copy_(buf, non_blocking=True)
-        ev = ev or torch.cuda.Event()
-        ev.record()
-        self._h2d_done[name] = ev
         return dev
+
+    def _end_uploads(self):
+        if self._uploaded:
+            ev = self._h2d_done[self._slot] or torch.cuda.Event()
+            ev.record(self._copy_stream)
+            self._h2d_done[self._slot] = ev
+            torch.cuda.current_stream().wait_event(ev)
+
+    def _step_enqueued(self, eng):
+        """After the step's launches: mark the input slot as consumed and start the losses' way back to the host."""
+        slot = self._slot
+        cur = torch.cuda.current_stream()
+        if self._uploaded:
+            ev = self._consumed[slot] or torch.cuda.Event()
+            ev.record(cur)
+            self._consumed[slot] = ev
+        if self._loss_host is None:
+            self._loss_host = torch.zeros((2, 2), dtype=torch.float32).pin_memory()
+        if self._loss_ev[slot] is not None:
+            self._loss_ev[slot].synchronize()  # nobody may still be waiting for the values of two steps ago
+        self._loss_host[slot].copy_(eng.losses, non_blocking=True)
+        ev = self._loss_ev[slot] or torch.cuda.Event()
+        ev.record(cur)
+        self._loss_ev[slot] = ev
+        self._steps_done += 1
+
+    def losses_host(self, lag=0):
+        """(gen_loss, disc_loss) of the step `lag` steps back as Python floats, through an asynchronous copy into
+        page-locked memory that was enqueued right behind that step.  lag=0 waits for the step just enqueued (what
+        float(self.gen_loss) does); lag=1 returns the previous step's values while the current one runs -- the train
+        loop's per-step print (model.py:260) then costs no pipeline bubble.  None if that step does not exist."""
+        if lag not in (0, 1) or self._steps_done <= lag:
+            return None
+        slot = (self._slot - lag) & 1
+        self._loss_ev[slot].synchronize()
+        return float(self._loss_host[slot, 0]), float(self._loss_host[slot, 1])
 
     # ---- the hot path ---------------------------------------------------------------------------------
     def train_step(self, args=None):
         """model.py:169-200.  Inputs come from self.real_A / self.seg_A / self.mask_A exactly as in the
         reference's train loop (model.py:249-256)."""
+        self._begin_uploads()
         real_A = self._upload("real_A", self.real_A)
         seg_A = self._upload("seg_A", self.seg_A)
         mask_A = self._upload("mask_A", self.mask_A)
+        self._end_uploads()
         B, H, W, _ = real_A.shape
         rt = self._ensure_runtime(B, H, W, (int(mask_A.shape[1]), int(mask_A.shape[2])))
         eng = rt.engine
@@ -151,8 +208,11 @@ class sggan(object):
             eng.step_adam(L.NET_D, overlapped=True)    # side stream: runs while G's all-reduce is in flight
             hg.wait()
             eng.step_adam(L.NET_G)                     # joins the side stream
+        self._step_enqueued(eng)
+        # views into buffers the NEXT step overwrites (clone to keep); float(self.gen_loss) synchronises, losses_host() is
+        # the asynchronous way
         self.fake_A = eng.last_fake()
-        self.gen_loss, self.disc_loss = eng.losses[0], eng.losses[1]  # device scalars; float() syncs
+        self.gen_loss, self.disc_loss = eng.losses[0], eng.losses[1]
         return self.gen_loss, self.disc_loss
 
     def generate_test_images(self, sample_imgA):
@@ -202,8 +262,12 @@ class sggan(object):
                 for idx, (a, s, m) in enumerate(it):
                     self.real_A, self.seg_A, self.mask_A = a, s, m
                     self.train_step(args)
-                    print("Epoch: [%2d] [%4d] time: %4.4f Gen_Loss: %f Disc_Loss: %f " % (
-                        epoch, idx, time.time() - start_time, float(self.gen_loss), float(self.disc_loss)))
+                    # the reference prints both losses every step (model.py:260); here the line is one step late so that
+                    # the host never waits for the step it has just enqueued
+                    got = self.losses_host(lag=1)
+                    if got is not None:
+                        print("Epoch: [%2d] [%4d] time: %4.4f Gen_Loss: %f Disc_Loss: %f " % (
+                            epoch, idx - 1, time.time() - start_time, got[0], got[1]))
         finally:
             if getattr(args, "checkpoint_dir", None):
                 self.save(args.checkpoint_dir, epoch)

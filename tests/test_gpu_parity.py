@@ -435,6 +435,51 @@ def test_model_api(L, O, tmp_path):
     assert abs(float(m.disc_loss_p2p(d, -d)) - float(O.disc_loss_p2p(d.cpu(), -d.cpu()))) < 1e-5
 
 
+def test_model_pipelined_host_batches(L, O):
+    """model.sggan.train_step with HOST batches that change every step: the double-buffered copy-stream uploads, the two
+    captured step graphs (one per device slot) and the one-step-late asynchronous loss readback give exactly the losses
+    of a run that synchronises after every step on device-resident copies of the same batches."""
+    M = importlib.import_module("sg-gan-tf2_b200.model")
+    # a tiny learning rate keeps the comparison about DATA MOVEMENT (which batch was read when): at lr 1e-3 a GAN on random
+    # data amplifies the 1e-7 noise of the remaining atomic reductions to percents within a few steps
+    ns = argparse.Namespace(batch_size=1, image_width=256, image_height=128, segment_class=34, use_resnet=True, lr_effective=1e-6)
+    batches = [O.synthetic_batch(1, 128, 256, 34, seed=40 + (i % 3))[:3] for i in range(7)]
+    gw = O.init_weights(O.generator_spec(), 1, randomize_affine=True)
+    dw = O.init_weights(O.discriminator_spec(segment_class=34), 2, randomize_affine=True)
+
+    def run(pipelined):
+        m = M.sggan(ns)
+        m.generator.set_weights([w.numpy() for w in gw])
+        m.discriminator.set_weights([w.numpy() for w in dw])
+        out = []
+        for i, (a, s, k) in enumerate(batches):
+            if pipelined:
+                # pinned tensors on even steps, pageable numpy on odd ones: both staging paths
+                m.real_A, m.seg_A, m.mask_A = (a.clone().pin_memory(), s.clone().pin_memory(), k.clone().pin_memory()) if i % 2 == 0 \
+                    else (a.numpy(), s.numpy(), k.numpy())
+                m.train_step(ns)
+                got = m.losses_host(lag=1)
+                assert (got is None) == (i == 0)
+                if got is not None:
+                    out.append(got)
+            else:
+                m.real_A, m.seg_A, m.mask_A = a.cuda(), s.cuda(), k.cuda()
+                m.train_step(ns)
+                out.append((float(m.gen_loss), float(m.disc_loss)))
+        if pipelined:
+            out.append(m.losses_host(lag=0))
+            assert m.runtime.engine._graph_key is not None  # the slots' graphs were captured and replayed
+        return np.array(out), m.generate_test_images(batches[0][0]).cpu()
+
+    lp, yp = run(True)
+    ls, ys = run(False)
+    assert lp.shape == ls.shape == (7, 2)
+    assert np.abs(lp - ls).max() <= 1e-4 * np.abs(ls).max(), (lp, ls)
+    assert (np.abs(ls[0] - ls[1]) / np.abs(ls[0])).max() > 1e-2  # the batches differ: a mixed-up slot would show
+    assert np.abs(lp - ls).max() < 0.1 * np.abs(ls[0] - ls[1]).min()
+    assert rel(yp, ys) < 1e-3, rel(yp, ys)
+
+
 # ---------------------------------------------------------------------------------------------- kernel probe
 PROBE_CASES = ["conv_small", "conv_small64", "conv_small256", "conv_swap128", "conv_swap64", "conv_pair_check",
                "conv_out7", "conv_out7_mid", "conv_out7_shift_small", "wgrad_small", "shift"]
@@ -455,13 +500,22 @@ def test_tc_probe_kernels(case):
 
 
 def test_tc_probe_pair_kernel():
-    """The opt-in CTA-pair (cta_group::2) kernel, including an odd tile count (dummy peer tile)."""
+    """The CTA-pair (cta_group::2) kernels: convolution (including an odd tile count: dummy peer tile) and weight gradient."""
     import subprocess
     exe = os.path.join(ROOT, "build", "tc_probe")
     env = dict(os.environ, SGGAN_CONV_PAIR="1")
     for case in ("conv_pair_check", "conv_pair_odd"):
         out = subprocess.run([exe, case], capture_output=True, text=True, timeout=300, env=env)
         assert out.returncode == 0 and "CTA-pair persistent kernel" in out.stdout and ("RESULT %s PASS" % case) in out.stdout, \
+            out.stdout[-2000:]
+    for case in ("wgrad_pair_small", "wgrad_pair_wide"):
+        out = subprocess.run([exe, case], capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0 and "(CTA-pair kernel)" in out.stdout and ("RESULT %s PASS" % case) in out.stdout, out.stdout[-2000:]
+    # and the single-CTA kernels the pair kernels replaced stay correct (SGGAN_CONV_PAIR=0 / SGGAN_WGRAD_PAIR=0)
+    env0 = dict(os.environ, SGGAN_CONV_PAIR="0", SGGAN_WGRAD_PAIR="0")
+    for case in ("conv_pair_check", "wgrad_pair_small"):
+        out = subprocess.run([exe, case], capture_output=True, text=True, timeout=300, env=env0)
+        assert out.returncode == 0 and "pair" not in out.stdout.replace(case, "") and ("RESULT %s PASS" % case) in out.stdout, \
             out.stdout[-2000:]
 
 
