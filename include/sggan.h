@@ -193,7 +193,10 @@ int sggan_seg_edge_weight(const float* seg, float* weight, int B, int H, int W, 
 /* gradloss_criterion (module.py:347-351): out = device float; d_in (may be null) = d out / d in */
 int sggan_gradloss(const float* in, const float* target, const float* weight, float* out, float* d_in, int B, int H,
                    int W, void* stream);
-/* Keras Adam apply (model.py:199-200): t = 1-based step index */
+/* tf_deriv (module.py:325-334): per-channel 3x3 Sobel x / y, x [B,H,W,C] -> out [B,Ho,Wo,2C] (channel c*2 + {x,y});
+ * valid = 0: 'SAME' zero padding (Ho = H), 1: 'VALID' (Ho = H - 2) */
+int sggan_tf_deriv(const float* x, float* out, int B, int H, int W, int C, int valid, void* stream);
+/* Keras Adam apply (model.py:199-200): t = 1-based step index; the four buffers 16-byte aligned */
 int sggan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t t, float lr, float beta1,
                     float beta2, float eps, void* stream);
 /* one_hot + nearest resample of a class-id map to the D logit grid (utils.py:158-165,190):

@@ -88,6 +88,7 @@ SYMBOLS = {
     "sggan_criterion": (_I, [_P, _P, _I64, _I, _P, _P]),
     "sggan_seg_edge_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "sggan_gradloss": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "sggan_tf_deriv": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "sggan_adam_step": (_I, [_P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _P]),
     "sggan_onehot_mask": (_I, [_P, _P] + [_I] * 6 + [_P]),
     "sggan_rgb_to_class": (_I, [_P, _P, _I64, _P]),

@@ -690,8 +690,19 @@ int sggan_gradloss(const float* in, const float* target, const float* weight, fl
   launch_gradloss(in, target, weight, B, H, W, 1.f, out, d_in, st);
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
+int sggan_tf_deriv(const float* x, float* out, int B, int H, int W, int C, int valid, void* stream) {
+  if (B < 1 || C < 1 || H < (valid ? 3 : 1) || W < (valid ? 3 : 1)) { g_err = "tf_deriv: empty output"; return SGGAN_E_INVALID; }
+  launch_sobel_deriv(x, B, H, W, C, valid ? 1 : 0, out, (cudaStream_t)stream);
+  return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
 int sggan_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int64_t t, float lr, float beta1,
                     float beta2, float eps, void* stream) {
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v)) & 15) {
+    g_err = "sggan_adam_step: p, g, m and v must be 16-byte aligned (128-bit accesses)";
+    return SGGAN_E_INVALID;
+  }
+  if (t < 1 || n < 0) { g_err = "sggan_adam_step: t is the 1-based step index"; return SGGAN_E_INVALID; }
   const float alpha_t = float(double(lr) * sqrt(1.0 - pow(double(beta2), double(t))) / (1.0 - pow(double(beta1), double(t))));
   launch_adam(p, g, m, v, n, alpha_t, beta1, beta2, eps, 1.f, (cudaStream_t)stream);
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;

@@ -587,64 +587,136 @@ void launch_seg_edge_weight(const float* seg, int B, int H, int W, float* weight
   seg_edge_weight_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(seg, B, H, W, weight);
 }
 
-// Sobel responses (x, y) of channel c at (i, j) with SAME zero padding (module.py:325-334).
-__device__ __forceinline__ void sobel_at(const float* img, int H, int W, int i, int j, int c, float* gx, float* gy) {
-  float v[3][3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      const int ii = i + a - 1, jj = j + q - 1;
-      v[a][q] = (ii >= 0 && ii < H && jj >= 0 && jj < W) ? img[(int64_t(ii) * W + jj) * 3 + c] : 0.f;
-    }
-  *gx = (v[0][2] - v[0][0]) + 2.f * (v[1][2] - v[1][0]) + (v[2][2] - v[2][0]);
-  *gy = (v[2][0] - v[0][0]) + 2.f * (v[2][1] - v[0][1]) + (v[2][2] - v[0][2]);
-}
+// ---- gradient-sensitive loss (module.py:325-351) as ONE shared-memory-tiled pass ------------------------------------
+// loss = mean_{b,i,j} w[i,j] * mean_{c, d in {x,y}} | |S_d in|[i,j,c] - |S_d tgt|[i,j,c] |, S = 3x3 Sobel with SAME zero
+// padding; d loss / d in[u,v,c] = sum over the 3x3 positions (i,j) whose window covers (u,v) of
+// w * sgn(e_d) * sgn(S_d in) * K_d[u-i+1][v-j+1].  A block owns a 16 x 64 tile of pixels:
+//   phase 1  `in` and `tgt` with a 2-pixel halo -> shared memory (coalesced rows, zeros outside the image);
+//   phase 2  both Sobel responses at every position of the tile + 1-pixel halo, out of shared memory: the loss terms of
+//            the tile's own positions and the six coefficients  w * sgn(e_d) * sgn(S_d in)  per position -> shared memory;
+//   phase 3  every pixel of the tile gathers its 9 x 2 x 3 coefficient taps and writes d_in.
+// Each input byte is read from HBM once (+ halo re-reads out of L2): (2 x 12 + 4) B read, 12 B written per pixel; the
+// naive form evaluated ~160 Sobel windows per pixel from global memory (233 us at 8 x 256 x 512; this one: profiles/).
+constexpr int kGlTh = 16, kGlTw = 64;
+constexpr int kGlIw = kGlTw + 4, kGlIh = kGlTh + 4;  // image tile with halo 2
+constexpr int kGlCw = kGlTw + 2, kGlCh = kGlTh + 2;  // coefficient tile with halo 1
 __device__ __forceinline__ float sgnf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
-
+__device__ __forceinline__ void sobel_smem(const float* t, int r, int q, int c, float* gx, float* gy) {
+  // t: [kGlIh][kGlIw][3], (r, q) = position in halo-2 coordinates of the window CENTRE
+  const float* p0 = t + ((r - 1) * kGlIw + (q - 1)) * 3 + c;
+  const float* p1 = p0 + kGlIw * 3;
+  const float* p2 = p1 + kGlIw * 3;
+  const float a00 = p0[0], a01 = p0[3], a02 = p0[6], a10 = p1[0], a12 = p1[6], a20 = p2[0], a21 = p2[3], a22 = p2[6];
+  *gx = (a02 - a00) + 2.f * (a12 - a10) + (a22 - a20);
+  *gy = (a20 - a00) + 2.f * (a21 - a01) + (a22 - a02);
+}
 __global__ void __launch_bounds__(256) gradloss_kernel(const float* __restrict__ in, const float* __restrict__ tgt,
                                                        const float* __restrict__ wgt, int B, int H, int W,
                                                        float scale, float* loss_slot, float* d_in) {
+  extern __shared__ float gl_smem[];
+  float* s_in = gl_smem;                          // [kGlIh][kGlIw][3]
+  float* s_tg = s_in + kGlIh * kGlIw * 3;
+  float* s_cf = s_tg + kGlIh * kGlIw * 3;         // [kGlCh][kGlCw][c][d]
   __shared__ float sh[32];
-  const int64_t tot = int64_t(B) * H * W;
-  const float inv = 1.f / (float(tot) * 6.f);
-  const float KX[3][3] = {{-1, 0, 1}, {-2, 0, 2}, {-1, 0, 1}};
-  const float KY[3][3] = {{-1, -2, -1}, {0, 0, 0}, {1, 2, 1}};
+  const int b = blockIdx.z, i0 = blockIdx.y * kGlTh, j0 = blockIdx.x * kGlTw;
+  const float* ib = in + int64_t(b) * H * W * 3;
+  const float* tb = tgt + int64_t(b) * H * W * 3;
+  const float* wb = wgt + int64_t(b) * H * W;
+  const float inv = 1.f / (float(int64_t(B) * H * W) * 6.f);
+  // ---- phase 1
+  for (int e = threadIdx.x; e < kGlIh * kGlIw * 3; e += 256) {
+    const int r = e / (kGlIw * 3), x = e - r * (kGlIw * 3);
+    const int i = i0 - 2 + r, j = j0 - 2 + x / 3;
+    const bool ok = i >= 0 && i < H && j >= 0 && j < W;
+    const int64_t g = (int64_t(i) * W + (j0 - 2)) * 3 + x;
+    s_in[e] = ok ? __ldg(ib + g) : 0.f;
+    s_tg[e] = ok ? __ldg(tb + g) : 0.f;
+  }
+  __syncthreads();
+  // ---- phase 2
   float lsum = 0.f;
-  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < tot; idx += int64_t(gridDim.x) * blockDim.x) {
-    const int b = int(idx / (int64_t(H) * W));
-    const int r = int(idx - int64_t(b) * H * W), u = r / W, v = r - u * W;
-    const float* ib = in + int64_t(b) * H * W * 3;
-    const float* tb = tgt + int64_t(b) * H * W * 3;
-    const float* wb = wgt + int64_t(b) * H * W;
-    float g[3] = {0.f, 0.f, 0.f};
-    for (int a = 0; a < 3; ++a)
-      for (int q = 0; q < 3; ++q) {
-        // output position (i, j) whose 3x3 window touches (u, v) through tap (a, q)
-        const int i = u - (a - 1), j = v - (q - 1);
-        if (i < 0 || i >= H || j < 0 || j >= W) continue;
-        const float w = wb[int64_t(i) * W + j];
-        for (int c = 0; c < 3; ++c) {
-          float gxi, gyi, gxt, gyt;
-          sobel_at(ib, H, W, i, j, c, &gxi, &gyi);
-          sobel_at(tb, H, W, i, j, c, &gxt, &gyt);
-          const float ex = fabsf(gxi) - fabsf(gxt), ey = fabsf(gyi) - fabsf(gyt);
-          if (a == 1 && q == 1) lsum += w * (fabsf(ex) + fabsf(ey));
-          if (w != 0.f) g[c] += w * (sgnf(ex) * sgnf(gxi) * KX[a][q] + sgnf(ey) * sgnf(gyi) * KY[a][q]);
+  for (int e = threadIdx.x; e < kGlCh * kGlCw; e += 256) {
+    const int r = e / kGlCw, q = e - r * kGlCw;
+    const int i = i0 - 1 + r, j = j0 - 1 + q;
+    const bool ok = i >= 0 && i < H && j >= 0 && j < W;
+    const float w = ok ? __ldg(wb + int64_t(i) * W + j) : 0.f;
+    const bool own = ok && r >= 1 && r <= kGlTh && q >= 1 && q <= kGlTw;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float gxi, gyi, gxt, gyt;
+      sobel_smem(s_in, r + 1, q + 1, c, &gxi, &gyi);
+      sobel_smem(s_tg, r + 1, q + 1, c, &gxt, &gyt);
+      const float ex = fabsf(gxi) - fabsf(gxt), ey = fabsf(gyi) - fabsf(gyt);
+      if (own) lsum += w * (fabsf(ex) + fabsf(ey));
+      s_cf[e * 6 + c * 2] = w * sgnf(ex) * sgnf(gxi);
+      s_cf[e * 6 + c * 2 + 1] = w * sgnf(ey) * sgnf(gyi);
+    }
+  }
+  __syncthreads();
+  // ---- phase 3
+  if (d_in != nullptr) {
+    const float KX[3][3] = {{-1, 0, 1}, {-2, 0, 2}, {-1, 0, 1}};
+    const float KY[3][3] = {{-1, -2, -1}, {0, 0, 0}, {1, 2, 1}};
+    for (int e = threadIdx.x; e < kGlTh * kGlTw * 3; e += 256) {
+      const int r = e / (kGlTw * 3), x = e - r * (kGlTw * 3), q = x / 3, c = x - q * 3;
+      const int u = i0 + r, v = j0 + q;
+      if (u >= H || v >= W) continue;
+      float g = 0.f;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          // window centre (i, j) = (u - (a - 1), v - (t - 1)) -> coefficient-tile coordinates (r + 1 - (a - 1), q + 1 - (t - 1))
+          const float* cf = s_cf + ((r + 2 - a) * kGlCw + (q + 2 - t)) * 6 + c * 2;
+          g += cf[0] * KX[a][t] + cf[1] * KY[a][t];
         }
-      }
-    if (d_in != nullptr)
-      for (int c = 0; c < 3; ++c) d_in[idx * 3 + c] = g[c] * inv * scale;
+      d_in[(int64_t(b) * H * W + int64_t(u) * W + j0) * 3 + x] = g * inv * scale;
+    }
   }
   lsum = block_sum(lsum, sh);
   if (threadIdx.x == 0 && loss_slot != nullptr) atomicAdd(loss_slot, lsum * inv);
 }
 void launch_gradloss(const float* in, const float* target, const float* weight, int B, int H, int W, float scale,
                      float* loss_slot, float* d_in, cudaStream_t st) {
-  const int64_t tot = int64_t(B) * H * W;
+  dim3 grid((W + kGlTw - 1) / kGlTw, (H + kGlTh - 1) / kGlTh, B);
+  constexpr size_t smem = size_t(2 * kGlIh * kGlIw * 3 + kGlCh * kGlCw * 6) * sizeof(float);  // 61 KB: three blocks per SM
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gradloss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    attr_set = true;
+  }
+  gradloss_kernel<<<grid, 256, smem, st>>>(in, target, weight, B, H, W, scale, loss_slot, d_in);
+}
+
+// module.tf_deriv (module.py:325-334) as a standalone operator: Sobel x / y per channel, SAME zero padding or VALID;
+// out[b, i, j, c * 2 + d].  Any channel count; one thread per output (pixel, channel), rows read coalesced.
+__global__ void __launch_bounds__(256) sobel_deriv_kernel(const float* __restrict__ x, int B, int H, int W, int C, int valid,
+                                                          float* __restrict__ out) {
+  const int Ho = valid ? H - 2 : H, Wo = valid ? W - 2 : W;
+  const int64_t tot = int64_t(B) * Ho * Wo * C;
+  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < tot; idx += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(idx % C);
+    const int64_t pix = idx / C;
+    const int j = int(pix % Wo), i = int((pix / Wo) % Ho), b = int(pix / (int64_t(Wo) * Ho));
+    const float* xb = x + int64_t(b) * H * W * C + c;
+    float v[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int ii = i + a - (valid ? 0 : 1), jj = j + q - (valid ? 0 : 1);
+        v[a][q] = (ii >= 0 && ii < H && jj >= 0 && jj < W) ? __ldg(xb + (int64_t(ii) * W + jj) * C) : 0.f;
+      }
+    out[idx * 2] = (v[0][2] - v[0][0]) + 2.f * (v[1][2] - v[1][0]) + (v[2][2] - v[2][0]);
+    out[idx * 2 + 1] = (v[2][0] - v[0][0]) + 2.f * (v[2][1] - v[0][1]) + (v[2][2] - v[0][2]);
+  }
+}
+void launch_sobel_deriv(const float* x, int B, int H, int W, int C, int valid, float* out, cudaStream_t st) {
+  const int64_t tot = int64_t(B) * (valid ? H - 2 : H) * (valid ? W - 2 : W) * C;
   int blocks = int((tot + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gradloss_kernel<<<blocks, 256, 0, st>>>(in, target, weight, B, H, W, scale, loss_slot, d_in);
+  if (blocks < 1) blocks = 1;
+  sobel_deriv_kernel<<<blocks, 256, 0, st>>>(x, B, H, W, C, valid, out);
 }
 
 __global__ void __launch_bounds__(256) criterion_kernel(const float* __restrict__ a, const float* __restrict__ b,

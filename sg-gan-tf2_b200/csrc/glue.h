@@ -87,6 +87,8 @@ void launch_gradloss(const float* in, const float* target, const float* weight, 
                      float scale, float* loss_slot, float* d_in, cudaStream_t st);
 // Plain criteria (module.py:336-345) as reductions: mode 0 abs, 1 squared, 2 sigmoid-CE(logits=a, labels=b)
 void launch_criterion(const float* a, const float* b, int64_t n, int mode, float* out, cudaStream_t st);
+// module.tf_deriv: Sobel x / y per channel, out [B][Ho][Wo][C * 2]; valid = 0: SAME zero padding, 1: VALID
+void launch_sobel_deriv(const float* x, int B, int H, int W, int C, int valid, float* out, cudaStream_t st);
 
 // Keras Adam (Appendix A.8) over a flat fp32 buffer; g is scaled by gscale first.
 // step_dev != null: alpha_t is computed on the device from *step_dev (completed steps) and lr instead of being passed in.

@@ -272,18 +272,17 @@ def tf_kernel_prep_3d(kernel, n_channels):
 
 
 def tf_deriv(batch, ksize=3, padding="SAME"):
-    """Sobel x / y per channel (module.py:325-334); returned as (B,H,W,2*C), channel = c*2 + {x,y}.
-    Only the fused gradloss kernel uses it on the hot path; this standalone form is plain torch glue on
-    the device and exists for API completeness."""
+    """Sobel x / y per channel (module.py:325-334); returned as (B,H,W,2*C), channel = c*2 + {x,y} (depthwise_conv2d's
+    channel order).  libsggan's sobel_deriv_kernel; the training step uses the fused gradloss kernel instead."""
+    import ctypes as C
     x = L.as_cuda_f32(batch)
-    n_ch = x.shape[3]
-    gx = torch.tensor([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], dtype=torch.float32, device=x.device)
-    gy = torch.tensor([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], dtype=torch.float32, device=x.device)
-    w = torch.stack([gx, gy]).repeat(n_ch, 1, 1).unsqueeze(1)
-    xi = x.permute(0, 3, 1, 2)
-    if padding == "SAME":
-        xi = torch.nn.functional.pad(xi, (1, 1, 1, 1))
-    return torch.nn.functional.conv2d(xi, w, groups=n_ch).permute(0, 2, 3, 1).contiguous()
+    if ksize != 3 or padding.upper() not in ("SAME", "VALID"):
+        raise L.SgganError("tf_deriv: ksize 3, padding SAME or VALID (the reference's kernel is hard-coded 3x3)")
+    B, H, W, n_ch = x.shape
+    valid = padding.upper() == "VALID"
+    out = torch.empty((B, H - 2 * valid, W - 2 * valid, 2 * n_ch), dtype=torch.float32, device=x.device)
+    L.check(L.lib().sggan_tf_deriv(C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), B, H, W, n_ch, int(valid), L.stream_ptr()))
+    return out
 
 
 def _criterion(a, b, mode):

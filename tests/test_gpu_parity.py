@@ -197,8 +197,27 @@ def test_seg_edge_weight_and_gradloss(L, mod, O):
     ref = O.gradloss_criterion(a, t, wref)
     (gref,) = torch.autograd.grad(ref, a)
     val, grad = mod.gradloss_criterion(a.detach(), t, wref, return_grad=True)
-    assert abs(float(val) - float(ref)) < 1e-5 * (1 + abs(float(ref)))
+    assert abs(float(val) - float(ref.detach())) < 1e-5 * (1 + abs(float(ref.detach())))
     assert rel(grad, gref) < 1e-4
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 37, 150), (2, 16, 64), (1, 3, 5), (1, 64, 129)])
+def test_gradloss_tiles(mod, O, B, H, W):
+    """The shared-memory-tiled gradient-sensitive loss across tile borders (16 x 64 tiles, ragged edges, an image smaller
+    than a tile): value and gradient against autograd of the oracle; arbitrary (non-binary) weights."""
+    g = torch.Generator().manual_seed(H * W)
+    a = torch.rand(B, H, W, 3, generator=g).requires_grad_(True)
+    t = torch.rand(B, H, W, 3, generator=g)
+    w = torch.rand(B, H, W, 1, generator=g) * (torch.rand(B, H, W, 1, generator=g) > 0.3)
+    ref = O.gradloss_criterion(a, t, w)
+    (gref,) = torch.autograd.grad(ref, a)
+    val, grad = mod.gradloss_criterion(a.detach(), t, w, return_grad=True)
+    assert abs(float(val) - float(ref.detach())) < 1e-5 * (1 + abs(float(ref.detach())))
+    assert rel(grad, gref) < 1e-4
+    x = torch.rand(B, H, W, 5, generator=g)
+    assert rel(mod.tf_deriv(x), O.tf_deriv(x)) < 1e-6                       # any channel count
+    if H >= 3 and W >= 3:
+        assert rel(mod.tf_deriv(x, padding="VALID"), O.tf_deriv(x, padding="VALID")) < 1e-6
 
 
 def test_adam_step(L, O):
