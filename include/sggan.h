@@ -220,6 +220,10 @@ int sggan_rgb_argmax_labels(const float* img, int32_t* labels, int B, int H, int
 int sggan_fast_hist(const int32_t* label_true, const int32_t* label_pred, int64_t n, int n_class, int64_t* hist,
                     void* stream);
 
+/* ---- host helper: CRC-32C (Castagnoli) as used by the TF checkpoint format the reference saves (model.py:463-466);
+ * crc = value to extend, 0 to start.  Runs on the CPU, touches no device. */
+uint32_t sggan_crc32c(const void* data, size_t n, uint32_t crc);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,7 @@ SYMBOLS = {
     "sggan_seg_edge_weight": (_I, [_P, _P, _I, _I, _I, _P]),
     "sggan_gradloss": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "sggan_tf_deriv": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "sggan_crc32c": (C.c_uint32, [_P, _SZ, C.c_uint32]),
     "sggan_adam_step": (_I, [_P, _P, _P, _P, _I64, _I64, _F, _F, _F, _F, _P]),
     "sggan_onehot_mask": (_I, [_P, _P] + [_I] * 6 + [_P]),
     "sggan_rgb_to_class": (_I, [_P, _P, _I64, _P]),

@@ -3,6 +3,7 @@
 // HBM-bound byte / integer work: coalesced reads, a shared-memory histogram per block, 64-bit global counters.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/sggan.h"
 
@@ -62,4 +63,35 @@ extern "C" int sggan_fast_hist(const int32_t* label_true, const int32_t* label_p
   sggan::fast_hist_kernel<<<blocks, 256, size_t(n_class) * n_class * sizeof(unsigned int), (cudaStream_t)stream>>>(
       label_true, label_pred, n, n_class, reinterpret_cast<unsigned long long*>(hist));
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
+}
+
+// Host helper of the checkpoint reader / writer (tf_checkpoint.py): CRC-32C (Castagnoli, reflected 0x82F63B78) as the TF
+// tensor-bundle format uses it for every table block and every tensor.  crc = value to extend (0 to start).
+extern "C" uint32_t sggan_crc32c(const void* data, size_t n, uint32_t crc) {
+  static uint32_t table[8][256];
+  static bool ready = false;
+  if (!ready) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xFF];
+    ready = true;
+  }
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = ~crc;
+  while (n >= 8) {  // slicing-by-8
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = table[7][lo & 0xFF] ^ table[6][(lo >> 8) & 0xFF] ^ table[5][(lo >> 16) & 0xFF] ^ table[4][lo >> 24] ^
+        table[3][hi & 0xFF] ^ table[2][(hi >> 8) & 0xFF] ^ table[1][(hi >> 16) & 0xFF] ^ table[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = table[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  return ~c;
 }

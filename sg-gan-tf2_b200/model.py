@@ -272,20 +272,27 @@ class sggan(object):
             if getattr(args, "checkpoint_dir", None):
                 self.save(args.checkpoint_dir, epoch)
 
-    def save(self, checkpoint_dir, ep):
-        """model.py:450-468 (same directory layout; .npz instead of TF checkpoints)."""
+    def save(self, checkpoint_dir, ep, optimizer=True):
+        """model.py:450-468: `<dir>/<dataset>/gen/cp-NNNN.ckpt` and `…/disc/cp-NNNN.ckpt` as TF checkpoints (the format
+        Keras' save_weights writes there, tf_checkpoint.py); plus, unlike the reference, the Adam state beside them."""
         path = "%s/%s" % (checkpoint_dir, self.dataset_dir)
         for sub in ("gen", "disc"):
             os.makedirs(os.path.join(path, sub), exist_ok=True)
-        self.generator.save_weights(os.path.join(path, "gen/cp-%04d.ckpt" % ep))
-        self.discriminator.save_weights(os.path.join(path, "disc/cp-%04d.ckpt" % ep))
+        opt = optimizer and self.runtime is not None
+        self.generator.save_weights(os.path.join(path, "gen/cp-%04d.ckpt" % ep), optimizer=opt)
+        self.discriminator.save_weights(os.path.join(path, "disc/cp-%04d.ckpt" % ep), optimizer=opt)
 
     def load(self, checkpoint_dir):
-        """model.py:471-503: latest checkpoint of both nets, False if either is missing."""
+        """model.py:471-503: the latest checkpoint of both nets (tf.train.latest_checkpoint = the directory's `checkpoint`
+        state file; .npz files of earlier versions of this package are still found), False if either is missing."""
+        from . import tf_checkpoint
         path = "%s/%s" % (checkpoint_dir, self.dataset_dir)
 
         def latest(sub):
             d = os.path.join(path, sub)
+            p = tf_checkpoint.latest_checkpoint(d) if os.path.isdir(d) else None
+            if p:
+                return p
             fs = sorted(f for f in os.listdir(d) if f.endswith(".ckpt.npz")) if os.path.isdir(d) else []
             return os.path.join(d, fs[-1]) if fs else None
 

@@ -12,6 +12,7 @@ shape it is called with.
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 import torch
@@ -91,6 +92,7 @@ class _Net:
         self.runtime = runtime
         runtime.bound[self.net_id] = self
         eng.weights_changed()
+        self._restore_optimizer()
 
     def _infer_runtime(self, key_kw, batch, height, width):
         """A runtime for an off-plan forward call (e.g. sampling one image in the middle of training,
@@ -117,14 +119,50 @@ class _Net:
         if self.runtime is not None:
             self.runtime.engine.weights_changed()
 
-    # Keras' Model.save_weights / load_weights write TF checkpoints (model.py:463-466,499-500); here the
-    # same variable list goes to an .npz.
-    def save_weights(self, path):
-        np.savez(path if path.endswith(".npz") else path + ".npz", *self.get_weights())
+    # Keras' Model.save_weights / load_weights (model.py:463-466,499-500): a path without an .npz / .h5 suffix is a TF
+    # checkpoint prefix -> `<path>.index` + `<path>.data-00000-of-00001` + the directory's `checkpoint` state file, in
+    # the tensor-bundle format with Keras' object-graph variable names (tf_checkpoint.py); `.npz` keeps the plain list.
+    def layer_kinds(self):
+        raise NotImplementedError
+
+    def save_weights(self, path, optimizer=False):
+        """optimizer=True also writes `<path>.opt.npz` with this network's Adam slots and the step count (the reference
+        saves weights only, so a resumed run there restarts Adam; here the state can travel)."""
+        if path.endswith(".npz"):
+            np.savez(path, *self.get_weights())
+        else:
+            from . import tf_checkpoint
+            tf_checkpoint.save(path, self.get_weights(), self.layer_kinds())
+        if optimizer:
+            if self.runtime is None:
+                raise L.SgganError("save_weights(optimizer=True): the network has not been planned yet (no Adam state)")
+            eng = self.runtime.engine
+            np.savez(path + ".opt.npz", m=eng.flat(self.net_id, 2).cpu().numpy(), v=eng.flat(self.net_id, 3).cpu().numpy(),
+                     step=np.int64(L.lib().sggan_step_count(eng.h)))
 
     def load_weights(self, path):
-        z = np.load(path if path.endswith(".npz") else path + ".npz")
-        self.set_weights([z["arr_%d" % i] for i in range(len(z.files))])
+        if path.endswith(".npz") or (not os.path.exists(path + ".index") and os.path.exists(path + ".npz")):
+            z = np.load(path if path.endswith(".npz") else path + ".npz")
+            self.set_weights([z["arr_%d" % i] for i in range(len(z.files))])
+        else:
+            from . import tf_checkpoint
+            self.set_weights(tf_checkpoint.load(path, self.layer_kinds()))
+        self._pending_opt = path + ".opt.npz" if os.path.exists(path + ".opt.npz") else None
+        self._restore_optimizer()
+
+    def _restore_optimizer(self):
+        """Adam slots + step count from the sidecar of the last load_weights, as soon as an engine owns the weights."""
+        p = getattr(self, "_pending_opt", None)
+        if p is None or self.runtime is None:
+            return
+        z = np.load(p)
+        eng = self.runtime.engine
+        if z["m"].size != eng.flat(self.net_id, 2).numel():
+            raise L.SgganError("optimizer state %s does not match this network" % p)
+        eng.flat(self.net_id, 2).copy_(torch.as_tensor(z["m"]))
+        eng.flat(self.net_id, 3).copy_(torch.as_tensor(z["v"]))
+        L.check(L.lib().sggan_set_step_count(eng.h, int(z["step"])))
+        self._pending_opt = None
 
 
 class GeneratorResnet(_Net):
@@ -154,6 +192,9 @@ class GeneratorResnet(_Net):
                 i += 2
         self.n_blocks = n_blocks
         self.input_hw = (image_height, image_width)
+
+    def layer_kinds(self):
+        return ["conv", "norm"] * 3 + ["conv", "norm", "conv", "norm"] * self.n_blocks + ["deconv", "norm"] * 2 + ["conv"]
 
     def forward_fp32(self, x, precision="tf32x3"):
         """The same network on the fp32-storage operator tier (ops.conv2d_raw / deconv2d_raw / instance_norm_raw with
@@ -219,6 +260,9 @@ class Discriminator(_Net):
             self._vars[i + 3] = torch.zeros(shapes[i + 3])
         self._vars[-1] = torch.zeros(shapes[-1])
         self.segment_class = segment_class
+
+    def layer_kinds(self):
+        return ["conv"] + ["conv", "norm"] * 6 + ["conv"]
 
     def __call__(self, inputs):
         x, mask = inputs

@@ -444,11 +444,29 @@ def test_model_api(L, O, tmp_path):
     gw = [v.clone().cpu() for v in m.generator.trainable_variables]
     out = m.generate_test_images(real_A.numpy())
     assert rel(out, O.generator_resnet(real_A, gw)) < 3e-2
+    m.train_step(ns)
+    gw = [v.clone().cpu() for v in m.generator.trainable_variables]
     m.save(str(tmp_path), 3)
+    # the reference's layout and format (model.py:450-468): TF checkpoints + the directory's `checkpoint` state file
+    assert sorted(os.listdir(tmp_path / "city" / "gen")) == ["checkpoint", "cp-0003.ckpt.data-00000-of-00001", "cp-0003.ckpt.index",
+                                                             "cp-0003.ckpt.opt.npz"]
     m2 = M.sggan(ns)
     assert m2.load(str(tmp_path))
     for a, b in zip(m2.generator.trainable_variables, gw):
         assert torch.equal(a.cpu(), b)
+    # resume: the Adam slots and the step count come back with the weights, so the next step of the restored model is the
+    # next step of the original one (same batch, same state -> same update up to the backward's atomic-add noise)
+    m2.real_A, m2.seg_A, m2.mask_A = m.real_A, m.seg_A, m.mask_A
+    before = {net: m.runtime.engine.flat(net, 0).clone() for net in (L.NET_G, L.NET_D)}
+    m2.train_step(ns)
+    m.train_step(ns)
+    e1, e2 = m.runtime.engine, m2.runtime.engine
+    assert L.lib().sggan_step_count(e2.h) == L.lib().sggan_step_count(e1.h) == 3
+    for net in (L.NET_G, L.NET_D):
+        upd = rel(e1.flat(net, 0), before[net])                             # size of one step
+        assert upd > 1e-3
+        assert rel(e2.flat(net, 3), e1.flat(net, 3)) < 1e-3                 # Adam v continued, not restarted from zero
+        assert rel(e2.flat(net, 0), e1.flat(net, 0)) < 0.2 * upd, (net, upd)
     d = m.discriminator([seg_A, mask])
     assert tuple(d.shape) == (1, 1, 5, 1)
     assert abs(float(m.disc_loss_p2p(d, -d)) - float(O.disc_loss_p2p(d.cpu(), -d.cpu()))) < 1e-5
