@@ -116,3 +116,34 @@ def rgb_to_class(img_rgb):
     out = torch.empty(rgb.shape[:-1], dtype=torch.uint8, device=rgb.device)
     L.check(L.lib().sggan_rgb_to_class(C.c_void_p(rgb.data_ptr()), C.c_void_p(out.data_ptr()), out.numel(), L.stream_ptr()))
     return out
+
+
+class ImagePool(object):
+    """utils.py:27-53: the history buffer of generated images, same call contract and the same use of numpy's global
+    random state (np.random.rand twice per swap, so a seeded run replays the reference's choices).
+
+    `image` is the 4-element list the reference passes; elements may be numpy arrays or CUDA tensors -- swapped-out
+    entries are returned as they were stored, nothing is copied to the host.  The reference's trainer never calls the pool
+    on the path that runs (model.py:169-200 feeds the fresh fake_A); it exists for callers that do."""
+
+    def __init__(self, maxsize=50):
+        self.maxsize = maxsize
+        self.num_img = 0
+        self.images = []
+
+    def __call__(self, image):
+        if self.maxsize <= 0:
+            return image
+        if self.num_img < self.maxsize:
+            self.images.append(image)
+            self.num_img += 1
+            return image
+        if np.random.rand() > 0.5:
+            idx = int(np.random.rand() * self.maxsize)
+            tmp1, tmp3 = self.images[idx][0], self.images[idx][2]
+            self.images[idx][0], self.images[idx][2] = image[0], image[2]
+            idx = int(np.random.rand() * self.maxsize)
+            tmp2, tmp4 = self.images[idx][1], self.images[idx][3]
+            self.images[idx][1], self.images[idx][3] = image[1], image[3]
+            return [tmp1, tmp2, tmp3, tmp4]
+        return image

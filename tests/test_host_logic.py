@@ -7,6 +7,8 @@ import importlib
 import os
 import re
 
+import numpy as np
+
 import pytest
 import torch
 
@@ -121,3 +123,32 @@ def test_bench_reference_arm_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["unit"] == "img/s"
+
+
+def test_image_pool_follows_the_reference_contract():
+    """utils.py:27-53: fills up to maxsize returning its input, then swaps elements 0/2 and 1/3 of two random slots half
+    of the time; driven by numpy's global random state like the reference, so a seeded run is reproducible."""
+    import importlib
+    U = importlib.import_module("sg-gan-tf2_b200.utils")
+    pool = U.ImagePool(maxsize=3)
+    items = [[("a", i), ("b", i), ("c", i), ("d", i)] for i in range(8)]
+    for i in range(3):
+        assert pool(items[i]) is items[i] and pool.num_img == i + 1
+    np.random.seed(4)
+    outs = [pool(list(items[i])) for i in range(3, 8)]
+    np.random.seed(4)
+    # replay the reference's decisions with the same random draws
+    mirror = [[("a", i), ("b", i), ("c", i), ("d", i)] for i in range(3)]
+    for i, got in zip(range(3, 8), outs):
+        img = items[i]
+        if np.random.rand() > 0.5:
+            j = int(np.random.rand() * 3)
+            t1, t3 = mirror[j][0], mirror[j][2]
+            mirror[j][0], mirror[j][2] = img[0], img[2]
+            j = int(np.random.rand() * 3)
+            t2, t4 = mirror[j][1], mirror[j][3]
+            mirror[j][1], mirror[j][3] = img[1], img[3]
+            assert got == [t1, t2, t3, t4]
+        else:
+            assert got == img
+    assert U.ImagePool(0)(items[0]) is items[0]
