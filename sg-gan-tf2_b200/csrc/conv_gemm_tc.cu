@@ -475,9 +475,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // Barriers: a_full / b_full live in the leader CTA (rank 0) and count the TMA bytes of BOTH CTAs;
 // a_empty / b_empty / acc_full exist in both CTAs and are signalled by multicast tcgen05.commit;
 // acc_empty lives in the leader and collects one arrival per epilogue warp of both CTAs.
-constexpr int kPairEpiTile = 32 * 33 * 4;                       // one warp's transposition tile
-constexpr int kPairEpiBytes = kEpiWarps * kPairEpiTile + 2 * 4 * 256 * 8;  // + red[2][4][256] float2
-constexpr int kPairAStages = 3, kPairBStages = 7;
+constexpr int kPairEpiTile = 32 * 33 * 4;                       // one warp's transposition tile (fallback epilogue)
+// staged epilogue: the 128 x 256 bf16 tile row-major (pitch + 16 B: conflict-free 16-byte row writes), then 4 KB of partial
+// column sums and 1 KB of output offsets; the fallback epilogue (fp32 output / partial channel tile) fits inside
+constexpr int kPairStagePitch = 256 * 2 + 16;
+constexpr int kPairEpiBytes = kTileM * kPairStagePitch + 4096 + 1024;
+static_assert(kPairEpiBytes >= kEpiWarps * kPairEpiTile + 2 * 4 * 256 * 8, "fallback epilogue scratch");
+constexpr int kPairAStages = 3, kPairBStages = 6;
 constexpr int kPairAStage = (kTileM + kHaloRows) * 128, kPairBStage = 128 * 128;
 constexpr int kPairSmem = kPairAStages * kPairAStage + kPairBStages * kPairBStage + kPairEpiBytes + 1024;
 
@@ -611,6 +615,14 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const float alpha = p.act_alpha;
     const bool vec_ok = (!p.out_f32) && ((p.omap.C & 7) == 0);
     const uint32_t empty_addr0 = mapa_u32(smem_u32(&acc_empty[0]), 0), empty_addr1 = mapa_u32(smem_u32(&acc_empty[1]), 0);
+    // staged epilogue (bf16 output, all 256 channels): the tile goes row-major into shared memory, every valid output
+    // position then leaves as ONE 512-byte bulk async copy and the statistics are column sums of the staged bf16 values
+    // (as in the single-CTA kernel).  ~5k cycles per tile instead of ~12k with per-thread global stores and the fp32
+    // transposition tiles: what matters is the LAST tile of a CTA, whose epilogue no MMA hides.
+    const bool staged = !p.out_f32 && (p.omap.C & 7) == 0 && p.Cout == 256;
+    uint8_t* S = reinterpret_cast<uint8_t*>(epi);
+    float2* comb = reinterpret_cast<float2*>(S + kTileM * kPairStagePitch);               // [2][256]
+    long long* rowoff = reinterpret_cast<long long*>(S + kTileM * kPairStagePitch + 4096);  // [128]
     int k = 0;
     for (int j = cl; j < npairs; j += ncl, ++k) {
       const int buf = k & 1;
@@ -626,6 +638,60 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const float msk = valid ? 1.f : 0.f;
       mbar_wait(&acc_full[buf], (k >> 1) & 1, 3);
       tc_fence_after();
+      if (staged) {
+        // the previous tile's bulk copies have finished READING the staging tile (issued by the half == 0 threads)
+        bulk_wait_group_read0();
+        named_bar_sync(1, kEpiThreads);
+        for (int c0 = half * 32; c0 < 256; c0 += 32 * (kEpiWarps / 4)) {
+          float v[32];
+          tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(buf * 256 + c0), v);
+          const float4* sb4 = reinterpret_cast<const float4*>(sbias + c0);
+#pragma unroll
+          for (int g4 = 0; g4 < 8; ++g4) {
+            const float4 bb = sb4[g4];
+            v[4 * g4] += bb.x; v[4 * g4 + 1] += bb.y; v[4 * g4 + 2] += bb.z; v[4 * g4 + 3] += bb.w;
+          }
+          if (act == SG_ACT_RELU) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], 0.f);
+          } else if (act == SG_ACT_LRELU) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = fmaxf(v[e], alpha * v[e]);
+          } else if (act == SG_ACT_TANH) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = tanhf(v[e]);
+          }
+          uint4* srow = reinterpret_cast<uint4*>(S + row * kPairStagePitch + c0 * 2);
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            uint4 w;
+            w.x = valid ? pack_bf16x2(v[8 * g4], v[8 * g4 + 1]) : 0u;  // rows outside the image count as zeros
+            w.y = valid ? pack_bf16x2(v[8 * g4 + 2], v[8 * g4 + 3]) : 0u;
+            w.z = valid ? pack_bf16x2(v[8 * g4 + 4], v[8 * g4 + 5]) : 0u;
+            w.w = valid ? pack_bf16x2(v[8 * g4 + 6], v[8 * g4 + 7]) : 0u;
+            srow[g4] = w;
+          }
+        }
+        // this warp's share of the accumulator has been read: hand it back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0);
+        if (half == 0) rowoff[row] = valid ? obase : -1;
+        fence_proxy_async_smem();  // the bulk copies (async proxy) read what this thread just wrote
+        named_bar_sync(1, kEpiThreads);
+        if (half == 0) {
+          const long long off = rowoff[row];
+          if (off >= 0) {
+            bulk_store_1d(reinterpret_cast<__nv_bfloat16*>(p.out) + off, S + row * kPairStagePitch, 512u);
+            bulk_commit_group();
+          }
+        }
+        if (has_stats && tile_ok)  // tile_ok is uniform over the CTA
+          staged_stats(S, kPairStagePitch, 256, kEpiThreads, et, comb, 2,
+                       reinterpret_cast<float2*>(p.stats) + (int64_t(b) * p.stats_T + p.stats_t0 + t128) * p.Cout);
+        if (dbg && et == 0 && k < 6) dbg[8 + k] = clock64();
+        continue;
+      }
       for (int c0 = half * 32; c0 < 256; c0 += 32 * (kEpiWarps / 4)) {
         float v[32];
         tmem_ld32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(buf * 256 + c0), v);
@@ -702,6 +768,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
       if (dbg && et == 0 && k < 6) dbg[8 + k] = clock64();
     }
+    if (staged) bulk_wait_group_read0();  // shared memory must outlive the reads of the last tile's copies
   }
   tc_fence_before();
   __syncthreads();
