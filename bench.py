@@ -356,7 +356,7 @@ def main():
                      "frac": (achieved / peak_tf) if achieved else None,
                      "frac_of_burst_peak": (achieved / peak_burst) if achieved else None, "peak_burst": peak_burst,
                      "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
-                     "kernel": "conv_gemm_tc_kernel, residual-block 3x3 256->256 forward (%d launches timed with CUDA events "
+                     "kernel": "conv_gemm_pair_kernel (cta_group::2), residual-block 3x3 256->256 forward (%d launches timed with CUDA events "
                                "in a separate pass after the timed region; algorithmic %.2f GFLOP per launch)" % (conv_n, conv_flops / 1e9),
                      "peak_source": "bf16_tflops_sustained / bf16_tflops of " + src},
         "roofline_hbm": [x for x in (hbm_obj(1, "row_stream_kernel<APPLY>: instance norm + ReLU + reflect-pad frame behind the first "
