@@ -281,9 +281,8 @@ def test_generator_forward_layerwise(L, O):
             assert rel(eng.debug_buffer(L.NET_G, li + 1, 0), taps[nm]) < 3e-2, nm
     assert rel(eng.debug_buffer(L.NET_G, 1, 0), taps["c1"]) < 1e-2  # one layer deep: single-op accuracy
     assert rel(fake, ref) < 3e-2 and float(fake.abs().max()) <= 1.0
-    # instance-norm statistics are accumulated with fp32 atomics (order varies at the 1e-7 level), so two
-    # runs agree to bf16 rounding noise, not bit for bit
-    assert rel(eng.gen_forward(real_A), fake) < 1e-2
+    # the forward pass is bit-reproducible: per-tile statistics partials are added in a fixed order (no atomics)
+    assert torch.equal(eng.gen_forward(real_A), fake)
 
 
 def test_discriminator_forward_layerwise(L, O):
