@@ -267,7 +267,7 @@ def main():
     #      residual-block convolution (tensor roofline) and the two instance-norm passes around it (HBM roofline)
     prof = {}
     if not infer:
-        for kind in (0, 1, 2):
+        for kind in (0, 1, 2, 3):
             eng.profile_begin(18 * max(4, min(args.steps, 10)) + 8, kind=kind)
             for _ in range(max(4, min(args.steps, 10))):
                 step()
@@ -373,7 +373,11 @@ def main():
                                                  "conv of each residual block, read Y + write X"),
                                      hbm_obj(2, "row_stream_kernel<BWD_REDUCE> + <BWD_APPLY>: instance-norm backward of the same layers (two "
                                                 "launches timed together, side stream joined first); algorithmic = read Y + read dX + "
-                                                "write dY, the reduce pass re-reads Y and dX on top of that")) if x],
+                                                "write dY, the reduce pass re-reads Y and dX on top of that"),
+                                     hbm_obj(3, "loss kernels of the generator side, one group per step: " +
+                                             ("seg_edge_weight + gradloss (tiled Sobel loss and its gradient) + " if args.loss_mode == "sggan" else "") +
+                                             "fake_grad (L1 sign + GAN gradient, tanh') + finalize_losses; algorithmic = every input "
+                                             "read once, every output written once")) if x],
         "sustained": sustained,
     }
     if not args.no_cpu_baseline and world == 1 and not infer:

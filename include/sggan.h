@@ -126,7 +126,9 @@ const float* sggan_last_fake(const sggan_handle* h);
 int sggan_profile_begin(sggan_handle* h, int max_launches);
 /* Which launches sggan_profile_begin/end bracket (default 0): 0 = the residual-block 3x3 convolutions (forward; work =
  * FLOPs), 1 = the instance-norm + ReLU apply pass behind the first convolution of every block (work = algorithmic bytes:
- * read Y, write the next frame), 2 = the instance-norm backward of the same layers (read Y and dX, write dY). */
+ * read Y, write the next frame), 2 = the instance-norm backward of the same layers (read Y and dX, write dY), 3 = the
+ * generator-side loss kernels as one group per step (seg-edge weights and the gradient-sensitive loss in SG-GAN mode, the
+ * L1 / GAN gradient seed, the loss finalize; work = every input read once, every output written once). */
 int sggan_profile_select(sggan_handle* h, int kind);
 int sggan_profile_end(sggan_handle* h, double* total_ms, int* launches, double* flops_per_launch);
 

@@ -331,8 +331,8 @@ class Engine:
         return self.workspace[off:off + 4 * n].view(torch.float32).view(c.batch, c.image_height, c.image_width, 3)
 
     def profile_begin(self, max_launches=8192, kind=0):
-        """kind 0: residual-block convolutions (work = FLOPs); 1: their norm-apply passes; 2: their norm backward
-        (work = algorithmic bytes)."""
+        """kind 0: residual-block convolutions (work = FLOPs); 1: their norm-apply passes; 2: their norm backward; 3: the
+        generator-side loss kernels, one group per step (work = algorithmic bytes)."""
         check(lib().sggan_profile_select(self.h, kind))
         check(lib().sggan_profile_begin(self.h, max_launches))
         self._profiling = True  # the events are recorded by eager launches: no graph replay while profiling

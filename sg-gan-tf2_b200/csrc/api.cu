@@ -297,7 +297,7 @@ int sggan_profile_begin(sggan_handle* h, int max_launches) {
   return 0;
 }
 int sggan_profile_select(sggan_handle* h, int kind) {
-  if (kind < 0 || kind > 2) { g_err = "profile kind must be 0, 1 or 2"; return SGGAN_E_INVALID; }
+  if (kind < 0 || kind > 3) { g_err = "profile kind must be 0 .. 3"; return SGGAN_E_INVALID; }
   h->e.prof_kind = kind;
   return 0;
 }
@@ -318,7 +318,15 @@ int sggan_profile_end(sggan_handle* h, double* total_ms, int* launches, double* 
     const double tensor_bytes = 2.0 * l.nb * l.Hout * l.Wout * double(l.Cout);  // one bf16 activation tensor of the layer
     if (e.prof_kind == 0) *flops_per_launch = 2.0 * l.nb * l.Hout * l.Wout * double(l.Cout) * l.Cin * l.k * l.k;
     else if (e.prof_kind == 1) *flops_per_launch = 2.0 * tensor_bytes;  // read Y, write the next frame
-    else *flops_per_launch = 3.0 * tensor_bytes;                        // read Y and dX, write dY
+    else if (e.prof_kind == 2) *flops_per_launch = 3.0 * tensor_bytes;  // read Y and dX, write dY
+    else {
+      // loss group, bytes per pixel: fake_grad reads fake, target and dD (3 x 12 B) and writes the 8-channel bf16 seed
+      // frame (16 B); SG-GAN mode adds seg_edge_weight (12 B read, 4 B written), gradloss (2 x 12 + 4 B read, 12 B
+      // written) and fake_grad's read of that gradient (12 B)
+      const double px = double(e.cfg.batch) * e.cfg.image_height * e.cfg.image_width;
+      const bool sg = e.cfg.loss_mode == SGGAN_LOSS_SGGAN && e.cfg.Lg_lambda != 0.f;
+      *flops_per_launch = px * (52.0 + (sg ? 68.0 : 0.0));
+    }
   }
   return 0;
 }

@@ -882,6 +882,13 @@ int Engine::step_bwd_g() {
   fg.fake = fake; fg.dD = dD; fg.B = B; fg.H = H; fg.W = W; fg.loss = loss; fg.dst = lo.dY; fg.dmap = lo.dymap;
   fg.dbias = G.g + G.T[lo.ti_b].offset;
   float l1w, lgw = 0.f;
+  // profile kind 3: the loss kernels of the generator side (seg-edge weights + gradient-sensitive loss in SG-GAN mode,
+  // the L1 / GAN gradient seed, the loss finalize) timed as one group
+  const bool timed_l = prof_on && prof_kind == 3 && prof_used + 2 <= prof_ev.size();
+  if (timed_l) {
+    join_side();  // D's Adam + re-pack run on the side stream right now: keep them out of the timed interval
+    cudaEventRecord(prof_ev[prof_used++], st);
+  }
   if (cfg.loss_mode == SGGAN_LOSS_P2P) {
     fg.target = seg_A_; l1w = cfg.p2p_lambda;
   } else {
@@ -896,6 +903,7 @@ int Engine::step_bwd_g() {
   fg.l1_weight = l1w;
   launch_fake_grad(fg, st); ++nlaunch;
   launch_finalize_losses(loss, l1w, float(B) * H * W * 3.f, lgw, losses_out_, st); ++nlaunch;
+  if (timed_l) cudaEventRecord(prof_ev[prof_used++], st);
   // output conv
   if ((r = run_wgrad(lo, G))) return r;
   if ((r = run_conv_list(lo.dgrad))) return r;

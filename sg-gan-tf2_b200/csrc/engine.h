@@ -116,7 +116,8 @@ struct Engine {
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
   bool prof_on = false;
-  int prof_kind = 0;  // 0 residual-block conv forward, 1 norm-apply forward of those layers, 2 their norm backward
+  int prof_kind = 0;  // 0 residual-block conv forward, 1 norm-apply forward of those layers, 2 their norm backward,
+                      // 3 the generator-side loss kernels (one group per step)
 
   int build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t stream, bool dry_run, size_t* need);
   int pack_weights(int net, cudaStream_t s = nullptr);

@@ -116,10 +116,29 @@ static inline int pix_per_block_for(int HW, int B) {
 }
 
 // ------------------------------------------------------------------------------------------ prep
-__global__ void prep_image3_kernel(const float* __restrict__ src, int B, int H, int W, sg_bf16* dst, FrameMap m,
-                                   int dst_b0) {
+// Four pixels (12 fp32 = three 128-bit loads) per thread; the 8-channel bf16 frame pixels are written through write_frame8
+// (reflected copies included), 16 bytes each -- consecutive pixels of a row are consecutive in the frame, so a warp writes
+// 2 KB runs.  W % 4 == 0 and a 16-byte aligned source (checked by the launcher), else one pixel per thread.
+__global__ void __launch_bounds__(256) prep_image3_kernel(const float* __restrict__ src, int B, int H, int W, sg_bf16* dst,
+                                                          FrameMap m, int dst_b0, int vec) {
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t tot = int64_t(B) * H * W;
+  if (vec) {
+    const int64_t p0 = idx * 4;
+    if (p0 >= tot) return;
+    const int b = int(p0 / (int64_t(H) * W));
+    const int r = int(p0 - int64_t(b) * H * W);
+    const int i = r / W, j = r - i * W;
+    const float4* s4 = reinterpret_cast<const float4*>(src + p0 * 3);
+    const float4 a = __ldg(s4), c = __ldg(s4 + 1), d = __ldg(s4 + 2);
+    const float f[12] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float v[8] = {f[3 * q], f[3 * q + 1], f[3 * q + 2], 0.f, 0.f, 0.f, 0.f, 0.f};
+      write_frame8(dst, m, dst_b0 + b, i, j + q, 0, v);
+    }
+    return;
+  }
   if (idx >= tot) return;
   const int b = int(idx / (int64_t(H) * W));
   const int r = int(idx - int64_t(b) * H * W);
@@ -131,7 +150,9 @@ __global__ void prep_image3_kernel(const float* __restrict__ src, int B, int H, 
 void launch_prep_image3(const float* src, int B, int H, int W, sg_bf16* dst, const FrameMap& dmap, int dst_b0,
                         cudaStream_t st) {
   const int64_t tot = int64_t(B) * H * W;
-  prep_image3_kernel<<<unsigned((tot + 255) / 256), 256, 0, st>>>(src, B, H, W, dst, dmap, dst_b0);
+  const int vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  const int64_t nthr = vec ? tot / 4 : tot;
+  prep_image3_kernel<<<unsigned((nthr + 255) / 256), 256, 0, st>>>(src, B, H, W, dst, dmap, dst_b0, vec);
 }
 
 __global__ void f32_to_frame_kernel(const float* __restrict__ src, int B, int H, int W, int C, sg_bf16* dst,
@@ -518,29 +539,68 @@ void launch_mask_reduce(const float* x, const float* mask, int B, int Hd, int Wd
   mask_reduce_kernel<<<unsigned((tot + 127) / 128), 128, 0, st>>>(x, mask, B, Hd, Wd, hm, wm, Cs, out);
 }
 
+// L1 sign gradient + discriminator / gradient-loss gradients, times tanh', into the 8-channel bf16 seed frame of the output
+// convolution; sum |diff| and the bias gradient on the way.  VEC: four pixels per thread, every stream read with three
+// 128-bit loads (W % 4 == 0, 16-byte aligned sources); else one pixel per thread.
+template <bool VEC>
 __global__ void __launch_bounds__(256) fake_grad_kernel(const FakeGradParams p) {
   __shared__ float sh[32];
+  constexpr int PX = VEC ? 4 : 1;
   const int64_t tot = int64_t(p.B) * p.H * p.W;
   const float inv_n = 1.f / (float(tot) * 3.f);
+  const float lw = p.l1_weight * inv_n;
   float l1 = 0.f, db[3] = {0.f, 0.f, 0.f};
-  for (int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < tot; idx += int64_t(gridDim.x) * blockDim.x) {
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t * PX < tot; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t idx = t * PX;
     const int b = int(idx / (int64_t(p.H) * p.W));
     const int r = int(idx - int64_t(b) * p.H * p.W);
     const int i = r / p.W, j = r - i * p.W;
-    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float f[3 * PX], tg[3 * PX], g[3 * PX];
+    if (VEC) {
+      const float4* f4 = reinterpret_cast<const float4*>(p.fake + idx * 3);
+      const float4* t4 = reinterpret_cast<const float4*>(p.target + idx * 3);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      const float f = p.fake[idx * 3 + c], t = p.target[idx * 3 + c];
-      const float diff = f - t;
-      l1 += fabsf(diff);
-      float g = p.l1_weight * inv_n * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
-      if (p.dD != nullptr) g += p.dD[idx * 3 + c];
-      if (p.dG != nullptr) g += p.dG[idx * 3 + c];
-      g *= (1.f - f * f);
-      v[c] = g;
-      db[c] += g;
+      for (int q = 0; q < 3; ++q) {
+        const float4 a = __ldg(f4 + q), c = __ldg(t4 + q);
+        f[4 * q] = a.x; f[4 * q + 1] = a.y; f[4 * q + 2] = a.z; f[4 * q + 3] = a.w;
+        tg[4 * q] = c.x; tg[4 * q + 1] = c.y; tg[4 * q + 2] = c.z; tg[4 * q + 3] = c.w;
+      }
+#pragma unroll
+      for (int e = 0; e < 12; ++e) g[e] = 0.f;
+      if (p.dD != nullptr) {
+        const float4* d4 = reinterpret_cast<const float4*>(p.dD + idx * 3);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { const float4 a = __ldg(d4 + q); g[4 * q] += a.x; g[4 * q + 1] += a.y; g[4 * q + 2] += a.z; g[4 * q + 3] += a.w; }
+      }
+      if (p.dG != nullptr) {
+        const float4* d4 = reinterpret_cast<const float4*>(p.dG + idx * 3);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { const float4 a = __ldg(d4 + q); g[4 * q] += a.x; g[4 * q + 1] += a.y; g[4 * q + 2] += a.z; g[4 * q + 3] += a.w; }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        f[c] = p.fake[idx * 3 + c];
+        tg[c] = p.target[idx * 3 + c];
+        g[c] = (p.dD != nullptr ? p.dD[idx * 3 + c] : 0.f) + (p.dG != nullptr ? p.dG[idx * 3 + c] : 0.f);
+      }
     }
-    write_frame8(p.dst, p.dmap, b, i, j, 0, v);
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+      float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int e = 3 * q + c;
+        const float diff = f[e] - tg[e];
+        l1 += fabsf(diff);
+        // the same order of operations as before: L1 sign term first, then the two gradient streams
+        float gg = lw * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f)) + g[e];
+        gg *= (1.f - f[e] * f[e]);
+        v[c] = gg;
+        db[c] += gg;
+      }
+      write_frame8(p.dst, p.dmap, b, i, j + q, 0, v);
+    }
   }
   l1 = block_sum(l1, sh);
   if (threadIdx.x == 0) atomicAdd(p.loss + 2, l1);
@@ -551,9 +611,14 @@ __global__ void __launch_bounds__(256) fake_grad_kernel(const FakeGradParams p) 
 }
 void launch_fake_grad(const FakeGradParams& p, cudaStream_t st) {
   const int64_t tot = int64_t(p.B) * p.H * p.W;
-  int blocks = int((tot + 255) / 256);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(p.fake) | reinterpret_cast<uintptr_t>(p.target) |
+                       reinterpret_cast<uintptr_t>(p.dD) | reinterpret_cast<uintptr_t>(p.dG);
+  const bool vec = (p.W % 4 == 0) && (al & 15) == 0;
+  const int64_t nthr = vec ? tot / 4 : tot;
+  int blocks = int((nthr + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  fake_grad_kernel<<<blocks, 256, 0, st>>>(p);
+  if (vec) fake_grad_kernel<true><<<blocks, 256, 0, st>>>(p);
+  else fake_grad_kernel<false><<<blocks, 256, 0, st>>>(p);
 }
 
 __global__ void finalize_losses_kernel(const float* loss, float l1_weight, float n_l1, float lg_weight, float* out) {
