@@ -14,9 +14,12 @@ model order (Conv2D / Conv2DTranspose: kernel, bias; tfa InstanceNormalization: 
 `_CHECKPOINTABLE_OBJECT_GRAPH` holding the serialized TrackableObjectGraph.  The table blocks are written uncompressed
 (BundleWriter sets kNoCompression); a snappy block (type 1) in a foreign file is reported, not guessed at.
 
-TensorFlow 2.1 is not installable in this environment, so this module is validated by round trips and by the format's own
-checksums (every block and every tensor carries a masked CRC32C, which the reader verifies) -- not against a file written
-by the reference.  The layout constants below cite the TF sources they restate.
+TensorFlow 2.1 is not installable in this environment and the reference ships no checkpoint, so the container layout is
+validated by round trips and by the format's own checksums (every block and every tensor carries a masked CRC32C, which the
+reader verifies).  The checksum layer itself (crc32c, mask) and the protobuf wire reader ARE checked against bytes TF wrote:
+the TFRecord frames of a TensorBoard log the reference ships use the same masked CRC-32C
+(tests/golden/reference_tfevents_records.bin, tests/test_tf_checkpoint.py).  The layout constants below cite the TF sources
+they restate.
 """
 from __future__ import annotations
 

@@ -87,3 +87,38 @@ def test_latest_checkpoint_absent(T, tmp_path):
     assert T.latest_checkpoint(str(tmp_path)) is None
     (tmp_path / "checkpoint").write_text('model_checkpoint_path: "cp-0001.ckpt"\n')
     assert T.latest_checkpoint(str(tmp_path)) is None      # named but not there
+
+
+def test_checksums_and_wire_format_against_bytes_written_by_tensorflow(T):
+    """tests/golden/reference_tfevents_records.bin: TFRecord frames copied verbatim from a TensorBoard log the reference's
+    trainer wrote (make_tfrecord_fixture.py).  TFRecord uses the same masked CRC-32C as the checkpoint format, so every
+    frame TF wrote must verify with our crc32c / mask, and our protobuf wire reader must recover the scalar the reference
+    logged (its first 'Generator Loss')."""
+    data = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_tfevents_records.bin"), "rb").read()
+    pos, n, scalars = 0, 0, {}
+    while pos < len(data):
+        (ln,) = struct.unpack("<Q", data[pos:pos + 8])
+        (c_len,) = struct.unpack("<I", data[pos + 8:pos + 12])
+        rec = data[pos + 12:pos + 12 + ln]
+        (c_rec,) = struct.unpack("<I", data[pos + 12 + ln:pos + 16 + ln])
+        assert T._mask(T.crc32c(data[pos:pos + 8])) == c_len and T._unmask(c_len) == T.crc32c(data[pos:pos + 8])
+        assert T._mask(T.crc32c(rec)) == c_rec
+        for f, _, v in T._pb_fields(rec):                      # Event: summary = 5 -> Summary.value = 1
+            if f != 5:
+                continue
+            for f2, _, val in T._pb_fields(v):
+                tag = num = None
+                for f3, _, x in T._pb_fields(val):             # Value: tag = 1, tensor = 8 -> TensorProto
+                    if f3 == 1:
+                        tag = bytes(x).decode()
+                    if f3 == 8:
+                        for f4, w4, y in T._pb_fields(x):      # tensor_content = 4 (raw bytes) or float_val = 5
+                            if f4 in (4, 5) and len(bytes(y)) >= 4:
+                                num = struct.unpack("<f", bytes(y)[:4])[0]
+                if tag is not None and num is not None:
+                    scalars.setdefault(tag, []).append(num)
+        pos += 16 + ln
+        n += 1
+    assert n >= 40 and pos == len(data)
+    assert abs(scalars["Generator Loss"][0] - 5.78389835357666) < 1e-6
+    assert len(scalars["Discriminator Loss"]) == 11 and abs(scalars["Mean IoU"][0] - 0.2222737967967987) < 1e-7
