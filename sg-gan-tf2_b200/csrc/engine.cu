@@ -353,7 +353,7 @@ int layer_prepare_wgrad(Layer& l, float* dW, int nimg, bool dry, float* part, si
     if (ks > chunks / 8) ks = chunks / 8;
     if (ks < 1) ks = 1;
     q.ksplit = ks;
-    if (part != nullptr && !q.x_pair) {
+    if (part != nullptr) {  // (the sliding-window layers too: their few KB of partials instead of fp32 atomics)
       const int64_t numel = int64_t(q.ntaps) * q.dw_tap_stride;
       if (size_t(numel) * size_t(ks) <= part_elems && (numel & 3) == 0) { q.part = part; q.part_stride = numel; }
     }
@@ -600,6 +600,11 @@ int Engine::build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t
   wg_part = (float*)a.take(wg_part_elems * 4);
   step_dev = (long long*)a.take(sizeof(long long));
   in_part = (float*)a.take(in_bwd_partials_bytes(512));  // per-block partial sums of the norm-backward reduce pass
+  {
+    const Layer& h0 = D.L[0];
+    red_scratch = (float*)a.take(ordered_sum_scratch_floats(B, H, W, c.segment_class, h0.Cout, h0.Hout, h0.Wout, h0.nbv) * 4);
+    red_ticket = (unsigned int*)a.take(16 * sizeof(unsigned int));
+  }
   for (int i = 0; i < 2; ++i) {
     pack_jobs[i] = (PackParams*)a.take(kMaxPackJobs * sizeof(PackParams));
     pack_starts[i] = (int*)a.take((kMaxPackJobs + 1) * sizeof(int));
@@ -844,6 +849,7 @@ int Engine::step_fwd_bwd_d(const float* real_A, const float* seg_A, const float*
   dl.disc_scale = cfg.loss_mode == SGGAN_LOSS_SGGAN ? 0.5f : 1.f;
   dl.logits = logits; dl.loss = loss; dl.dst = l4.dY; dl.dmap = l4.dymap;
   dl.dbias = D.g + D.T[l4.ti_b].offset;
+  dl.red = OrderedSum{red_scratch, red_ticket + 0};
   launch_disc_loss(dl, st); ++nlaunch;
   // D backward over 3B virtual images; weights see the first 2B (disc_tape), the last B carry the
   // generator's GAN gradient back to fake_A (gen_tape)   (model.py:196-197)
@@ -860,6 +866,7 @@ int Engine::step_fwd_bwd_d(const float* real_A, const float* seg_A, const float*
         ab.g = dx_src(up); ab.Z = up.X; ab.zmap = up.xmap; ab.B = l.nbv; ab.H = l.Hout; ab.W = l.Wout; ab.C = l.Cout;
         ab.nb_act = 2 * B; ab.act_wrap = B; ab.alpha = l.alpha; ab.dst = l.dY; ab.dmap = l.dymap;
         ab.dbias = D.g + D.T[l.ti_b].offset; ab.nb_bias = 2 * B;
+        ab.red = OrderedSum{red_scratch, red_ticket + 1};
         launch_act_bwd(ab, st); ++nlaunch;
       }
     }
@@ -881,6 +888,7 @@ int Engine::step_bwd_g() {
   memset(&fg, 0, sizeof(fg));
   fg.fake = fake; fg.dD = dD; fg.B = B; fg.H = H; fg.W = W; fg.loss = loss; fg.dst = lo.dY; fg.dmap = lo.dymap;
   fg.dbias = G.g + G.T[lo.ti_b].offset;
+  fg.red = OrderedSum{red_scratch, red_ticket + 2};
   float l1w, lgw = 0.f;
   // profile kind 3: the loss kernels of the generator side (seg-edge weights + gradient-sensitive loss in SG-GAN mode,
   // the L1 / GAN gradient seed, the loss finalize) timed as one group
@@ -895,7 +903,7 @@ int Engine::step_bwd_g() {
     fg.target = real_A_; l1w = cfg.L1_lambda; lgw = cfg.Lg_lambda;
     if (lgw != 0.f) {
       launch_seg_edge_weight(seg_A_, B, H, W, edge_w, st);
-      launch_gradloss(fake, real_A_, edge_w, B, H, W, lgw, loss + 3, dGl, st);
+      launch_gradloss(fake, real_A_, edge_w, B, H, W, lgw, loss + 3, dGl, st, OrderedSum{red_scratch, red_ticket + 3});
       nlaunch += 2;
       fg.dG = dGl;
     }

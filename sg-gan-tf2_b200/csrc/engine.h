@@ -93,6 +93,8 @@ struct Engine {
   int pack_njobs[2], pack_blocks[2];
   float* wg_part;  // split-K partial tiles of the weight-gradient GEMMs (shared by all layers)
   float* in_part;  // per-block partial sums of the norm-backward reduce pass (consumed by the apply pass that follows)
+  float* red_scratch = nullptr;        // deposits of the ordered cross-block sums of the loss / seed kernels (OrderedSum)
+  unsigned int* red_ticket = nullptr;  // one arrival counter per such kernel (self-resetting)
   int glue_err = 0;  // first failed row-stream launch of the current phase (reported when the phase ends)
   size_t wg_part_elems;
   uint8_t *zero_begin, *zero_end;

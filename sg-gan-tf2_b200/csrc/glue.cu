@@ -9,6 +9,8 @@
 #include "glue.h"
 
 #include <cuda_bf16.h>
+
+#include <algorithm>
 #include <math.h>
 
 namespace sggan {
@@ -345,6 +347,8 @@ void launch_in_param_grad(const float* sums, int nb, int C, float* dgamma, float
 }
 
 // ------------------------------------------------------------------------------------------ gather
+__device__ bool grid_sum_ordered(const float* part_sm, int K, const OrderedSum& red, float* out, float* tmp_sm);  // below
+
 __global__ void __launch_bounds__(kGlueThreads) act_bwd_kernel(const ActBwdParams p, int ppb) {
   extern __shared__ float sred[];
   const int b = blockIdx.y;
@@ -405,18 +409,35 @@ __global__ void __launch_bounds__(kGlueThreads) act_bwd_kernel(const ActBwdParam
     }
     write_frame8(p.dst, p.dmap, b, i, j, c0, d);
   }
-  if (p.dbias != nullptr && b < p.nb_bias) {
+  if (p.dbias == nullptr) return;
+  // bias gradient: the ppi threads that share a channel group park their sums, thread t < C adds them in order; blocks of
+  // images >= nb_bias (the generator's virtual images) deposit zeros so that every block takes part in the ordered sum
+  const bool counts = b < p.nb_bias;
+  float* slab = sred + p.C;  // [ppi][C]
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(&sred[c0 + e], acc[e]);
+  for (int e = 0; e < 8; ++e) slab[lp * p.C + c0 + e] = counts ? acc[e] : 0.f;
+  __syncthreads();
+  for (int t = threadIdx.x; t < p.C; t += kGlueThreads) {
+    float s = 0.f;
+    for (int q = 0; q < ppi; ++q) s += slab[q * p.C + t];
+    sred[t] = s;
   }
   __syncthreads();
-  if (p.dbias != nullptr && b < p.nb_bias)
+  if (p.red.scratch != nullptr) {
+    grid_sum_ordered(sred, p.C, p.red, p.dbias, slab);
+  } else if (counts) {
     for (int t = threadIdx.x; t < p.C; t += kGlueThreads) atomicAdd(p.dbias + t, sred[t]);
+  }
 }
 void launch_act_bwd(const ActBwdParams& p, cudaStream_t st) {
   const int HW = p.H * p.W, ppb = pix_per_block_for(HW, p.B);
   dim3 grid((HW + ppb - 1) / ppb, p.B);
-  act_bwd_kernel<<<grid, kGlueThreads, p.C * sizeof(float), st>>>(p, ppb);
+  // shared memory: [C] block sums + [ppi][C] = kGlueThreads * 8 per-thread sums (also >= kGlueThreads floats of scratch)
+  act_bwd_kernel<<<grid, kGlueThreads, (p.C + kGlueThreads * 8) * sizeof(float), st>>>(p, ppb);
+}
+int act_bwd_blocks(int B, int H, int W) {
+  const int HW = H * W, ppb = pix_per_block_for(HW, B);
+  return ((HW + ppb - 1) / ppb) * B;
 }
 
 // ------------------------------------------------------------------------------------------ losses
@@ -437,6 +458,41 @@ __device__ float block_sum(float v, float* sh) {
   return r;  // valid in warp 0
 }
 
+// See OrderedSum (glue.h).  part_sm[0..K) = this block's partial values in shared memory (all threads may read them after the
+// caller's __syncthreads); the last block accumulates the grid totals into out[0..K).  tmp_sm: blockDim.x floats of
+// shared memory.  Called by all threads of every block.
+__device__ bool grid_sum_ordered(const float* part_sm, int K, const OrderedSum& red, float* out, float* tmp_sm) {
+  const int nblk = gridDim.x * gridDim.y * gridDim.z;
+  const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  __shared__ unsigned int s_last;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) __stcg(red.scratch + size_t(bid) * K + k, part_sm[k]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicInc(red.ticket, unsigned(nblk - 1)) == unsigned(nblk - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return false;
+  __threadfence();
+  // thread (g, k): deposits g, g + groups, ... of value k, added in that order; then the groups in order
+  for (int k0 = 0; k0 < K; k0 += blockDim.x) {
+    const int kn = min(K - k0, int(blockDim.x));
+    const int groups = blockDim.x / kn;
+    const int g = threadIdx.x / kn, k = threadIdx.x - g * kn;
+    float acc = 0.f;
+    if (g < groups)
+      for (int b = g; b < nblk; b += groups) acc += __ldcg(red.scratch + size_t(b) * K + k0 + k);
+    __syncthreads();
+    if (g < groups) tmp_sm[g * kn + k] = acc;
+    __syncthreads();
+    if (int(threadIdx.x) < kn) {
+      float t = 0.f;
+      for (int q = 0; q < groups; ++q) t += tmp_sm[q * kn + threadIdx.x];
+      out[k0 + threadIdx.x] += t;
+    }
+  }
+  __syncthreads();
+  return true;  // uniform over the block: this is the block that holds the totals
+}
+
 // The logits are KB-sized (B x 5 x 13 at 256x512): two small multi-block launches.
 __global__ void disc_logits_kernel(const DiscLossParams p) {
   const int Ho = max(p.Hd, p.hm), Wo = max(p.Wd, p.wm);
@@ -453,13 +509,12 @@ __global__ void disc_logits_kernel(const DiscLossParams p) {
 }
 __global__ void __launch_bounds__(256) disc_loss_grad_kernel(const DiscLossParams p) {
   __shared__ float sh[32];
-  extern __shared__ float sbias[];
+  __shared__ float tmp[256];
+  extern __shared__ float sbias[];  // [groups][Cs] partial bias gradients, [2 + Cs] block partials, [2 + Cs] grid totals
   const int Ho = max(p.Hd, p.hm), Wo = max(p.Wd, p.wm);
   const int B2 = 2 * p.B, npos = Ho * Wo;
   const float N = float(p.B) * npos;
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x;
-  for (int t = threadIdx.x; t < p.Cs; t += blockDim.x) sbias[t] = 0.f;
-  __syncthreads();
   // losses
   float lg = 0.f, ld = 0.f;
   for (int idx = gtid; idx < B2 * npos; idx += gstride) {
@@ -476,47 +531,74 @@ __global__ void __launch_bounds__(256) disc_loss_grad_kernel(const DiscLossParam
   }
   lg = block_sum(lg, sh);
   ld = block_sum(ld, sh);
-  if (threadIdx.x == 0) {
-    atomicAdd(p.loss + 0, lg / N);
-    atomicAdd(p.loss + 1, ld * p.disc_scale / N);
-  }
-  // d logits -> d h4 (3B virtual images: real-D, fake-D, fake-G) and the bias gradient (first 2B)
-  const int tot = 3 * p.B * p.Hd * p.Wd * p.Cs;
-  for (int idx = gtid; idx < tot; idx += gstride) {
-    const int c = idx % p.Cs;
-    int r = idx / p.Cs;
-    const int jh = r % p.Wd;
-    r /= p.Wd;
-    const int ih = r % p.Hd, v = r / p.Hd;
-    const int bs = v < B2 ? v : v - p.B;
-    const float label = (v < p.B || v >= B2) ? 1.f : 0.f;
-    const float sc = (v < B2 ? p.disc_scale : 1.f) / N;
-    const int I0 = p.Hd == 1 ? 0 : ih, I1 = p.Hd == 1 ? Ho : ih + 1;
-    const int J0 = p.Wd == 1 ? 0 : jh, J1 = p.Wd == 1 ? Wo : jh + 1;
-    float g = 0.f;
-    for (int I = I0; I < I1; ++I)
-      for (int J = J0; J < J1; ++J) {
-        const int im = p.hm == 1 ? 0 : I, jm = p.wm == 1 ? 0 : J;
-        const float x = p.logits[(bs * Ho + I) * Wo + J];
-        const float dl = (p.lsgan ? 2.f * (x - label) : (sigmoidf(x) - label)) * sc;
-        g += dl * p.mask[((int64_t(bs % p.B) * p.hm + im) * p.wm + jm) * p.Cs + c];
-      }
-    reinterpret_cast<__nv_bfloat16*>(p.dst)[(int64_t(v) * p.dmap.frame_pix + frame_pixel(p.dmap, ih, jh)) * p.dmap.C + c] =
-        __float2bfloat16_rn(g);
-    if (v < B2) atomicAdd(&sbias[c], g);
-  }
+  // d logits -> d h4 (3B virtual images: real-D, fake-D, fake-G) and the bias gradient (first 2B).  Thread (g, c) keeps its
+  // channel and walks the positions g, g + G * gridDim.x, ..., so its bias partial needs no atomics.
+  const int G = blockDim.x / p.Cs;  // position groups per block (7 at Cs = 34)
+  const int g = threadIdx.x / p.Cs, c = threadIdx.x - g * p.Cs;
+  const int npos_h = 3 * p.B * p.Hd * p.Wd;
+  float bsum = 0.f;
+  if (g < G)
+    for (int pos = blockIdx.x * G + g; pos < npos_h; pos += gridDim.x * G) {
+      int r = pos;
+      const int jh = r % p.Wd;
+      r /= p.Wd;
+      const int ih = r % p.Hd, v = r / p.Hd;
+      const int bs = v < B2 ? v : v - p.B;
+      const float label = (v < p.B || v >= B2) ? 1.f : 0.f;
+      const float sc = (v < B2 ? p.disc_scale : 1.f) / N;
+      const int I0 = p.Hd == 1 ? 0 : ih, I1 = p.Hd == 1 ? Ho : ih + 1;
+      const int J0 = p.Wd == 1 ? 0 : jh, J1 = p.Wd == 1 ? Wo : jh + 1;
+      float gv = 0.f;
+      for (int I = I0; I < I1; ++I)
+        for (int J = J0; J < J1; ++J) {
+          const int im = p.hm == 1 ? 0 : I, jm = p.wm == 1 ? 0 : J;
+          const float x = p.logits[(bs * Ho + I) * Wo + J];
+          const float dl = (p.lsgan ? 2.f * (x - label) : (sigmoidf(x) - label)) * sc;
+          gv += dl * p.mask[((int64_t(bs % p.B) * p.hm + im) * p.wm + jm) * p.Cs + c];
+        }
+      reinterpret_cast<__nv_bfloat16*>(p.dst)[(int64_t(v) * p.dmap.frame_pix + frame_pixel(p.dmap, ih, jh)) * p.dmap.C + c] =
+          __float2bfloat16_rn(gv);
+      if (v < B2) bsum += gv;
+    }
+  if (g < G) sbias[g * p.Cs + c] = bsum;
   __syncthreads();
-  for (int t = threadIdx.x; t < p.Cs; t += blockDim.x)
-    if (sbias[t] != 0.f) atomicAdd(p.dbias + t, sbias[t]);
+  float bc = 0.f;
+  if (int(threadIdx.x) < p.Cs)
+    for (int q = 0; q < G; ++q) bc += sbias[q * p.Cs + threadIdx.x];
+  __syncthreads();
+  float* part = sbias + G * p.Cs;  // [2 + Cs]
+  if (int(threadIdx.x) < p.Cs) part[2 + threadIdx.x] = bc;
+  if (threadIdx.x == 0) { part[0] = lg / N; part[1] = ld * p.disc_scale / N; }
+  __syncthreads();
+  if (p.red.scratch != nullptr) {
+    // totals: loss[0], loss[1], dbias[0..Cs) -- two destinations, so the last block adds into a staging row first
+    float* tot = part + 2 + p.Cs;
+    for (int t = threadIdx.x; t < 2 + p.Cs; t += blockDim.x) tot[t] = 0.f;
+    __syncthreads();
+    if (grid_sum_ordered(part, 2 + p.Cs, p.red, tot, tmp)) {
+      if (threadIdx.x < 2) p.loss[threadIdx.x] += tot[threadIdx.x];
+      if (int(threadIdx.x) < p.Cs) p.dbias[threadIdx.x] += tot[2 + threadIdx.x];
+    }
+  } else {
+    if (threadIdx.x < 2) atomicAdd(p.loss + threadIdx.x, part[threadIdx.x]);
+    if (int(threadIdx.x) < p.Cs && part[2 + threadIdx.x] != 0.f) atomicAdd(p.dbias + threadIdx.x, part[2 + threadIdx.x]);
+  }
 }
 void launch_disc_loss(const DiscLossParams& p, cudaStream_t st) {
   const int Ho = p.Hd > p.hm ? p.Hd : p.hm, Wo = p.Wd > p.wm ? p.Wd : p.wm;
   const int nlog = 2 * p.B * Ho * Wo;
   disc_logits_kernel<<<(nlog + 127) / 128, 128, 0, st>>>(p);
-  const int tot = 3 * p.B * p.Hd * p.Wd * p.Cs;
-  int blocks = (tot + 255) / 256;
+  const int G = 256 / p.Cs;
+  const int npos_h = 3 * p.B * p.Hd * p.Wd;
+  int blocks = (npos_h + G - 1) / G;
   if (blocks > 148) blocks = 148;
-  disc_loss_grad_kernel<<<blocks, 256, p.Cs * sizeof(float), st>>>(p);
+  if (blocks < 1) blocks = 1;
+  disc_loss_grad_kernel<<<blocks, 256, (G * p.Cs + 2 * (2 + p.Cs)) * sizeof(float), st>>>(p);
+}
+int disc_loss_blocks(int B, int Hd, int Wd, int Cs) {
+  const int G = 256 / Cs;
+  int blocks = (3 * B * Hd * Wd + G - 1) / G;
+  return blocks > 148 ? 148 : (blocks < 1 ? 1 : blocks);
 }
 
 __global__ void mask_reduce_kernel(const float* __restrict__ x, const float* __restrict__ mask, int B, int Hd, int Wd,
@@ -602,11 +684,23 @@ __global__ void __launch_bounds__(256) fake_grad_kernel(const FakeGradParams p) 
       write_frame8(p.dst, p.dmap, b, i, j + q, 0, v);
     }
   }
+  __shared__ float part[4], gsum[4], tmp[256];
   l1 = block_sum(l1, sh);
-  if (threadIdx.x == 0) atomicAdd(p.loss + 2, l1);
+  if (threadIdx.x == 0) part[0] = l1;
   for (int c = 0; c < 3; ++c) {
     const float s = block_sum(db[c], sh);
-    if (threadIdx.x == 0) atomicAdd(p.dbias + c, s);
+    if (threadIdx.x == 0) part[1 + c] = s;
+  }
+  if (threadIdx.x < 4) gsum[threadIdx.x] = 0.f;
+  __syncthreads();
+  if (p.red.scratch != nullptr) {
+    if (grid_sum_ordered(part, 4, p.red, gsum, tmp)) {
+      if (threadIdx.x == 0) p.loss[2] += gsum[0];
+      if (threadIdx.x < 3) p.dbias[threadIdx.x] += gsum[1 + threadIdx.x];
+    }
+  } else if (threadIdx.x == 0) {
+    atomicAdd(p.loss + 2, part[0]);
+    for (int c = 0; c < 3; ++c) atomicAdd(p.dbias + c, part[1 + c]);
   }
 }
 void launch_fake_grad(const FakeGradParams& p, cudaStream_t st) {
@@ -619,6 +713,13 @@ void launch_fake_grad(const FakeGradParams& p, cudaStream_t st) {
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (vec) fake_grad_kernel<true><<<blocks, 256, 0, st>>>(p);
   else fake_grad_kernel<false><<<blocks, 256, 0, st>>>(p);
+}
+size_t ordered_sum_scratch_floats(int B, int H, int W, int Cs, int C_h0, int H_h0, int W_h0, int nb_h0) {
+  size_t n = size_t(148 * 8) * 4;                                            // fake_grad: at most 148 * 8 blocks x 4 values
+  n = std::max(n, size_t((W + 63) / 64) * ((H + 15) / 16) * B);             // gradloss: one value per tile
+  n = std::max(n, size_t(148) * (2 + Cs));                                   // disc_loss_grad
+  n = std::max(n, size_t(act_bwd_blocks(nb_h0, H_h0, W_h0)) * C_h0);         // act_bwd of D's first layer
+  return n + 64;
 }
 
 __global__ void finalize_losses_kernel(const float* loss, float l1_weight, float n_l1, float lg_weight, float* out) {
@@ -677,7 +778,7 @@ __device__ __forceinline__ void sobel_smem(const float* t, int r, int q, int c, 
 }
 __global__ void __launch_bounds__(256) gradloss_kernel(const float* __restrict__ in, const float* __restrict__ tgt,
                                                        const float* __restrict__ wgt, int B, int H, int W,
-                                                       float scale, float* loss_slot, float* d_in) {
+                                                       float scale, float* loss_slot, float* d_in, OrderedSum red) {
   extern __shared__ float gl_smem[];
   float* s_in = gl_smem;                          // [kGlIh][kGlIw][3]
   float* s_tg = s_in + kGlIh * kGlIw * 3;
@@ -739,10 +840,18 @@ __global__ void __launch_bounds__(256) gradloss_kernel(const float* __restrict__
     }
   }
   lsum = block_sum(lsum, sh);
-  if (threadIdx.x == 0 && loss_slot != nullptr) atomicAdd(loss_slot, lsum * inv);
+  if (loss_slot == nullptr) return;
+  if (red.scratch != nullptr) {
+    __shared__ float part[1], tmp[256];
+    if (threadIdx.x == 0) part[0] = lsum * inv;
+    __syncthreads();
+    grid_sum_ordered(part, 1, red, loss_slot, tmp);
+  } else if (threadIdx.x == 0) {
+    atomicAdd(loss_slot, lsum * inv);
+  }
 }
 void launch_gradloss(const float* in, const float* target, const float* weight, int B, int H, int W, float scale,
-                     float* loss_slot, float* d_in, cudaStream_t st) {
+                     float* loss_slot, float* d_in, cudaStream_t st, OrderedSum red) {
   dim3 grid((W + kGlTw - 1) / kGlTw, (H + kGlTh - 1) / kGlTh, B);
   constexpr size_t smem = size_t(2 * kGlIh * kGlIw * 3 + kGlCh * kGlCw * 6) * sizeof(float);  // 61 KB: three blocks per SM
   static bool attr_set = false;
@@ -750,7 +859,7 @@ void launch_gradloss(const float* in, const float* target, const float* weight, 
     cudaFuncSetAttribute(gradloss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     attr_set = true;
   }
-  gradloss_kernel<<<grid, 256, smem, st>>>(in, target, weight, B, H, W, scale, loss_slot, d_in);
+  gradloss_kernel<<<grid, 256, smem, st>>>(in, target, weight, B, H, W, scale, loss_slot, d_in, red);
 }
 
 // module.tf_deriv (module.py:325-334) as a standalone operator: Sobel x / y per channel, SAME zero padding or VALID;

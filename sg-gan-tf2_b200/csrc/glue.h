@@ -29,6 +29,16 @@ int launch_grad_gather(const GradSrc& g1, const GradSrc& g2, int B, int H, int W
 // Backward of an activation applied in a conv epilogue (discriminator h0: LeakyReLU without norm):
 // dy = dz * act'(z), z read from the frame the epilogue wrote; also accumulates the bias gradient
 // over the first nb_bias images.
+// Deterministic cross-block sums: every block deposits its partial values in `scratch` ([blocks][K] floats), the block
+// that draws the last ticket adds all deposits in block order (fixed assignment to threads, fixed combination tree) and
+// accumulates the totals into the destination -- no floating-point atomics, so the result does not depend on the order in
+// which blocks finish.  `ticket` wraps back to zero by itself (atomicInc).  scratch == nullptr: the kernels fall back to
+// atomicAdd (stand-alone operator calls without a workspace).
+struct OrderedSum {
+  float* scratch;
+  unsigned int* ticket;
+};
+
 struct ActBwdParams {
   GradSrc g;
   const sg_bf16* Z;
@@ -40,6 +50,7 @@ struct ActBwdParams {
   FrameMap dmap;
   float* dbias;
   int nb_bias;
+  OrderedSum red;  // scratch: gridDim.x * nb_bias * C floats
 };
 void launch_act_bwd(const ActBwdParams& p, cudaStream_t st);
 
@@ -57,6 +68,7 @@ struct DiscLossParams {
   sg_bf16* dst;      // dY frame of h4 for the 3B virtual images (real-D, fake-D, fake-G)
   FrameMap dmap;     // C = padded channel count
   float* dbias;      // [Cs] += over the first 2B images
+  OrderedSum red;    // scratch: blocks * (2 + Cs) floats
 };
 void launch_disc_loss(const DiscLossParams& p, cudaStream_t st);
 
@@ -73,6 +85,7 @@ struct FakeGradParams {
   sg_bf16* dst;     // 8-channel dY frame of the output conv
   FrameMap dmap;
   float* dbias;  // [3]
+  OrderedSum red;  // scratch: blocks * 4 floats
 };
 void launch_fake_grad(const FakeGradParams& p, cudaStream_t st);
 
@@ -84,7 +97,9 @@ void launch_finalize_losses(const float* loss, float l1_weight, float n_l1, floa
 // gradient w.r.t. `in`.  All fp32 NHWC 3-channel.
 void launch_seg_edge_weight(const float* seg, int B, int H, int W, float* weight, cudaStream_t st);
 void launch_gradloss(const float* in, const float* target, const float* weight, int B, int H, int W,
-                     float scale, float* loss_slot, float* d_in, cudaStream_t st);
+                     float scale, float* loss_slot, float* d_in, cudaStream_t st, OrderedSum red = OrderedSum{nullptr, nullptr});
+// floats of OrderedSum scratch the four loss / seed kernels need for this problem size (the largest of them)
+size_t ordered_sum_scratch_floats(int B, int H, int W, int Cs, int C_h0, int H_h0, int W_h0, int nb_bias);
 // Plain criteria (module.py:336-345) as reductions: mode 0 abs, 1 squared, 2 sigmoid-CE(logits=a, labels=b)
 void launch_criterion(const float* a, const float* b, int64_t n, int mode, float* out, cudaStream_t st);
 // module.tf_deriv: Sobel x / y per channel, out [B][Ho][Wo][C * 2]; valid = 0: SAME zero padding, 1: VALID
