@@ -1405,7 +1405,10 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
     // epilogue is exposed: 58 us against 73 us for the residual convolution (1.34 against 1.06 PFLOP/s)
     const char* env = getenv("SGGAN_CONV_PAIR");
     const bool allow = !(env && env[0] == '0');
-    if (allow && !p.tf32 && p.BN == 256 && p.CoutPad == 256 && p.shift_kw == 0 && int64_t(T128) * p.B >= 148) {
+    // also below one wave (batch-1 inference: 65 tiles): a pair finishes a 128-row tile in ~28k cycles (18.4k of MMAs + set-up
+    // + epilogue), the single-CTA kernel needs ~60k for its two tiles, and neither fills the 148 SMs
+    constexpr int kPairMinTiles = 8;
+    if (allow && !p.tf32 && p.BN == 256 && p.CoutPad == 256 && p.shift_kw == 0 && int64_t(T128) * p.B >= kPairMinTiles) {
       L->pair = 1;
       L->T128 = T128;
       L->npairs = (T128 * p.B + 1) / 2;
