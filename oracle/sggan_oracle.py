@@ -261,6 +261,48 @@ def generator_resnet(x, w, n_blocks=None, taps=None, emu=None):
     return pred
 
 
+def generator_unet_spec(gf_dim=64, in_c=3, out_c=3):
+    """module.py:125-206 as (kind, kernel shape, has_norm) in Keras creation order: eight 3x3 'same' convolutions, then
+    eight 3x3 'same' stride-1 transposed convolutions (kernel (kh, kw, Cout, Cin)); every layer but the last has a norm."""
+    g = gf_dim
+    enc = [in_c, g, 2 * g, 4 * g, 8 * g, 8 * g, 8 * g, 8 * g, 8 * g]
+    dec = [8 * g, 8 * g, 8 * g, 8 * g, 8 * g, 4 * g, 2 * g, g, out_c]
+    spec = [("conv", (3, 3, enc[i], enc[i + 1]), True) for i in range(8)]
+    spec += [("deconv", (3, 3, dec[i + 1], dec[i]), i < 7) for i in range(8)]
+    return spec
+
+
+def generator_unet(x, w, training=False, drop_masks=None):
+    """module.py:125-206.  All layers run at the input resolution (3x3, stride 1, 'same'); LeakyReLU() is Keras' default
+    alpha 0.3; the skips are ADDS (d_k + e_{8-k}); Dropout(0.5) on d1..d3 only acts in training mode (inverted dropout:
+    kept values are scaled by 2) -- `drop_masks` supplies the three keep masks then, since TF's generator cannot be matched."""
+    idx = [0]
+
+    def take(n):
+        r = w[idx[0]:idx[0] + n]
+        idx[0] += n
+        return r
+
+    e, h = [], x
+    for i in range(8):
+        k, b, g, be = take(4)
+        h = instance_norm(conv2d(h, k, b, 1, "SAME"), g, be)
+        h = torch.relu(h) if i == 7 else lrelu(h, 0.3)
+        e.append(h)
+    d = e[7]
+    for i in range(7):
+        k, b, g, be = take(4)
+        d = conv2d_transpose(d, k, b, 1)
+        if i < 3 and training:
+            d = d * drop_masks[i] * 2.0
+        d = instance_norm(d, g, be) + e[6 - i]
+        if i in (2, 6):
+            d = torch.relu(d)
+    k, b = take(2)
+    assert idx[0] == len(w)
+    return torch.tanh(conv2d_transpose(d, k, b, 1))
+
+
 def discriminator(x, mask, w, taps=None, emu=None):
     """module.py:272-318.  w = flat Keras-order list (28 tensors).  Returns (B,Hd,Wd,1).
     `emu`: see BF16Emu (None = exact restatement)."""

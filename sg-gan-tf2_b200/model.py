@@ -8,7 +8,8 @@ into libsggan_sm100.so (forward, both backward passes, Adam) -- no TensorFlow, n
 
 Deliberate deviations: D5 -- `fake_A = G(real_A)` every step (the reference's
 concat-with-previous-fake branch only survives step 2 at batch 10); D6 -- `lr` is live but
-defaults to the reference-effective 0.001; D9 -- only the `use_resnet` generator exists.
+defaults to the reference-effective 0.001; D9 -- training uses the `use_resnet` generator; `generator_unet` (the CLI default)
+runs forward only.
 Data loading / eval / TensorBoard (model.py:202-448) are host orchestration outside the path:
 `train()` consumes an iterable of numpy batches instead of globbing PNGs.
 """
@@ -23,8 +24,8 @@ import torch.distributed as dist
 
 from . import _lib as L
 from . import module
-from .module import (abs_criterion, discriminator, generator_resnet, gradloss_criterion, mae_criterion,  # noqa: F401
-                     sce_criterion, tf_kernel_prep_3d)
+from .module import (abs_criterion, discriminator, generator_resnet, generator_unet, gradloss_criterion,  # noqa: F401
+                     mae_criterion, sce_criterion, tf_kernel_prep_3d)
 
 
 class sggan(object):
@@ -41,8 +42,9 @@ class sggan(object):
         r = getattr(args, "ratio_gan2seg", 10)
         self.alpha_recip = 1. / r if r > 0 else 0
         self.use_pix2pix = getattr(args, "use_pix2pix", False)
-        if self.use_pix2pix or not getattr(args, "use_resnet", True):
-            raise L.SgganError("only the use_resnet generator + semantic-aware discriminator path is implemented "
+        self.use_resnet = bool(getattr(args, "use_resnet", True))
+        if self.use_pix2pix:
+            raise L.SgganError("the pix2pix generator / discriminator pair (BatchNorm, 4x4 stride-2, Dropout) is not built "
                                "(SURVEY D9 / 8(f) row f4)")
         self.use_lsgan = bool(getattr(args, "use_lsgan", True))
         self.criterionGAN = mae_criterion if self.use_lsgan else sce_criterion
@@ -52,7 +54,10 @@ class sggan(object):
         self.lr = getattr(args, "lr_effective", 0.001)  # model.py:82,205: hard-coded 0.001 (args.lr unused)
         self.beta1 = getattr(args, "beta1", 0.5)
         self.discriminator = discriminator(self.image_height, self.image_width, getattr(args, "ndf", 64), self.segment_class)
-        self.generator = generator_resnet(self.image_height, self.image_width, getattr(args, "ngf", 64), self.output_c_dim)
+        # use_resnet=False is the reference CLI's default (main.py:39): generator_unet, forward only here -- sampling and
+        # testing work, train_step needs the ResNet generator (the fused engine, which is what BASELINE names)
+        self.generator = generator_resnet(self.image_height, self.image_width, getattr(args, "ngf", 64), self.output_c_dim) \
+            if self.use_resnet else module.generator_unet(getattr(args, "ngf", 64), self.output_c_dim)
         self.kernels = [tf_kernel_prep_3d(np.array([[0, 0, 0], [-1, 0, 1], [0, 0, 0]]), self.input_c_dim),
                         tf_kernel_prep_3d(np.array([[0, -1, 0], [0, 0, 0], [0, 1, 0]]), self.input_c_dim)]
         self.kernel = np.stack(self.kernels, axis=-1).astype(np.float32)  # "DerivKernel_seg" (model.py:109-112)
@@ -187,6 +192,9 @@ class sggan(object):
     def train_step(self, args=None):
         """model.py:169-200.  Inputs come from self.real_A / self.seg_A / self.mask_A exactly as in the
         reference's train loop (model.py:249-256)."""
+        if not self.use_resnet:
+            raise L.SgganError("train_step: the fused training engine is built for generator_resnet (use_resnet=True); "
+                               "generator_unet runs forward only (module.GeneratorUnet)")
         self._begin_uploads()
         real_A = self._upload("real_A", self.real_A)
         seg_A = self._upload("seg_A", self.seg_A)

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["generator_resnet", "discriminator", "residule_block", "tf_kernel_prep_3d", "tf_deriv", "abs_criterion",
+__all__ = ["generator_resnet", "generator_unet", "discriminator", "residule_block", "tf_kernel_prep_3d", "tf_deriv", "abs_criterion",
            "mae_criterion", "sce_criterion", "gradloss_criterion"]
 
 _SEED = 19  # main.py:4 tf.random.set_seed(19)
@@ -279,6 +279,85 @@ class Discriminator(_Net):
             else:
                 rt = self._infer_runtime(kw, B, H, W)
         return rt.engine.disc_forward(x, mask)
+
+
+class GeneratorUnet(_Net):
+    """generator_unet (module.py:125-206), the reference CLI's default generator: eight 3x3 'same' convolutions + instance
+    norm + LeakyReLU(0.3) at the input resolution, eight 3x3 'same' stride-1 transposed convolutions + instance norm with
+    additive skips, Dropout(0.5) on the first three in training mode, tanh.
+
+    FORWARD ONLY, on the operator tier (ops.conv2d_raw / instance_norm_raw; precision "bf16" = the training path's tcgen05
+    kernels with bf16 storage, "tf32" / "tf32x3" = fp32 storage): sampling / testing with this generator works, training it
+    does not (the fused step engine is the ResNet generator's, which is what BASELINE names).  A stride-1 'same' transposed
+    convolution IS a convolution with the kernel flipped and its channel axes exchanged, so it runs on the same kernels."""
+    net_id = None
+
+    def __init__(self, gf_dim=64, output_c_dim=3, seed=_SEED):
+        g = gf_dim
+        enc = [3, g, 2 * g, 4 * g, 8 * g, 8 * g, 8 * g, 8 * g, 8 * g]
+        dec = [8 * g, 8 * g, 8 * g, 8 * g, 8 * g, 4 * g, 2 * g, g, output_c_dim]
+        shapes = []
+        for i in range(8):
+            shapes += [(3, 3, enc[i], enc[i + 1]), (enc[i + 1],), (enc[i + 1],), (enc[i + 1],)]
+        for i in range(8):
+            shapes += [(3, 3, dec[i + 1], dec[i]), (dec[i + 1],)]
+            if i < 7:
+                shapes += [(dec[i + 1],), (dec[i + 1],)]
+        super().__init__(shapes, seed)
+        i = 0
+        while i < len(shapes):
+            self._vars[i + 1] = torch.zeros(shapes[i + 1])
+            if i + 2 < len(shapes) and len(shapes[i + 2]) == 1:
+                self._vars[i + 2] = torch.ones(shapes[i + 2])
+                self._vars[i + 3] = torch.zeros(shapes[i + 3])
+                i += 4
+            else:
+                i += 2
+
+    def layer_kinds(self):
+        return ["conv", "norm"] * 8 + ["deconv", "norm"] * 7 + ["deconv"]
+
+    def bind(self, runtime):
+        raise L.SgganError("generator_unet runs on the operator tier only (no fused training engine)")
+
+    def __call__(self, x, training=False, precision="bf16", drop_masks=None):
+        from . import ops
+        x = L.as_cuda_f32(x)
+        v = [t if t.is_cuda else t.to(x.device) for t in self._vars]
+
+        def prec(cin, cout):  # the bf16 tier takes channel counts in multiples of 64; the 3-channel ends go to the tf32 tier
+            return precision if (precision != "bf16" or (cin % 64 == 0 and cout % 64 == 0)) else "tf32"
+
+        e, h, i = [], x, 0
+        for li in range(8):
+            k, b, g, be = v[i:i + 4]
+            i += 4
+            h = ops.conv2d_raw(h, k, b, stride=1, padding="SAME", precision=prec(k.shape[2], k.shape[3]))
+            h = ops.instance_norm_raw(h, g, be, eps=1e-3, act="relu" if li == 7 else "lrelu", alpha=0.3,
+                                      precision=precision if h.shape[3] % 64 == 0 and h.shape[3] <= 512 else "fp32")
+            e.append(h)
+        d = e[7]
+        for li in range(8):
+            k, b = v[i], v[i + 1]
+            # Conv2DTranspose(3x3, stride 1, 'same'), kernel (kh, kw, Cout, Cin)  ==  Conv2D with w'[kh, kw, ci, co] = w[2-kh, 2-kw, co, ci]
+            kc = k.flip(0, 1).permute(0, 1, 3, 2).contiguous()
+            d = ops.conv2d_raw(d, kc, b, stride=1, padding="SAME", precision=prec(kc.shape[2], kc.shape[3]))
+            if li == 7:
+                return torch.tanh(d)
+            g, be = v[i + 2], v[i + 3]
+            i += 4
+            if li < 3 and training:  # Dropout(0.5), inverted: kept values are doubled
+                m = drop_masks[li].to(d.device) if drop_masks is not None else (torch.rand_like(d) >= 0.5).float()
+                d = d * m * 2.0
+            d = ops.instance_norm_raw(d, g, be, eps=1e-3, act=None, residual=e[6 - li], precision=precision)
+            if li in (2, 6):
+                d = torch.relu(d)
+        raise AssertionError("unreachable")
+
+
+def generator_unet(gf_dim=64, output_c_dim=3):
+    print("generator_unet")
+    return GeneratorUnet(gf_dim, output_c_dim)
 
 
 def generator_resnet(image_height=64, image_width=64, gf_dim=64, output_c_dim=3, n_blocks=9):

@@ -101,9 +101,17 @@ def test_keras_variable_order():
     lim = (6.0 / (7 * 7 * 3 + 7 * 7 * 64)) ** 0.5
     assert float(gv[0].abs().max()) <= lim  # glorot-uniform bound
     model = importlib.import_module("sg-gan-tf2_b200.model")
+    # use_resnet=False (the reference CLI's default) builds generator_unet: 62 variables in Keras order, forward only --
+    # train_step says so loudly instead of training something else
     ns = argparse.Namespace(batch_size=1, image_width=512, image_height=256, use_resnet=False)
+    m = model.sggan(ns)
+    uv = m.generator.trainable_variables
+    assert len(uv) == 62 and tuple(uv[0].shape) == (3, 3, 3, 64) and tuple(uv[-2].shape) == (3, 3, 3, 64)  # last: (kh, kw, Cout=3, Cin=64)
+    assert tuple(uv[32].shape) == (3, 3, 512, 512) and m.generator.layer_kinds().count("deconv") == 8
     with pytest.raises(Exception, match="use_resnet"):
-        model.sggan(ns)
+        m.train_step(ns)
+    with pytest.raises(Exception, match="pix2pix"):
+        model.sggan(argparse.Namespace(batch_size=1, image_width=512, image_height=256, use_pix2pix=True))
 
 
 def test_bench_reference_arm_line():
