@@ -19,7 +19,7 @@ static thread_local std::string g_err;
 namespace sggan {
 int layer_geometry(Layer& l);
 int layer_prepare_fwd(Layer& l, const float* bias, void* out, const FrameMap& omap, int out_f32, bool dry);
-int layer_prepare_dgrad(Layer& l, int b0, int nimg, bool dry);
+int layer_prepare_dgrad(Layer& l, int b0, int nimg, bool dry, const ConvGemmParams* nr = nullptr);
 int layer_prepare_wgrad(Layer& l, float* dW, int nimg, bool dry, float* part, size_t part_elems);
 }  // namespace sggan
 

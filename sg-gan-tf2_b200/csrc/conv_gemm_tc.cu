@@ -481,18 +481,24 @@ constexpr int kPairEpiTile = 32 * 33 * 4;                       // one warp's tr
 constexpr int kPairStagePitch = 256 * 2 + 16;
 constexpr int kPairEpiBytes = kTileM * kPairStagePitch + 4096 + 1024;
 static_assert(kPairEpiBytes >= kEpiWarps * kPairEpiTile + 2 * 4 * 256 * 8, "fallback epilogue scratch");
-constexpr int kPairAStages = 3, kPairBStages = 6;
+constexpr int kPairAStages = 3, kPairBStages = 6;  // (maximum; a launch that also folds the norm-backward sums runs 2 + 5)
 constexpr int kPairAStage = (kTileM + kHaloRows) * 128, kPairBStage = 128 * 128;
 constexpr int kPairSmem = kPairAStages * kPairAStage + kPairBStages * kPairBStage + kPairEpiBytes + 1024;
+// norm-backward fold: the Y rows matching a quarter of the tile (32 positions x 512 B), double buffered
+constexpr int kPairYQuarter = 32 * 512;
+constexpr int kPairFoldAStages = 2, kPairFoldBStages = 5;
+constexpr int kPairFoldSmem = kPairFoldAStages * kPairAStage + kPairFoldBStages * kPairBStage + kPairEpiBytes + 2 * kPairYQuarter + 1024;
+static_assert(kPairFoldSmem <= kPairSmem, "the fold variant must fit the same shared-memory opt-in");
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA8,
                       const __grid_constant__ CUtensorMap tmBh, const ConvGemmParams p, const int T128,
-                      const int npairs) {
+                      const int npairs, const int a_stages, const int b_stages) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
   __shared__ uint64_t a_full[kPairAStages], a_empty[kPairAStages], b_full[kPairBStages], b_empty[kPairBStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
+  __shared__ uint64_t y_full[2], y_empty[2];  // norm-backward fold: Y quarter buffers
   __shared__ uint32_t tmem_base_sh;
   __shared__ __align__(16) float sbias[256];
 
@@ -500,8 +506,10 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const uint32_t rank = cluster_ctarank();
   const int ncl = gridDim.x >> 1, cl = blockIdx.x >> 1;
   uint8_t* smA = smem;
-  uint8_t* smB = smem + kPairAStages * kPairAStage;
-  float* epi = reinterpret_cast<float*>(smB + kPairBStages * kPairBStage);
+  uint8_t* smB = smem + a_stages * kPairAStage;
+  float* epi = reinterpret_cast<float*>(smB + b_stages * kPairBStage);
+  uint8_t* ybuf = reinterpret_cast<uint8_t*>(epi) + kPairEpiBytes;  // only carved when the launch folds (nr_Y != null)
+  const bool fold = p.nr_Y != nullptr;
   const int cchunks = p.Cin / kChunkK;
   const int total_tiles = p.B * T128;
   // debug stamps, 16 per CTA: [0] start, [1] set-up done, [2+k] MMAs of tile k issued (leader),
@@ -513,6 +521,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int s = 0; s < kPairAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kPairBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], kEpiWarps); }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmA8);
@@ -540,8 +549,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int b = gtc / T128, m0 = (gtc - b * T128) * kTileM;
         for (int r = 0; r < p.nruns; ++r)
           for (int cc = 0; cc < cchunks; ++cc, ++g) {
-            const int s = g % kPairAStages;
-            mbar_wait(&a_empty[s], ((g / kPairAStages) & 1) ^ 1, 1);
+            const int s = g % a_stages;
+            mbar_wait(&a_empty[s], ((g / a_stages) & 1) ^ 1, 1);
             uint8_t* sa = smA + s * kPairAStage;
             const int row0 = m0 + p.run_off[r];
             if (rank == 0) mbar_arrive_expect_tx(&a_full[s], 2 * kPairAStage);
@@ -559,8 +568,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int r = 0, t0 = 0; r < p.nruns; t0 += p.run_len[r], ++r)
           for (int cc = 0; cc < cchunks; ++cc)
             for (int q = 0; q < p.run_len[r]; ++q, ++it) {
-              const int s = it % kPairBStages;
-              mbar_wait(&b_empty[s], ((it / kPairBStages) & 1) ^ 1, 4);
+              const int s = it % b_stages;
+              mbar_wait(&b_empty[s], ((it / b_stages) & 1) ^ 1, 4);
               if (rank == 0) mbar_arrive_expect_tx(&b_full[s], 2 * kPairBStage);
               tma_load_2d_pair(&tmBh, mapa_u32(smem_u32(&b_full[s]), 0), smB + s * kPairBStage, cc * kChunkK,
                                int(p.run_w[t0 + q]) * p.CoutPad + int(rank) * 128);
@@ -579,13 +588,13 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         uint32_t acc = 0;
         for (int r = 0; r < p.nruns; ++r)
           for (int cc = 0; cc < cchunks; ++cc, ++g) {
-            const int sa_i = g % kPairAStages;
-            mbar_wait(&a_full[sa_i], (g / kPairAStages) & 1, 2);
+            const int sa_i = g % a_stages;
+            mbar_wait(&a_full[sa_i], (g / a_stages) & 1, 2);
             tc_fence_after();
             const uint32_t a_base = smem_u32(smA + sa_i * kPairAStage);
             for (int q = 0; q < p.run_len[r]; ++q, ++it) {
-              const int sb_i = it % kPairBStages;
-              mbar_wait(&b_full[sb_i], (it / kPairBStages) & 1, 5);
+              const int sb_i = it % b_stages;
+              mbar_wait(&b_full[sb_i], (it / b_stages) & 1, 5);
               tc_fence_after();
               const uint64_t bdesc = desc_kmajor_sw128(smem_u32(smB + sb_i * kPairBStage));
               const uint64_t adesc = desc_kmajor_sw128(a_base + uint32_t(q) * 128u);
@@ -600,6 +609,37 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         umma_commit_pair(&acc_full[buf]);
         if (dbg && k < 6) dbg[2 + k] = clock64();
+      }
+    }
+  } else if (warp == 3 + kEpiWarps) {
+    // ------------------------------------------------------------ norm-backward fold: Y rows of the tile, a quarter at a time
+    // Position m of the padded grid belongs to source pixel (reflect(i - pad), reflect(j - pad)); each lane fetches the
+    // 512-byte channel row of ITS position of the quarter with one bulk copy (contiguous runs are not merged: 128 small
+    // copies per 18k-cycle tile are far from the copy engine's limit).
+    if (fold) {
+      int qn = 0;
+      for (int j = cl; j < npairs; j += ncl) {
+        const int gt = 2 * j + int(rank);
+        const bool tile_ok = gt < total_tiles;
+        const int gtc = tile_ok ? gt : 0;
+        const int b = gtc / T128, t128 = gtc - b * T128;
+        for (int qq = 0; qq < 4; ++qq, ++qn) {
+          const int s = qn & 1;
+          mbar_wait(&y_empty[s], ((qn >> 1) & 1) ^ 1, 7);
+          const int m = t128 * kTileM + qq * 32 + lane;
+          const int i = m / p.P, jj = m - i * p.P;
+          const bool valid = tile_ok && (m < p.M) && (i < p.Hv) && (jj < p.Wv);
+          const unsigned vm = __ballot_sync(0xffffffffu, valid);
+          if (lane == 0) mbar_arrive_expect_tx(&y_full[s], uint32_t(__popc(vm)) * 512u);
+          __syncwarp();
+          if (valid) {
+            int ri = i - p.nr_pad, rj = jj - p.nr_pad;
+            ri = ri < 0 ? -ri : (ri >= p.nr_H ? 2 * (p.nr_H - 1) - ri : ri);
+            rj = rj < 0 ? -rj : (rj >= p.nr_W ? 2 * (p.nr_W - 1) - rj : rj);
+            bulk_load_1d(ybuf + s * kPairYQuarter + lane * 512, p.nr_Y + ((int64_t(b) * p.nr_H + ri) * p.nr_W + rj) * 256, 512u,
+                         &y_full[s]);
+          }
+        }
       }
     }
   } else if (warp < 3 + kEpiWarps) {
@@ -623,7 +663,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint8_t* S = reinterpret_cast<uint8_t*>(epi);
     float2* comb = reinterpret_cast<float2*>(S + kTileM * kPairStagePitch);               // [2][256]
     long long* rowoff = reinterpret_cast<long long*>(S + kTileM * kPairStagePitch + 4096);  // [128]
-    int k = 0;
+    int k = 0, yq = 0;
     for (int j = cl; j < npairs; j += ncl, ++k) {
       const int buf = k & 1;
       const int gt = 2 * j + int(rank);
@@ -689,6 +729,53 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (has_stats && tile_ok)  // tile_ok is uniform over the CTA
           staged_stats(S, kPairStagePitch, 256, kEpiThreads, et, comb, 2,
                        reinterpret_cast<float2*>(p.stats) + (int64_t(b) * p.stats_T + p.stats_t0 + t128) * p.Cout);
+        if (fold) {
+          // (sum dz, sum dz * xhat) of this tile per channel: thread (cp, hh) owns channels 2cp, 2cp + 1 and rows
+          // hh * 16 .. hh * 16 + 15 of every quarter; dX comes from the staged bf16 tile (the value as stored, what the
+          // apply pass will read back), Y from the quarter buffers.  Same expressions as glue_rows.cu BWD_REDUCE.
+          const int cp = et & 127, hh = et >> 7;
+          float mu0 = 0.f, mu1 = 0.f, rs0 = 1.f, rs1 = 1.f, sc0 = 1.f, sc1 = 1.f, be0 = 0.f, be1 = 0.f;
+          if (tile_ok) {
+            const float n = float(p.nr_H) * float(p.nr_W);
+            const float4 st = __ldg(reinterpret_cast<const float4*>(p.nr_stats) + (int64_t(b) * 256 + 2 * cp) / 2);
+            const float2 ga = __ldg(reinterpret_cast<const float2*>(p.nr_gamma) + cp);
+            const float2 bt = __ldg(reinterpret_cast<const float2*>(p.nr_beta) + cp);
+            mu0 = st.x / n; rs0 = rsqrtf(fmaxf(st.y / n - mu0 * mu0, 0.f) + p.nr_eps);
+            mu1 = st.z / n; rs1 = rsqrtf(fmaxf(st.w / n - mu1 * mu1, 0.f) + p.nr_eps);
+            sc0 = ga.x * rs0; sc1 = ga.y * rs1; be0 = bt.x; be1 = bt.y;
+          }
+          const float gneg = p.nr_gneg;
+          float a10 = 0.f, a20 = 0.f, a11 = 0.f, a21 = 0.f;
+          for (int qq = 0; qq < 4; ++qq, ++yq) {
+            const int s = yq & 1;
+            mbar_wait(&y_full[s], (yq >> 1) & 1, 8);
+            const uint8_t* yb = ybuf + s * kPairYQuarter;
+#pragma unroll 4
+            for (int r = 0; r < 16; ++r) {
+              const int rq = hh * 16 + r, rt = qq * 32 + rq;
+              if (rowoff[rt] < 0) continue;  // outside the image: no copy was made for this row
+              const uint32_t dw = *reinterpret_cast<const uint32_t*>(S + rt * kPairStagePitch + cp * 4);
+              const uint32_t yw = *reinterpret_cast<const uint32_t*>(yb + rq * 512 + cp * 4);
+              const float d0 = __uint_as_float(dw << 16), d1 = __uint_as_float(dw & 0xffff0000u);
+              const float yc0 = __uint_as_float(yw << 16) - mu0, yc1 = __uint_as_float(yw & 0xffff0000u) - mu1;
+              const float dz0 = fmaf(yc0, sc0, be0) > 0.f ? d0 : d0 * gneg;
+              const float dz1 = fmaf(yc1, sc1, be1) > 0.f ? d1 : d1 * gneg;
+              a10 += dz0; a20 = fmaf(dz0, yc0, a20);
+              a11 += dz1; a21 = fmaf(dz1, yc1, a21);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&y_empty[s]);
+          }
+          // the two row halves, in order; comb is free (a dgrad launch takes no forward statistics)
+          float4* c4 = reinterpret_cast<float4*>(comb);
+          if (hh == 1) c4[cp] = make_float4(a10, a20 * rs0, a11, a21 * rs1);
+          named_bar_sync(2, kEpiThreads);
+          if (hh == 0 && tile_ok) {
+            const float4 o = c4[cp];
+            float4* dst = reinterpret_cast<float4*>(p.nr_part) + (int64_t(b) * T128 + t128) * 128 + cp;
+            *dst = make_float4(a10 + o.x, a20 * rs0 + o.y, a11 + o.z, a21 * rs1 + o.w);
+          }
+        }
         if (dbg && et == 0 && k < 6) dbg[8 + k] = clock64();
         continue;
       }
@@ -1415,6 +1502,10 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
       L->stat_tiles = T128;
       L->p.MT = 128;
     }
+    // norm-backward fold: only on the pair kernel's staged epilogue, for a plain (unit-scale) bf16 dgrad without statistics
+    L->nr_ok = (L->pair && p.nr_Y != nullptr && p.nr_part != nullptr && !p.out_f32 && (p.omap.C & 7) == 0 && p.Cout == 256 &&
+                p.stats == nullptr && p.o_scale == 1 && p.o_a == 0 && p.o_b == 0) ? 1 : 0;
+    if (!L->nr_ok) L->p.nr_Y = nullptr;
   }
   // transposed persistent kernel for layers with at most 128 output channels (bf16 output, one channel block)
   L->swap = 0;
@@ -1479,8 +1570,10 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
 int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
   if (L.pair) {
     const int clusters = L.npairs < 74 ? L.npairs : 74;  // one CTA pair per TPC (148 SMs)
-    cudaError_t e = launch_kernel_pdl(conv_gemm_pair_kernel, dim3(2 * clusters), dim3(kConvThreads), kPairSmem, st, pdl_enabled(),
-                                      L.tmA, L.tmA8, L.tmBh, L.p, L.T128, L.npairs);
+    cudaError_t e = launch_kernel_pdl(conv_gemm_pair_kernel, dim3(2 * clusters), dim3(kConvThreads),
+                                      size_t(L.nr_ok ? kPairFoldSmem : kPairSmem), st, pdl_enabled(), L.tmA, L.tmA8, L.tmBh, L.p,
+                                      L.T128, L.npairs, L.nr_ok ? kPairFoldAStages : kPairAStages,
+                                      L.nr_ok ? kPairFoldBStages : kPairBStages);
     return e == cudaSuccess ? 0 : -4100 - int(e);
   }
   if (L.swap) {

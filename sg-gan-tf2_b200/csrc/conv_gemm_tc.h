@@ -18,6 +18,7 @@ struct ConvGemmLaunch {
   size_t smem;
   int stat_tiles;          // 128-row statistics tiles per image this launch writes
   int pair, T128, npairs;  // CTA-pair persistent kernel (256-channel layers): tiles per image, pair tiles in all
+  int nr_ok = 0;           // the launch also folds the norm-backward sums of the layer below (ConvGemmParams::nr_*)
   CUtensorMap tmBh;        // 128-row weight tile (pair kernel: half of the channels; swap kernel: the M operand)
   int swap, T256, swap_pstages, swap_wstages, swap_nblk;  // transposed persistent kernel (<= 128 output channels): 256-pixel tiles per image
   size_t swap_smem;

@@ -232,12 +232,16 @@ static int layer_prepare_fwd_impl(Layer& l, const float* bias, void* out, const 
 }
 
 // dgrad launches: dX (plain, l.dxH x l.dxW x Cin) from the dY frames of images [b0, b0 + nimg).
-int layer_prepare_dgrad(Layer& l, int b0, int nimg, bool dry) {
+int layer_prepare_dgrad(Layer& l, int b0, int nimg, bool dry, const ConvGemmParams* nr = nullptr) {
   l.dgrad.clear();
   if (l.type == LT_WIN_C1) return 0;
   const int k = l.k, P = l.P;
   ConvGemmParams p;
   conv_common(p, l);
+  if (nr != nullptr && l.type == LT_S1) {  // fold the norm-backward sums of the layer below into this launch's epilogue
+    p.nr_Y = nr->nr_Y; p.nr_stats = nr->nr_stats; p.nr_gamma = nr->nr_gamma; p.nr_beta = nr->nr_beta; p.nr_part = nr->nr_part;
+    p.nr_eps = nr->nr_eps; p.nr_gneg = nr->nr_gneg; p.nr_H = nr->nr_H; p.nr_W = nr->nr_W; p.nr_pad = nr->nr_pad;
+  }
   const int Cdy = l.dymap.C;
   p.A = l.dY + int64_t(b0) * l.dymap.frame_pix * Cdy;
   p.a_frame_pix = l.dymap.frame_pix; p.a_row_stride = Cdy; p.B = nimg;
@@ -543,7 +547,25 @@ int Engine::prepare_layer(Net& n, int li) {
   if (r) return r;
   if (l.type == LT_WIN_H0) r = layer_prepare_dgrad(l, l.nb, l.nbv - l.nb, dry);
   else if (isG && li == 0) r = 0;
-  else r = layer_prepare_dgrad(l, 0, l.nbv, dry);
+  else {
+    // second convolution of a residual block: its dgrad produces the gradient w.r.t. pad(relu(norm(Y of the first
+    // convolution))) -- let that launch's epilogue accumulate the norm-backward sums of the first convolution's norm
+    // (SGGAN_FOLD_INRED=0: separate reduce pass)
+    static const bool fold_on = []() { const char* e = getenv("SGGAN_FOLD_INRED"); return !(e && e[0] == '0'); }();
+    const bool conv_b = isG && li >= 4 && li <= 3 + 2 * cfg.n_blocks - 1 && ((li - 3) & 1) == 1;
+    ConvGemmParams nr;
+    memset(&nr, 0, sizeof(nr));
+    Layer* below = conv_b ? &n.L[li - 1] : nullptr;
+    if (conv_b && fold_on && !dry && below->nr_part != nullptr && l.pad == PAD_REFLECT) {
+      nr.nr_Y = below->Y; nr.nr_stats = below->stats;
+      nr.nr_gamma = n.p + n.T[below->ti_g].offset; nr.nr_beta = n.p + n.T[below->ti_be].offset;
+      nr.nr_part = below->nr_part; nr.nr_eps = cfg.in_eps;
+      nr.nr_gneg = below->act == SG_ACT_RELU ? 0.f : (below->act == SG_ACT_LRELU ? below->alpha : 1.f);
+      nr.nr_H = below->Hout; nr.nr_W = below->Wout; nr.nr_pad = (l.k - 1) / 2;
+    }
+    r = layer_prepare_dgrad(l, 0, l.nbv, dry, nr.nr_Y ? &nr : nullptr);
+    if (below != nullptr) below->nr_T = (!dry && r == 0 && l.dgrad.size() == 1 && l.dgrad[0].nr_ok) ? l.dgrad[0].T128 : 0;
+  }
   if (r) return r;
   float* dW = n.g ? n.g + n.T[l.ti_w].offset : nullptr;
   return layer_prepare_wgrad(l, dW, l.nb, dry, wg_part, wg_part_elems);
@@ -600,6 +622,12 @@ int Engine::build(const sggan_config& c, void* ws, size_t ws_bytes, cudaStream_t
   wg_part = (float*)a.take(wg_part_elems * 4);
   step_dev = (long long*)a.take(sizeof(long long));
   in_part = (float*)a.take(in_bwd_partials_bytes(512));  // per-block partial sums of the norm-backward reduce pass
+  for (int li = 3; li + 1 <= 3 + 2 * c.n_blocks - 1; li += 2) {  // first convolution of every residual block (see prepare_layer)
+    Layer& la = G.L[li];
+    const Layer& lb = G.L[li + 1];
+    const int T = (lb.dxH * lb.P + 127) / 128;
+    la.nr_part = (float*)a.take(size_t(la.nbv) * T * la.Cout * 2 * 4);
+  }
   {
     const Layer& h0 = D.L[0];
     red_scratch = (float*)a.take(ordered_sum_scratch_floats(B, H, W, c.segment_class, h0.Cout, h0.Hout, h0.Wout, h0.nbv) * 4);
@@ -756,6 +784,14 @@ void Engine::in_bwd(Net& n, int li, const GradSrc& g1, const GradSrc& g2, int nb
     p.sync_ctr = l.bsync;
     const int r = launch_in_bwd_fused(p, st);
     if (r < 0 && glue_err == 0) glue_err = 5;
+    ++nlaunch;
+    return;
+  }
+  if (l.nr_T > 0 && gather_dst == nullptr && g2.ptr == nullptr) {
+    // the sums were accumulated per tile by the dgrad launch that produced g1 (its epilogue): apply pass only
+    p.sums_part = l.nr_part;
+    p.sums_nblk = l.nr_T;
+    if (launch_in_bwd_apply(p, st) < 0 && glue_err == 0) glue_err = 3;
     ++nlaunch;
     return;
   }

@@ -33,6 +33,8 @@ struct Layer {
   int nb, nbv;                // forward batch, backward (virtual) batch
   int ti_w, ti_b, ti_g, ti_be;  // tensor indices inside the net (-1 if absent)
   int P;                      // shared pitch of the input frame and the output-gradient frame
+  float* nr_part = nullptr;   // norm-backward sums of THIS layer's norm, per tile of the dgrad launch of the layer above that
+  int nr_T = 0;               // produced them in its epilogue (ConvGemmParams::nr_*); nr_T = tiles per image, 0 = not folded
   int CoutK;                  // Cout padded to a multiple of 64 (channels of the dY frame)
   int CoutN;                  // rows per weight slab in the forward GEMM
   int CinN;                   // rows per weight slab in the dgrad GEMM

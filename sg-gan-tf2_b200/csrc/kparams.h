@@ -97,6 +97,19 @@ struct ConvGemmParams {
   // tf32 mode (the fp32-accurate tier): A and Wt hold fp32 elements (pre-rounded to tf32), K per tap is a multiple of 32,
   // the tensor cores run kind::tf32, the output is fp32.  conv_gemm_tc_kernel only.
   int tf32;
+  // CTA-pair kernel, dgrad launches only (nr_Y != null): this launch produces the gradient w.r.t. the padded input grid
+  // of a convolution whose input is act(instance_norm(Y)) + a reflect border of nr_pad pixels.  The epilogue then also
+  // accumulates that norm layer's backward sums per 128-position tile and channel: (sum dz, sum dz * xhat) with
+  // dz = act'(z) * dX at the source pixel of every (reflected) grid position -- the "reduce" pass of the norm backward
+  // (glue_rows.cu BWD_REDUCE) without re-reading dX.  nr_part: [B][tiles per image][C][2]; nr_gneg: slope of the
+  // activation on its non-positive side (ReLU 0, LeakyReLU alpha, none 1).
+  const sg_bf16* nr_Y;      // [B][nr_H][nr_W][Cout] raw convolution output of the layer below
+  const float* nr_stats;    // [B][Cout][2] (sum y, sum y^2)
+  const float* nr_gamma;
+  const float* nr_beta;
+  float* nr_part;
+  float nr_eps, nr_gneg;
+  int nr_H, nr_W, nr_pad;
   long long* dbg;  // optional per-CTA clock64 stamps [grid][8] (tests/gpu/tc_probe.cu); null in production
 };
 
