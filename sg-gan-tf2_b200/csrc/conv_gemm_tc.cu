@@ -481,24 +481,30 @@ constexpr int kPairEpiTile = 32 * 33 * 4;                       // one warp's tr
 constexpr int kPairStagePitch = 256 * 2 + 16;
 constexpr int kPairEpiBytes = kTileM * kPairStagePitch + 4096 + 1024;
 static_assert(kPairEpiBytes >= kEpiWarps * kPairEpiTile + 2 * 4 * 256 * 8, "fallback epilogue scratch");
-constexpr int kPairAStages = 3, kPairBStages = 6;  // (maximum; a launch that also folds the norm-backward sums runs 2 + 5)
+constexpr int kPairAStages = 3, kPairBStages = 6;  // (maximum; a launch that also folds the norm-backward sums runs 3 + 4)
 constexpr int kPairAStage = (kTileM + kHaloRows) * 128, kPairBStage = 128 * 128;
 constexpr int kPairSmem = kPairAStages * kPairAStage + kPairBStages * kPairBStage + kPairEpiBytes + 1024;
-// norm-backward fold: the Y rows matching a quarter of the tile (32 positions x 512 B), double buffered
-constexpr int kPairYQuarter = 32 * 512;
-constexpr int kPairFoldAStages = 2, kPairFoldBStages = 5;
-constexpr int kPairFoldSmem = kPairFoldAStages * kPairAStage + kPairFoldBStages * kPairBStage + kPairEpiBytes + 2 * kPairYQuarter + 1024;
+// norm-backward fold: the Y rows matching a slab of the tile (32 positions x 512 B, one per lane of the staging warp),
+// double buffered
+constexpr int kPairYRows = 32, kPairYSlab = kPairYRows * 512, kPairYBufs = 2, kPairYSlabs = kTileM / kPairYRows;
+constexpr int kPairFoldAStages = 3, kPairFoldBStages = 4;
+constexpr int kPairFoldSmem = kPairFoldAStages * kPairAStage + kPairFoldBStages * kPairBStage + kPairEpiBytes + kPairYBufs * kPairYSlab + 1024;
 static_assert(kPairFoldSmem <= kPairSmem, "the fold variant must fit the same shared-memory opt-in");
 
+// FOLD: the launch also accumulates the norm-backward sums of the layer below (ConvGemmParams::nr_*); it then runs 3 + 4
+// pipeline stages instead of 3 + 6 to make room for the Y slab buffers (2 + 5 measured 4 us slower per launch).  Compile-time, because the ring indices
+// (g % stages, g / stages) sit in the single-thread MMA issue loop: as run-time divisions they cost 15 % of the kernel.
+template <bool FOLD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kConvThreads, 1)
 conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA8,
                       const __grid_constant__ CUtensorMap tmBh, const ConvGemmParams p, const int T128,
-                      const int npairs, const int a_stages, const int b_stages) {
+                      const int npairs) {
+  constexpr int a_stages = FOLD ? kPairFoldAStages : kPairAStages, b_stages = FOLD ? kPairFoldBStages : kPairBStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
   __shared__ uint64_t a_full[kPairAStages], a_empty[kPairAStages], b_full[kPairBStages], b_empty[kPairBStages];
   __shared__ uint64_t acc_full[2], acc_empty[2];
-  __shared__ uint64_t y_full[2], y_empty[2];  // norm-backward fold: Y quarter buffers
+  __shared__ uint64_t y_full[kPairYBufs], y_empty[kPairYBufs];  // norm-backward fold: Y slab buffers
   __shared__ uint32_t tmem_base_sh;
   __shared__ __align__(16) float sbias[256];
 
@@ -509,7 +515,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint8_t* smB = smem + a_stages * kPairAStage;
   float* epi = reinterpret_cast<float*>(smB + b_stages * kPairBStage);
   uint8_t* ybuf = reinterpret_cast<uint8_t*>(epi) + kPairEpiBytes;  // only carved when the launch folds (nr_Y != null)
-  const bool fold = p.nr_Y != nullptr;
+  constexpr bool fold = FOLD;
   const int cchunks = p.Cin / kChunkK;
   const int total_tiles = p.B * T128;
   // debug stamps, 16 per CTA: [0] start, [1] set-up done, [2+k] MMAs of tile k issued (leader),
@@ -521,7 +527,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int s = 0; s < kPairAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < kPairBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 2 * kEpiWarps); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], kEpiWarps); }
+    for (int s = 0; s < kPairYBufs; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], kEpiWarps); }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmA8);
@@ -612,10 +618,12 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else if (warp == 3 + kEpiWarps) {
-    // ------------------------------------------------------------ norm-backward fold: Y rows of the tile, a quarter at a time
-    // Position m of the padded grid belongs to source pixel (reflect(i - pad), reflect(j - pad)); each lane fetches the
-    // 512-byte channel row of ITS position of the quarter with one bulk copy (contiguous runs are not merged: 128 small
-    // copies per 18k-cycle tile are far from the copy engine's limit).
+    // ------------------------------------------------------------ norm-backward fold: Y rows of the tile, a slab at a time
+    // Position m of the padded grid belongs to source pixel (reflect(i - pad), reflect(j - pad)).  Lane r of this warp owns
+    // position r of the slab; runs of positions whose source rows are consecutive in memory (the interior of a grid row;
+    // reflected border positions stand alone) are found with two ballots, and only the FIRST lane of a run issues a bulk
+    // copy, for the whole run: 1-4 copies per slab instead of 32 (per-lane copies serialise in the issue loop: measured
+    // ~3k cycles per slab, which made the kernel epilogue-bound).
     if (fold) {
       int qn = 0;
       for (int j = cl; j < npairs; j += ncl) {
@@ -623,21 +631,30 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const bool tile_ok = gt < total_tiles;
         const int gtc = tile_ok ? gt : 0;
         const int b = gtc / T128, t128 = gtc - b * T128;
-        for (int qq = 0; qq < 4; ++qq, ++qn) {
-          const int s = qn & 1;
-          mbar_wait(&y_empty[s], ((qn >> 1) & 1) ^ 1, 7);
-          const int m = t128 * kTileM + qq * 32 + lane;
+        const sg_bf16* yimg = p.nr_Y + int64_t(b) * p.nr_H * p.nr_W * 256;
+        for (int qq = 0; qq < kPairYSlabs; ++qq, ++qn) {
+          const int s = qn % kPairYBufs;
+          if (lane == 0) mbar_wait(&y_empty[s], ((qn / kPairYBufs) & 1) ^ 1, 7);
+          __syncwarp();
+          const int m = t128 * kTileM + qq * kPairYRows + lane;
           const int i = m / p.P, jj = m - i * p.P;
           const bool valid = tile_ok && (m < p.M) && (i < p.Hv) && (jj < p.Wv);
-          const unsigned vm = __ballot_sync(0xffffffffu, valid);
-          if (lane == 0) mbar_arrive_expect_tx(&y_full[s], uint32_t(__popc(vm)) * 512u);
-          __syncwarp();
+          int src = -1;
           if (valid) {
             int ri = i - p.nr_pad, rj = jj - p.nr_pad;
             ri = ri < 0 ? -ri : (ri >= p.nr_H ? 2 * (p.nr_H - 1) - ri : ri);
             rj = rj < 0 ? -rj : (rj >= p.nr_W ? 2 * (p.nr_W - 1) - rj : rj);
-            bulk_load_1d(ybuf + s * kPairYQuarter + lane * 512, p.nr_Y + ((int64_t(b) * p.nr_H + ri) * p.nr_W + rj) * 256, 512u,
-                         &y_full[s]);
+            src = ri * p.nr_W + rj;
+          }
+          const int prev = __shfl_up_sync(0xffffffffu, src, 1);
+          const bool start = valid && (lane == 0 || prev < 0 || src != prev + 1);
+          const unsigned vm = __ballot_sync(0xffffffffu, valid), sm = __ballot_sync(0xffffffffu, start);
+          if (lane == 0) mbar_arrive_expect_tx(&y_full[s], uint32_t(__popc(vm)) * 512u);
+          __syncwarp();
+          if (start) {
+            const unsigned after = lane == 31 ? 0u : ((sm | ~vm) >> (lane + 1));  // later positions that end this run
+            const int len = after ? __ffs(after) : 32 - lane;
+            bulk_load_1d(ybuf + s * kPairYSlab + lane * 512, yimg + int64_t(src) * 256, uint32_t(len) * 512u, &y_full[s]);
           }
         }
       }
@@ -731,7 +748,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                        reinterpret_cast<float2*>(p.stats) + (int64_t(b) * p.stats_T + p.stats_t0 + t128) * p.Cout);
         if (fold) {
           // (sum dz, sum dz * xhat) of this tile per channel: thread (cp, hh) owns channels 2cp, 2cp + 1 and rows
-          // hh * 16 .. hh * 16 + 15 of every quarter; dX comes from the staged bf16 tile (the value as stored, what the
+          // hh * 16 .. hh * 16 + 15 of every 32-row slab; dX comes from the staged bf16 tile (the value as stored, what the
           // apply pass will read back), Y from the quarter buffers.  Same expressions as glue_rows.cu BWD_REDUCE.
           const int cp = et & 127, hh = et >> 7;
           float mu0 = 0.f, mu1 = 0.f, rs0 = 1.f, rs1 = 1.f, sc0 = 1.f, sc1 = 1.f, be0 = 0.f, be1 = 0.f;
@@ -746,18 +763,29 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
           const float gneg = p.nr_gneg;
           float a10 = 0.f, a20 = 0.f, a11 = 0.f, a21 = 0.f;
-          for (int qq = 0; qq < 4; ++qq, ++yq) {
-            const int s = yq & 1;
-            mbar_wait(&y_full[s], (yq >> 1) & 1, 8);
-            const uint8_t* yb = ybuf + s * kPairYQuarter;
-#pragma unroll 4
-            for (int r = 0; r < 16; ++r) {
-              const int rq = hh * 16 + r, rt = qq * 32 + rq;
-              if (rowoff[rt] < 0) continue;  // outside the image: no copy was made for this row
-              const uint32_t dw = *reinterpret_cast<const uint32_t*>(S + rt * kPairStagePitch + cp * 4);
-              const uint32_t yw = *reinterpret_cast<const uint32_t*>(yb + rq * 512 + cp * 4);
+          for (int qq = 0; qq < kPairYSlabs; ++qq, ++yq) {
+            const int s = yq % kPairYBufs;
+            if (lane == 0) mbar_wait(&y_full[s], (yq / kPairYBufs) & 1, 8);  // one poller per warp: 256 spinning threads slow
+            __syncwarp();                                                     // the shared-memory pipe the MMAs read from
+            const uint8_t* yb = ybuf + s * kPairYSlab;
+            // branch-free over the 16 rows (independent loads first, so that they pipeline): rows outside the image carry
+            // no copy -- their dX is zero in the staged tile and their Y is masked here
+            const int rq0 = hh * (kPairYRows / 2), rt0 = qq * kPairYRows + rq0;
+            uint32_t okm = 0;
+#pragma unroll
+            for (int r = 0; r < kPairYRows / 2; ++r) okm |= (rowoff[rt0 + r] >= 0 ? 1u : 0u) << r;
+            uint32_t dwv[kPairYRows / 2], ywv[kPairYRows / 2];
+#pragma unroll
+            for (int r = 0; r < kPairYRows / 2; ++r) {
+              dwv[r] = *reinterpret_cast<const uint32_t*>(S + (rt0 + r) * kPairStagePitch + cp * 4);
+              ywv[r] = *reinterpret_cast<const uint32_t*>(yb + (rq0 + r) * 512 + cp * 4);
+            }
+#pragma unroll
+            for (int r = 0; r < kPairYRows / 2; ++r) {
+              const bool ok = (okm >> r) & 1u;
+              const uint32_t dw = dwv[r], yw = ok ? ywv[r] : 0u;
               const float d0 = __uint_as_float(dw << 16), d1 = __uint_as_float(dw & 0xffff0000u);
-              const float yc0 = __uint_as_float(yw << 16) - mu0, yc1 = __uint_as_float(yw & 0xffff0000u) - mu1;
+              const float yc0 = ok ? __uint_as_float(yw << 16) - mu0 : 0.f, yc1 = ok ? __uint_as_float(yw & 0xffff0000u) - mu1 : 0.f;
               const float dz0 = fmaf(yc0, sc0, be0) > 0.f ? d0 : d0 * gneg;
               const float dz1 = fmaf(yc1, sc1, be1) > 0.f ? d1 : d1 * gneg;
               a10 += dz0; a20 = fmaf(dz0, yc0, a20);
@@ -1558,7 +1586,9 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmemBudget + 1024);
     if (e != cudaSuccess) return -3000 - int(e);
-    e = cudaFuncSetAttribute(conv_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
+    e = cudaFuncSetAttribute(conv_gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
+    if (e != cudaSuccess) return -3100 - int(e);
+    e = cudaFuncSetAttribute(conv_gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairFoldSmem);
     if (e != cudaSuccess) return -3100 - int(e);
     e = cudaFuncSetAttribute(conv_gemm_swap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) return -3200 - int(e);
@@ -1570,10 +1600,10 @@ int prepare_conv_gemm(const ConvGemmParams& pin, ConvGemmLaunch* L) {
 int run_conv_gemm(const ConvGemmLaunch& L, cudaStream_t st) {
   if (L.pair) {
     const int clusters = L.npairs < 74 ? L.npairs : 74;  // one CTA pair per TPC (148 SMs)
-    cudaError_t e = launch_kernel_pdl(conv_gemm_pair_kernel, dim3(2 * clusters), dim3(kConvThreads),
-                                      size_t(L.nr_ok ? kPairFoldSmem : kPairSmem), st, pdl_enabled(), L.tmA, L.tmA8, L.tmBh, L.p,
-                                      L.T128, L.npairs, L.nr_ok ? kPairFoldAStages : kPairAStages,
-                                      L.nr_ok ? kPairFoldBStages : kPairBStages);
+    cudaError_t e = L.nr_ok ? launch_kernel_pdl(conv_gemm_pair_kernel<true>, dim3(2 * clusters), dim3(kConvThreads),
+                                                size_t(kPairFoldSmem), st, pdl_enabled(), L.tmA, L.tmA8, L.tmBh, L.p, L.T128, L.npairs)
+                            : launch_kernel_pdl(conv_gemm_pair_kernel<false>, dim3(2 * clusters), dim3(kConvThreads),
+                                                size_t(kPairSmem), st, pdl_enabled(), L.tmA, L.tmA8, L.tmBh, L.p, L.T128, L.npairs);
     return e == cudaSuccess ? 0 : -4100 - int(e);
   }
   if (L.swap) {

@@ -120,6 +120,35 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
   p.act = c.act;
   p.act_alpha = 0.3f;
   p.MT = c.MT;
+  // PROBE_FOLD=1: the launch also accumulates the norm-backward sums of a layer "below" whose raw output is nrY (identity
+  // position map: nr_pad = 0), as the engine's dgrad launches do for the residual blocks (ConvGemmParams::nr_*)
+  const bool probe_fold = getenv("PROBE_FOLD") && getenv("PROBE_FOLD")[0] == '1' && !c.use_stats && !c.out_f32;
+  std::vector<uint16_t> hY;
+  std::vector<float> hNs, hG, hBe;
+  uint16_t* dNY = nullptr;
+  float *dNs = nullptr, *dG = nullptr, *dBe = nullptr, *dNpart = nullptr;
+  if (probe_fold) {
+    hY.resize(out_elems);
+    for (auto& v : hY) v = f2bf(frand() * 2.f);
+    hNs.resize(size_t(c.B) * c.Cout * 2);
+    hG.resize(c.Cout);
+    hBe.resize(c.Cout);
+    const float n = float(c.H) * c.W;
+    for (int q = 0; q < c.B * c.Cout; ++q) { const float mu = 0.2f * frand(); hNs[2 * q] = mu * n; hNs[2 * q + 1] = (mu * mu + 0.5f + 0.3f * frand()) * n; }
+    for (int q = 0; q < c.Cout; ++q) { hG[q] = 1.f + 0.3f * frand(); hBe[q] = 0.3f * frand(); }
+    CK(cudaMalloc(&dNY, hY.size() * 2));
+    CK(cudaMalloc(&dNs, hNs.size() * 4));
+    CK(cudaMalloc(&dG, c.Cout * 4));
+    CK(cudaMalloc(&dBe, c.Cout * 4));
+    CK(cudaMalloc(&dNpart, size_t(c.B) * Tmax * c.Cout * 2 * 4));
+    CK(cudaMemcpy(dNY, hY.data(), hY.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dNs, hNs.data(), hNs.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dG, hG.data(), c.Cout * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dBe, hBe.data(), c.Cout * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dNpart, 0, size_t(c.B) * Tmax * c.Cout * 2 * 4));
+    p.nr_Y = reinterpret_cast<const sg_bf16*>(dNY); p.nr_stats = dNs; p.nr_gamma = dG; p.nr_beta = dBe; p.nr_part = dNpart;
+    p.nr_eps = 1e-3f; p.nr_gneg = 0.f; p.nr_H = c.H; p.nr_W = c.W; p.nr_pad = 0;
+  }
 
   ConvGemmLaunch L;
   int r = prepare_conv_gemm(p, &L);
@@ -192,6 +221,39 @@ static int run_conv_case(const ConvCase& c, int iters, bool full_check) {
   }
   printf("conv check: %lld positions, max_err %.4g (max |ref| %.3g), bad %d\n", (long long)nsample, max_err,
          max_ref, bad);
+  if (probe_fold) {
+    printf("norm-backward fold: %s\n", L.nr_ok ? "active" : "NOT taken by this launch");
+    if (L.nr_ok) {
+      // per (image, channel): sum over tiles of the partials against a CPU loop over the STORED output (bf16) and nrY
+      std::vector<float> part(size_t(c.B) * L.T128 * c.Cout * 2);
+      CK(cudaMemcpy(part.data(), dNpart, part.size() * 4, cudaMemcpyDeviceToHost));
+      const float n = float(c.H) * c.W;
+      double worst = 0;
+      for (int b = 0; b < c.B; ++b)
+        for (int ch = 0; ch < c.Cout; ch += 37) {
+          const float mu = hNs[(size_t(b) * c.Cout + ch) * 2] / n;
+          const float rs = 1.f / sqrtf(fmaxf(hNs[(size_t(b) * c.Cout + ch) * 2 + 1] / n - mu * mu, 0.f) + 1e-3f);
+          double r1 = 0, r2 = 0, g1 = 0, g2 = 0;
+          for (int i = 0; i < c.H; ++i)
+            for (int j = 0; j < c.W; ++j) {
+              const size_t oi = ((size_t(b) * c.H + i) * c.W + j) * c.Cout + ch;
+              const float d = bf2f(reinterpret_cast<uint16_t*>(hOut.data())[oi]);
+              const float yc = bf2f(hY[oi]) - mu;
+              const float dz = (yc * (hG[ch] * rs) + hBe[ch]) > 0.f ? d : 0.f;
+              r1 += dz;
+              r2 += double(dz) * yc * rs;
+            }
+          for (int t = 0; t < L.T128; ++t) {
+            g1 += part[((size_t(b) * L.T128 + t) * c.Cout + ch) * 2];
+            g2 += part[((size_t(b) * L.T128 + t) * c.Cout + ch) * 2 + 1];
+          }
+          worst = fmax(worst, fabs(g1 - r1) / (fabs(r1) + 1.0));
+          worst = fmax(worst, fabs(g2 - r2) / (fabs(r2) + 1.0));
+        }
+      printf("fold check: max rel err %.4g\n", worst);
+      if (worst > 2e-3) ++bad;
+    }
+  }
   if (c.use_stats && full_check) {
     double se = 0;
     for (size_t q = 0; q < s1.size(); ++q) {
@@ -814,6 +876,12 @@ int main(int argc, char** argv) {
   } else if (!strcmp(t, "conv_res")) {
     ConvCase c = {8, 64, 128, 256, 256, 256, 256, 3, SG_ACT_NONE, 0, 1};
     rc = run_conv_case(c, 20, false);
+  } else if (!strcmp(t, "conv_res_nostats")) {  // the dgrad-like form of conv_res (no statistics): PROBE_FOLD=1 adds the fold
+    ConvCase c = {8, 64, 128, 256, 256, 256, 256, 3, SG_ACT_NONE, 0, 0};
+    rc = run_conv_case(c, 20, false);
+  } else if (!strcmp(t, "conv_fold_check")) {  // odd tile count, ragged last tile, every position checked
+    ConvCase c = {3, 51, 126, 64, 256, 256, 256, 3, SG_ACT_NONE, 0, 0};
+    rc = run_conv_case(c, 0, true);
   } else if (!strcmp(t, "conv_pair_check")) {
     ConvCase c = {2, 80, 128, 64, 256, 256, 256, 3, SG_ACT_LRELU, 0, 1};
     rc = run_conv_case(c, 0, true);

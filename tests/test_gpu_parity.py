@@ -543,6 +543,10 @@ def test_tc_probe_pair_kernel():
         out = subprocess.run([exe, case], capture_output=True, text=True, timeout=300, env=env)
         assert out.returncode == 0 and "CTA-pair persistent kernel" in out.stdout and ("RESULT %s PASS" % case) in out.stdout, \
             out.stdout[-2000:]
+    # the dgrad epilogue that also accumulates the norm-backward sums of the layer below (odd tile count, ragged last tile)
+    out = subprocess.run([exe, "conv_fold_check"], capture_output=True, text=True, timeout=300, env=dict(env, PROBE_FOLD="1"))
+    assert out.returncode == 0 and "norm-backward fold: active" in out.stdout and "RESULT conv_fold_check PASS" in out.stdout, \
+        out.stdout[-2000:]
     for case in ("wgrad_pair_small", "wgrad_pair_wide"):
         out = subprocess.run([exe, case], capture_output=True, text=True, timeout=300, env=env)
         assert out.returncode == 0 and "(CTA-pair kernel)" in out.stdout and ("RESULT %s PASS" % case) in out.stdout, out.stdout[-2000:]
