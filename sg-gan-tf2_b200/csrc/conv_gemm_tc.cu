@@ -765,8 +765,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           float a10 = 0.f, a20 = 0.f, a11 = 0.f, a21 = 0.f;
           for (int qq = 0; qq < kPairYSlabs; ++qq, ++yq) {
             const int s = yq % kPairYBufs;
-            if (lane == 0) mbar_wait(&y_full[s], (yq / kPairYBufs) & 1, 8);  // one poller per warp: 256 spinning threads slow
-            __syncwarp();                                                     // the shared-memory pipe the MMAs read from
+            mbar_wait(&y_full[s], (yq / kPairYBufs) & 1, 8);
             const uint8_t* yb = ybuf + s * kPairYSlab;
             // branch-free over the 16 rows (independent loads first, so that they pipeline): rows outside the image carry
             // no copy -- their dX is zero in the staged tile and their Y is masked here
