@@ -4,14 +4,24 @@
 //                          pitch-linearised frames: TMA boxes -> smem (SWIZZLE_128B) ->
 //                          tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> staged epilogue (bias, act,
 //                          bf16 tile in smem, bulk async stores, per-(image,channel) sum / sum^2
-//                          partials for instance norm).  Used for Cout >= 256 and fp32 outputs.
+//                          partials for instance norm).  Used for Cout > 256, fp32 outputs and, with
+//                          kind::tf32 on fp32 frames, for the fp32-accurate operator tier.
+//   conv_gemm_pair_kernel  the 256-channel layers (the residual blocks: 80 % of the FLOPs) on CTA pairs,
+//                          tcgen05.mma.cta_group::2 with M = 256 over the pair, each CTA staging half of every
+//                          weight tile; persistent, TMEM double-buffered, staged epilogue.  MMAs retire at the
+//                          hardware rate (128 cycles per 128x256x16).  <true>: the dgrad form that also
+//                          accumulates the norm-backward sums of the layer below in its epilogue.
 //   conv_gemm_swap_kernel  the same operation with the operand roles exchanged (weights = M, 256 pixels
 //                          = N), persistent with two TMEM accumulators: layers with Cout <= 128 and
 //                          the 7x7 output convolution in shift-sum form.
-//   conv_gemm_pair_kernel  CTA-pair (cta_group::2) persistent variant for 256-channel layers; opt-in.
-//   wgrad_gemm_tc_kernel   weight gradient: MN-major operands (pixels are K), split-K over
+//   wgrad_gemm_pair_kernel weight gradient of the 256 x 256-channel layers on CTA pairs, two taps per CTA
+//                          sharing the dY half tile.
+//   wgrad_gemm_tc_kernel   the other weight gradients: MN-major operands (pixels are K), split-K over
 //                          images x pixel chunks into fp32 partial tiles, added in a fixed order by
 //                          wgrad_reduce_kernel.
+//
+// Every tcgen05 / TMA issue loop runs under elect_one_sync() (tc_common.cuh): under `if (lane == 0)` ptxas wraps each
+// UTCHMMA in an ELECT / BRA.U.ANY loop, which costs 22 % of the issue rate (156 instead of 128 cycles per MMA).
 //
 // Replaces the cuDNN/Eigen calls behind tf.keras.layers.Conv2D / Conv2DTranspose and their
 // gradients on the reference path (module.py:211-216,232-265,284-311; model.py:196-197).
@@ -897,8 +907,9 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 // =============================================================================================
 // Transposed ("swap A/B") persistent kernel for layers with at most 128 output channels.
 //
-// tcgen05.mma costs ~156 cycles per instruction whatever N is (tc_probe mma_rate), so an M = 128 pixels x
-// N = Cout <= 128 instruction wastes half (Cout 128) or three quarters (Cout 64) of the tensor pipe.  Here
+// An M = 128 pixels x N = Cout <= 128 instruction does not fill the tensor pipe (tc_probe mma_rate: 74 cycles at N = 128,
+// 63 at N = 64 against the ideal 64 / 32; the "156 cycles whatever N is" this kernel was first designed around was the
+// issue-loop artefact described at the top of the file).  Here
 // the roles are exchanged: the WEIGHT tile is the M operand (128 channel rows, zero/garbage rows above
 // Cout are never stored) and 256 PIXELS are the N operand, so every instruction is a full 128 x 256 x 16.
 // Both operands are K-major SWIZZLE_128B tiles either way, and the row-shifted descriptor that walks the
