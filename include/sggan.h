@@ -86,6 +86,11 @@ int sggan_disc_forward(sggan_handle* h, const float* x, const float* mask, float
 int sggan_step_forward_backward_d(sggan_handle* h, const float* real_A, const float* seg_A, const float* mask,
                                   float* losses_out);
 int sggan_step_backward_g(sggan_handle* h);
+/* The same backward in two parts, for data parallelism: after part 0 the generator gradients from element
+ * sggan_grad_split_offset(h) to the end of the flat buffer (sggan_flat_buffer(h, SGGAN_NET_G, 1): the middle residual block
+ * and every layer above it) are final, so their all-reduce runs underneath part 1, which produces the rest. */
+int sggan_step_backward_g_part(sggan_handle* h, int part);
+int64_t sggan_grad_split_offset(const sggan_handle* h);
 int sggan_step_adam(sggan_handle* h, int net);
 /* Same update, issued on the handle's internal side stream so that it overlaps whatever the caller enqueues next
  * (the data-parallel trainer updates D this way while G's all-reduce is in flight).  The next sggan_step_adam /

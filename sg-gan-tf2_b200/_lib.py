@@ -55,6 +55,8 @@ SYMBOLS = {
     "sggan_disc_forward": (_I, [_P, _P, _P, _P]),
     "sggan_step_forward_backward_d": (_I, [_P, _P, _P, _P, _P]),
     "sggan_step_backward_g": (_I, [_P]),
+    "sggan_step_backward_g_part": (_I, [_P, _I]),
+    "sggan_grad_split_offset": (_I64, [_P]),
     "sggan_step_adam": (_I, [_P, _I]),
     "sggan_step_adam_async": (_I, [_P, _I]),
     "sggan_train_step": (_I, [_P, _P, _P, _P, _P]),
@@ -280,9 +282,14 @@ class Engine:
             check(lib().sggan_step_forward_backward_d(self.h, C.c_void_p(a.data_ptr()), C.c_void_p(s.data_ptr()),
                                                       C.c_void_p(m.data_ptr()), C.c_void_p(self.losses.data_ptr())))
 
-    def step_backward_g(self):
+    def step_backward_g(self, part=None):
+        """part None: the whole generator backward; 0 / 1: its two halves (after part 0 the gradients from
+        grad_split_offset() on are final, see include/sggan.h)."""
         with _EngineStream(self):
-            check(lib().sggan_step_backward_g(self.h))
+            check(lib().sggan_step_backward_g(self.h) if part is None else lib().sggan_step_backward_g_part(self.h, part))
+
+    def grad_split_offset(self):
+        return int(lib().sggan_grad_split_offset(self.h))
 
     def step_adam(self, net, overlapped=False):
         """Adam + weight re-pack of one net; overlapped=True issues it on the engine's side stream (joined by the next

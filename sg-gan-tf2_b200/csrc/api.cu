@@ -139,6 +139,15 @@ int sggan_step_backward_g(sggan_handle* h) {
   FWD_ERR(h->e.step_bwd_g());
   return 0;
 }
+int sggan_step_backward_g_part(sggan_handle* h, int part) {
+  if (part != 0 && part != 1) { g_err = "part must be 0 or 1"; return SGGAN_E_INVALID; }
+  FWD_ERR(h->e.step_bwd_g(part));
+  return 0;
+}
+int64_t sggan_grad_split_offset(const sggan_handle* h) {
+  const Engine& e = h->e;
+  return e.G.T[e.G.L[e.bwd_split_layer()].ti_w].offset;
+}
 // both optimizers of a step use the same Adam time step; the counter advances when the second one has run
 static void adam_mark(Engine& e, int net) {
   e.adam_mask |= 1 << (net == SGGAN_NET_G ? 0 : 1);

@@ -914,12 +914,27 @@ int Engine::step_fwd_bwd_d(const float* real_A, const float* seg_A, const float*
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }
 
-int Engine::step_bwd_g() {
+// The layer at which a data-parallel caller may split the generator backward (sggan_step_backward_g_part): the first
+// convolution of the middle residual block.  Once the backward has passed it, the gradients of every tensor from that
+// layer's kernel to the end of the flat buffer are final (and contiguous), so their all-reduce can run underneath the
+// rest of the backward.
+int Engine::bwd_split_layer() const { return 3 + 2 * (cfg.n_blocks / 2); }
+
+// part < 0: the whole backward; part 0: loss seeds .. the split layer (inclusive); part 1: the rest.
+int Engine::step_bwd_g(int part) {
   const int B = cfg.batch, H = cfg.image_height, W = cfg.image_width;
   int r;
   const int nl = int(G.L.size());
+  const int li_split = bwd_split_layer();
   Layer& lo = G.L[nl - 1];
   static const bool fuse_gather = []() { const char* e = getenv("SGGAN_FUSE_GATHER"); return !(e && e[0] == '0'); }();
+  const int first_blk = 3, last_b = 3 + 2 * cfg.n_blocks - 1;
+  const Layer& rb = G.L[first_blk];
+  if (part == 1) {
+    if (!bwd_half_done) { err = "sggan_step_backward_g_part(1) without part 0"; return SGGAN_E_STATE; }
+    bwd_half_done = false;
+  } else {
+  bwd_half_done = false;
   FakeGradParams fg;
   memset(&fg, 0, sizeof(fg));
   fg.fake = fake; fg.dD = dD; fg.B = B; fg.H = H; fg.W = W; fg.loss = loss; fg.dst = lo.dY; fg.dmap = lo.dymap;
@@ -951,12 +966,15 @@ int Engine::step_bwd_g() {
   // output conv
   if ((r = run_wgrad(lo, G))) return r;
   if ((r = run_conv_list(lo.dgrad))) return r;
-  const int first_blk = 3, last_b = 3 + 2 * cfg.n_blocks - 1;
-  int cur = 0;  // resG ping-pong index holding the gradient w.r.t. the current block output
-  const Layer& rb = G.L[first_blk];
-  GradSrc gres = no_src();
-  GradSrc add = no_src();  // pending G_{k-1} = G_k + fold(dX of conv_a): materialised by the NEXT norm-backward reduce
-  for (int li = nl - 2; li >= 0; --li) {
+  bwd_cur = 0;
+  bwd_gres = no_src();
+  bwd_add = no_src();
+  }
+  int& cur = bwd_cur;         // resG ping-pong index holding the gradient w.r.t. the current block output
+  GradSrc& gres = bwd_gres;
+  GradSrc& add = bwd_add;     // pending G_{k-1} = G_k + fold(dX of conv_a): materialised by the NEXT norm-backward reduce
+  const int li_hi = part == 1 ? li_split - 1 : nl - 2, li_lo = part == 0 ? li_split : 0;
+  for (int li = li_hi; li >= li_lo; --li) {
     Layer& l = G.L[li];
     Layer& up = G.L[li + 1];
     const bool in_blocks = li >= first_blk && li <= last_b;
@@ -994,7 +1012,8 @@ int Engine::step_bwd_g() {
       }
     }
   }
-  join_side();
+  join_side();  // the weight gradients launched so far are final on `st`
+  if (part == 0) bwd_half_done = true;
   if (glue_err) { err = "row-stream launch failed (code " + std::to_string(glue_err) + ")"; glue_err = 0; return SGGAN_E_CUDA; }
   return cudaGetLastError() == cudaSuccess ? 0 : SGGAN_E_CUDA;
 }

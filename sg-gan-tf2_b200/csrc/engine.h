@@ -130,7 +130,12 @@ struct Engine {
   int disc_forward_2b(const float* real_img, const float* fake_img, int nimg_each);
   int disc_forward_user(const float* x, const float* mask, float* logits_out);
   int step_fwd_bwd_d(const float* real_A, const float* seg_A, const float* mask, float* losses_out);
-  int step_bwd_g();
+  int step_bwd_g(int part = -1);
+  int bwd_split_layer() const;
+  // state carried from part 0 to part 1 of a split generator backward
+  int bwd_cur = 0;
+  GradSrc bwd_gres = {}, bwd_add = {};
+  bool bwd_half_done = false;
   int step_adam(int net, bool on_side_stream = false);
 
  private:

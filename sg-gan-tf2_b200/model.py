@@ -208,13 +208,19 @@ class sggan(object):
         else:
             # data parallel: D gradients are final after phase 1 and are all-reduced on NCCL's stream while
             # the generator backward runs; G gradients follow; Adam applies 1/world_size.
+            # G's gradients go out in two buckets: the upper half of the network (final after the first half of the
+            # backward: a contiguous tail of the flat buffer) is reduced underneath the second half of the backward.
             eng.step_forward_backward_d(real_A, seg_A, mask_A)
             hd = dist.all_reduce(eng.flat(L.NET_D, 1), async_op=True)
-            eng.step_backward_g()
-            hg = dist.all_reduce(eng.flat(L.NET_G, 1), async_op=True)
+            gg, off = eng.flat(L.NET_G, 1), eng.grad_split_offset()
+            eng.step_backward_g(part=0)
+            h1 = dist.all_reduce(gg[off:], async_op=True)
+            eng.step_backward_g(part=1)
+            h2 = dist.all_reduce(gg[:off], async_op=True)
             hd.wait()                                  # long finished: it ran underneath the generator backward
-            eng.step_adam(L.NET_D, overlapped=True)    # side stream: runs while G's all-reduce is in flight
-            hg.wait()
+            eng.step_adam(L.NET_D, overlapped=True)    # side stream: runs while G's last bucket is in flight
+            h1.wait()
+            h2.wait()
             eng.step_adam(L.NET_G)                     # joins the side stream
         self._step_enqueued(eng)
         # views into buffers the NEXT step overwrites (clone to keep); float(self.gen_loss) synchronises, losses_host() is

@@ -672,6 +672,34 @@ def test_training_step_is_bit_reproducible(L, O):
             assert torch.equal(a, b)
 
 
+def test_split_generator_backward_is_the_same_backward(L, O):
+    """sggan_step_backward_g_part(0) + (1) == sggan_step_backward_g, bit for bit, and after part 0 the tail of G's flat
+    gradient buffer (from sggan_grad_split_offset on) already holds its final values -- what lets a data-parallel caller
+    all-reduce that bucket underneath part 1 (model.py)."""
+    B, H, W, nb = 2, 128, 256, 5
+    real_A, seg_A, mask, _ = O.synthetic_batch(B, H, W, 34, seed=31)
+    dev = [t.cuda() for t in (real_A, seg_A, mask)]
+    eng, _, _ = _engine(L, O, B, H, W, nb)
+    eng.step_forward_backward_d(*dev)
+    eng.step_backward_g()
+    torch.cuda.synchronize()
+    whole = eng.flat(L.NET_G, 1).clone()
+    eng2, _, _ = _engine(L, O, B, H, W, nb)
+    off = eng2.grad_split_offset()
+    assert 0 < off < whole.numel() and off == eng.grad_split_offset()
+    eng2.step_forward_backward_d(*dev)
+    eng2.step_backward_g(part=0)
+    torch.cuda.synchronize()
+    g = eng2.flat(L.NET_G, 1)
+    assert torch.equal(g[off:], whole[off:])            # the upper bucket is final
+    assert float(g[:off].abs().max()) == 0.0             # nothing of the lower bucket has been touched yet
+    eng2.step_backward_g(part=1)
+    torch.cuda.synchronize()
+    assert torch.equal(g, whole)
+    with pytest.raises(L.SgganError):
+        eng2.step_backward_g(part=1)                     # part 1 without part 0
+
+
 def test_graph_replay_matches_eager_launches(L, O):
     """The step captured as one CUDA graph (sggan_graph_capture / sggan_graph_launch) does what the 250 eager launches do:
     same losses and same weights, and Adam's time step keeps advancing from replay to replay (it is read from a
