@@ -219,6 +219,7 @@ class sggan(object):
             h2 = dist.all_reduce(gg[:off], async_op=True)
             hd.wait()                                  # long finished: it ran underneath the generator backward
             eng.step_adam(L.NET_D, overlapped=True)    # side stream: runs while G's last bucket is in flight
+            # (issuing D's Adam between the two parts, underneath part 1, hung the two-GPU NCCL run: left where it was)
             h1.wait()
             h2.wait()
             eng.step_adam(L.NET_G)                     # joins the side stream
