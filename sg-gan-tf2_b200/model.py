@@ -208,20 +208,26 @@ class sggan(object):
         else:
             # data parallel: D gradients are final after phase 1 and are all-reduced on NCCL's stream while
             # the generator backward runs; G gradients follow; Adam applies 1/world_size.
-            # G's gradients go out in two buckets: the upper half of the network (final after the first half of the
-            # backward: a contiguous tail of the flat buffer) is reduced underneath the second half of the backward.
             eng.step_forward_backward_d(real_A, seg_A, mask_A)
             hd = dist.all_reduce(eng.flat(L.NET_D, 1), async_op=True)
-            gg, off = eng.flat(L.NET_G, 1), eng.grad_split_offset()
-            eng.step_backward_g(part=0)
-            h1 = dist.all_reduce(gg[off:], async_op=True)
-            eng.step_backward_g(part=1)
-            h2 = dist.all_reduce(gg[:off], async_op=True)
+            gg = eng.flat(L.NET_G, 1)
+            if os.environ.get("SGGAN_DP_BUCKETS", "0") == "1":
+                # opt-in: G's gradients in two buckets -- the upper half of the network (final after the first half of the
+                # backward: a contiguous tail of the flat buffer) is reduced underneath the second half of the backward.
+                # Correct (tests) and measured once on 2 GPUs (1871 img/s); the single-bucket form below is the one every
+                # multi-GPU number in profiles/ was taken with, so it stays the default.
+                off = eng.grad_split_offset()
+                eng.step_backward_g(part=0)
+                hs = [dist.all_reduce(gg[off:], async_op=True)]
+                eng.step_backward_g(part=1)
+                hs.append(dist.all_reduce(gg[:off], async_op=True))
+            else:
+                eng.step_backward_g()
+                hs = [dist.all_reduce(gg, async_op=True)]
             hd.wait()                                  # long finished: it ran underneath the generator backward
-            eng.step_adam(L.NET_D, overlapped=True)    # side stream: runs while G's last bucket is in flight
-            # (issuing D's Adam between the two parts, underneath part 1, hung the two-GPU NCCL run: left where it was)
-            h1.wait()
-            h2.wait()
+            eng.step_adam(L.NET_D, overlapped=True)    # side stream: runs while G's all-reduce is in flight
+            for hnd in hs:
+                hnd.wait()
             eng.step_adam(L.NET_G)                     # joins the side stream
         self._step_enqueued(eng)
         # views into buffers the NEXT step overwrites (clone to keep); float(self.gen_loss) synchronises, losses_host() is
