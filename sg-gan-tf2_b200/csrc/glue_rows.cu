@@ -324,7 +324,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_stream_kernel(const Row
   const int b = blockIdx.y;
   const int ba = b < p.nb_act ? b : b - p.act_wrap;
   const int cpr = (p.W + p.CW - 1) / p.CW;  // chunks per row
-  const int nchunks = p.H * cpr;
   // each block owns a contiguous range of chunks, so consecutive chunks mostly share their image row
   const int cbeg = chunk_boundary(blockIdx.x, gridDim.x, p.H, cpr, p.mrows, p.wm);
   const int cend = chunk_boundary(blockIdx.x + 1, gridDim.x, p.H, cpr, p.mrows, p.wm);
@@ -735,7 +734,6 @@ __global__ void __launch_bounds__(kStreamThreads, 1) row_fused_bwd_kernel(const 
   const int b = blockIdx.y;
   const int ba = b < p.nb_act ? b : b - p.act_wrap;
   const int cpr = (p.W + p.CW - 1) / p.CW;
-  const int nchunks = p.H * cpr;
   const int cbeg = chunk_boundary(blockIdx.x, gridDim.x, p.H, cpr, p.mrows, p.wm);
   const int cend = chunk_boundary(blockIdx.x + 1, gridDim.x, p.H, cpr, p.mrows, p.wm);
   const int n = max(0, cend - cbeg);          // chunks of this block
