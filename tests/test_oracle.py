@@ -214,3 +214,24 @@ def test_mask_zoom_restatement_equals_scipy_on_shipped_label_maps(O, ref_fix):
                 full = np.zeros(Wy.shape[1])
                 full[y0[o]:y0[o] + wh] = wy[o]
                 assert np.abs(full - Wy[o]).max() < 1e-17
+
+
+def test_stride1_transposed_conv_is_a_flipped_conv(O):
+    """generator_unet's decoder (module.py:171-203) is built from Conv2DTranspose(3x3, stride 1, 'same').  Independent
+    formulation: that is Conv2D with w'[kh, kw, ci, co] = w[2-kh, 2-kw, co, ci] -- the identity module.GeneratorUnet relies on
+    to run the decoder on the convolution kernels -- and the whole oracle network keeps the input resolution."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 7, 9, 5, generator=g, dtype=torch.float64)
+    k = torch.rand(3, 3, 4, 5, generator=g, dtype=torch.float64) - 0.5          # (kh, kw, Cout, Cin)
+    b = torch.rand(4, generator=g, dtype=torch.float64)
+    ref = O.conv2d_transpose(x, k, b, 1)
+    alt = O.conv2d(x, k.flip(0, 1).permute(0, 1, 3, 2).contiguous(), b, 1, "SAME")
+    assert ref.shape == (2, 7, 9, 4) and (ref - alt).abs().max() < 1e-12
+    w = O.init_weights(O.generator_unet_spec(gf_dim=8), 5, dtype=torch.float64, randomize_affine=True)
+    assert len(w) == 62
+    img = torch.rand(1, 10, 12, 3, generator=g, dtype=torch.float64)
+    y = O.generator_unet(img, w)
+    assert y.shape == img.shape and float(y.abs().max()) <= 1.0
+    masks = [(torch.rand(1, 10, 12, 64, generator=g) >= 0.5).double() for _ in range(3)]
+    yt = O.generator_unet(img, w, training=True, drop_masks=masks)
+    assert (yt - y).abs().max() > 1e-6     # dropout only acts in training mode
